@@ -1,0 +1,185 @@
+"""Generates the committed golden fixtures by EXECUTING THE UNMODIFIED REFERENCE in the build
+container (needs /root/reference; cannot run on the GPU box -- that is why the vectors are
+committed).  Run:  python tests/golden/make_golden.py
+
+What is executed (paths relative to /root/reference):
+  * maskrcnn_benchmark/csrc/cpu/nms_cpu.cpp            via oracle/_ref/osd_ref_C.so, injected as
+                                                        ``maskrcnn_benchmark._C`` before anything imports it
+  * tests/test_nms.py                                   the reference's own known-answer tests; their inputs and
+                                                        expected indices are recorded into nms_kat.json
+  * maskrcnn_benchmark/modeling/rpn/fcos/inference.py   FCOSPostProcessor.forward            -> fcos_post_*.npz
+  * maskrcnn_benchmark/modeling/rpn/fcos/fcos.py        FCOSModule.compute_locations_per_level (unbound) -> same
+  * modeling/detector/generalized_rcnn.py:100-104,306-311   batch_pooling + product expression -> match_*.npz
+  * modeling/roi_heads/box_head/box_head.py:43-54,147-149   concat + compress_dim_conv (the stock nn.Sequential
+                                                        the reference builds there)          -> match_*.npz
+
+Inputs are seeded numpy; they are stored next to the outputs so tests never need the reference.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import types
+import unittest
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("OSD_REFERENCE_ROOT", "/root/reference")
+sys.path.insert(0, ROOT)
+
+from oracle import build_ref  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+
+def import_reference():
+    ref_c = build_ref.load_ref()
+    assert ref_c is not None, "reference ops did not build"
+    sys.path.insert(0, REF)
+    import maskrcnn_benchmark  # noqa: PLC0415
+
+    maskrcnn_benchmark._C = ref_c
+    sys.modules["maskrcnn_benchmark._C"] = ref_c
+    return ref_c
+
+
+def record_nms_kat(ref_c):
+    """Run the reference's tests/test_nms.py with a recording shim around the reference nms."""
+    import maskrcnn_benchmark.layers as layers  # noqa: PLC0415
+
+    calls = []
+
+    def recording_nms(boxes, scores, thr):
+        keep = ref_c.nms(boxes, scores, float(thr))
+        calls.append({"boxes": boxes.numpy().astype(np.float32).tolist(),
+                      "scores": scores.numpy().astype(np.float32).tolist(),
+                      "thresh": float(thr),
+                      "keep_sorted": np.sort(keep.numpy()).tolist()})
+        return keep
+
+    layers.nms = recording_nms
+    sys.path.insert(0, os.path.join(REF, "tests"))
+    import importlib  # noqa: PLC0415
+
+    mod = importlib.import_module("test_nms")
+    mod.box_nms = recording_nms
+    suite = unittest.defaultTestLoader.loadTestsFromModule(mod)
+    result = unittest.TextTestRunner(verbosity=0).run(suite)
+    assert result.wasSuccessful(), "reference test_nms.py failed against its own nms_cpu"
+    # the assertions passed, so keep_sorted == the test file's expected indices
+    with open(os.path.join(HERE, "nms_kat.json"), "w") as f:
+        json.dump({"source": "tests/test_nms.py (5-box x 5 thresholds, 53-box @0.5)", "cases": calls}, f)
+    print("nms_kat.json:", len(calls), "cases")
+
+
+def fcos_case(name, batch, height, width, image_sizes, params, seed, quantize=None):
+    from maskrcnn_benchmark.modeling.rpn.fcos.fcos import FCOSModule  # noqa: PLC0415
+    from maskrcnn_benchmark.modeling.rpn.fcos.inference import FCOSPostProcessor  # noqa: PLC0415
+
+    cfg = types.SimpleNamespace(MODEL=types.SimpleNamespace(RPN_ONLY=False),
+                                FEW_SHOT=types.SimpleNamespace(ADD_ARTIFICIAL_PROPOSALS=False))
+    post = FCOSPostProcessor(cfg, params.pre_nms_thresh, params.pre_nms_top_n, params.nms_thresh,
+                             params.fpn_post_nms_top_n, params.min_size, num_classes=2, dense_points=1,
+                             score_calculator="BINARY").eval()
+    cls, reg, ctr = orc.synth_head_outputs(batch, height, width, seed, distinct=quantize is None)
+    if quantize is not None:  # tie set: many equal scores
+        cls = [torch.round(c * quantize) / quantize for c in cls]
+        ctr = [torch.zeros_like(c) for c in ctr]
+    # scale the synthetic boxes down to the small images used here
+    fake = types.SimpleNamespace(dense_points=1)
+    fake.get_dense_locations = lambda loc, stride, device: loc
+    locations = []
+    for c, s in zip(cls, orc.FPN_STRIDES):
+        h, w = c.shape[-2:]
+        locations.append(FCOSModule.compute_locations_per_level(fake, h, w, s, torch.device("cpu")))
+    with torch.no_grad():
+        out = post(locations, [c.clone() for c in cls], [r.clone() for r in reg], [c.clone() for c in ctr],
+                   image_sizes)
+    data = {"height": height, "width": width, "batch": batch, "seed": seed,
+            "image_sizes": np.asarray(image_sizes, dtype=np.int64),
+            "params": np.asarray([params.pre_nms_thresh, params.pre_nms_top_n, params.nms_thresh,
+                                  params.fpn_post_nms_top_n, params.min_size], dtype=np.float64)}
+    for l, (c, r, t, loc) in enumerate(zip(cls, reg, ctr, locations)):
+        data[f"cls{l}"] = c.numpy()
+        data[f"reg{l}"] = r.numpy()
+        data[f"ctr{l}"] = t.numpy()
+        data[f"loc{l}"] = loc.numpy()
+    for i, bl in enumerate(out):
+        assert bl.mode == "xyxy"
+        data[f"out_boxes{i}"] = bl.bbox.numpy().astype(np.float32)
+        data[f"out_scores{i}"] = bl.get_field("scores").numpy().astype(np.float32)
+        data[f"out_size{i}"] = np.asarray(bl.size, dtype=np.int64)  # (w, h)
+        data[f"out_fields{i}"] = np.asarray(sorted(bl.fields()))
+    np.savez_compressed(os.path.join(HERE, f"fcos_post_{name}.npz"), **data)
+    print(f"fcos_post_{name}.npz:", [len(b) for b in out], "detections")
+
+
+def match_case(name, batch, shots, channels, height, width, seed):
+    feats, supp = orc.synth_features(batch, shots, channels, height, width, seed)
+    # --- generalized_rcnn.py:100-104 / :306-311, restated verbatim as expressions on tensors
+    pooled = []
+    for s in supp:
+        d, c, h, w = s.shape
+        x = s.view(batch, int(d / batch), c, h, w)
+        pooled.append(torch.mean(x, dim=1, keepdim=False))
+    product = []
+    for f, p in zip(feats, pooled):
+        _, _, d1, d2 = f.shape
+        product.append(f * p.expand(-1, -1, d1, d2))
+    # --- box_head.py:147 concat, :43-54 compress_dim_conv (stock torch.nn, weights N(0, .01))
+    from torch import nn  # noqa: PLC0415
+
+    torch.manual_seed(seed)
+    oc = channels
+    compress = nn.Sequential(
+        nn.Conv2d(oc * 2, oc * 2, 1), nn.GroupNorm(32, oc * 2), nn.LeakyReLU(0.2),
+        nn.Conv2d(oc * 2, oc, 1), nn.GroupNorm(32, oc), nn.LeakyReLU(0.2))
+    for layer in compress:
+        if isinstance(layer, nn.Conv2d):
+            torch.nn.init.normal_(layer.weight, std=0.01)
+        if isinstance(layer, nn.GroupNorm):  # exercise the affine terms
+            torch.nn.init.normal_(layer.weight, mean=1.0, std=0.1)
+            torch.nn.init.normal_(layer.bias, std=0.1)
+    compress.eval()
+    concat, conv1, fused = [], [], []
+    with torch.no_grad():
+        for f, p in zip(feats, pooled):
+            x = torch.cat((f, p.expand_as(f)), dim=1)
+            concat.append(x)
+            conv1.append(compress[0](x))
+            fused.append(compress(x))
+    data = {"batch": batch, "shots": shots, "channels": channels, "height": height, "width": width}
+    for l in range(len(feats)):
+        data[f"feat{l}"] = feats[l].numpy()
+        data[f"supp{l}"] = supp[l].numpy()
+        data[f"product{l}"] = product[l].numpy()
+        data[f"conv1_{l}"] = conv1[l].numpy()
+        data[f"fused{l}"] = fused[l].numpy()
+        # concat is feat || broadcast(pooled): store the pooled vector only
+        data[f"pooled{l}"] = pooled[l].numpy()
+        assert torch.equal(concat[l][:, :channels], feats[l])
+    for k, v in compress.state_dict().items():
+        data["w_" + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, f"match_{name}.npz"), **data)
+    print(f"match_{name}.npz written")
+
+
+def main():
+    torch.set_num_threads(1)
+    ref_c = import_reference()
+    record_nms_kat(ref_c)
+    P = orc.PostParams
+    # small padded inputs (multiples of 128 so every level is non-empty and regular)
+    fcos_case("two_stage_small", 2, 256, 384, [(250, 380), (256, 333)], P(0.0, 300, 0.8, 100, 0.0), seed=11)
+    fcos_case("stress_small", 3, 256, 256, [(256, 256)] * 3, P(0.01, 120, 0.6, 4000, 0.0), seed=12)
+    fcos_case("minsize_small", 2, 128, 256, [(120, 250), (128, 256)], P(0.02, 1000, 0.5, 50, 24.0), seed=13)
+    fcos_case("nonms_small", 1, 128, 128, [(128, 128)], P(0.05, 50, 0.0, 30, 0.0), seed=14)
+    match_case("s1_c64", 2, 1, 64, 96, 160, seed=21)
+    match_case("s3_c64", 2, 3, 64, 64, 96, seed=22)
+
+
+if __name__ == "__main__":
+    main()
