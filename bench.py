@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- matching + FCOS post-processing + NMS throughput (episodes/s) on N B200s of one box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A step = one pass of the hot path over one batch of 16 synthetic episodes per GPU (BASELINE.json configs[1]:
+siamese FCOS R-50-FPN geometry, 800x1333 target padded to 800x1344, C=256, 1 shot, two-stage post-processing
+parameters 0 / 6000 / 0.8 / 2000): the product matching of P3-P7 (one launch), then score -> per-level top-k ->
+decode/clip -> batched NMS -> post-NMS top-n.  The FCOS head between the two stages is outside the path: head
+outputs are synthetic and resident.  With N > 1 every rank owns 16 episodes (weak scaling) and
+each step ends with the all-gather of the [16, 2000, 6] detections over NCCL.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same metric through
+EpisodePipeline.run_host with pinned HOST buffers (H2D of all inputs + D2H of the detections inside the timed
+region), `roofline` describes the dominant streaming kernel, `cpu_baseline` the reference's CPU path timed on
+this box's host cores on a bounded sample.  `--impl reference` times that CPU path alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "matching+NMS episodes/s"
+UNIT = "episodes/s"
+BATCH = 16
+HEIGHT, WIDTH = 800, 1344          # 800x1333 zero-padded to a multiple of 32 (structures/image_list.py:56-63)
+IMAGE_SIZE = (800, 1333)
+CHANNELS, SHOTS = 256, 1
+PARAMS = dict(pre_nms_thresh=0.0, pre_nms_top_n=6000, nms_thresh=0.8, fpn_post_nms_top_n=2000, min_size=0.0)
+WORKLOAD = ("configs[1]: siamese FCOS R-50-FPN geometry, 16 episodes/GPU, 800x1333 (padded 800x1344), C=256, "
+            "1 shot, fp32 product matching + score/top-k(6000)/decode/NMS(0.8)/top-2000")
+
+
+def config_dict(n_gpus):
+    return {"workload": WORKLOAD, "episodes_per_gpu": BATCH, "global_episodes": BATCH * n_gpus,
+            "levels": "P3-P7 100x168,50x84,25x42,13x21,7x11", "match_mode": "product", "match_dtype": "f32",
+            "post_params": PARAMS, "parallelism": f"episode-dp{n_gpus}",
+            "cache": "inputs larger than L2 (367 MB features in + 367 MB out per step vs 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# synthetic inputs: features ~ N(0,1); cls ~ N(-4, 2^2); ctr ~ N(0,1); reg = exp(N(log 4s, .5^2))
+# ------------------------------------------------------------------------------------------------------
+def fill_inputs(pipe, seed):
+    import math
+
+    import torch
+
+    g = torch.Generator(device=pipe.device).manual_seed(seed)
+    for t in pipe.features + pipe.supp:
+        t.normal_(generator=g)
+    for t in pipe.cls:
+        t.normal_(mean=-4.0, std=2.0, generator=g)
+    for t in pipe.ctr:
+        t.normal_(generator=g)
+    for t, s in zip(pipe.reg, pipe.strides):
+        t.normal_(mean=math.log(4.0 * s), std=0.5, generator=g).exp_()
+
+
+# ------------------------------------------------------------------------------------------------------
+# the reference's CPU path on a bounded sample: torch.mul matching (generalized_rcnn.py:306-311) + the
+# post-processing restated with the same ATen ops (oracle) + the reference's own nms_cpu when it was compiled
+# ------------------------------------------------------------------------------------------------------
+class CpuReference:
+    def __init__(self, episodes=1, seed=7):
+        import torch
+
+        from oracle import build_ref
+        from oracle import oracle as orc
+
+        self.orc, self.torch = orc, torch
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.cores = torch.get_num_threads()
+        ref = None
+        try:
+            ref = build_ref.load_ref()
+        except Exception:  # noqa: BLE001
+            ref = None
+        self.kind = "reference" if ref is not None else "port"
+        if ref is not None:
+            self.nms_fn = lambda b, s, thr: ref.nms(torch.from_numpy(b), torch.from_numpy(s), float(thr)).numpy()
+        else:
+            self.nms_fn = None
+        self.episodes = episodes
+        self.feats, self.supp = orc.synth_features(episodes, SHOTS, CHANNELS, HEIGHT, WIDTH, seed)
+        self.cls, self.reg, self.ctr = orc.synth_head_outputs(episodes, HEIGHT, WIDTH, seed, distinct=False)
+        self.params = orc.PostParams(**PARAMS)
+        self.sizes = [IMAGE_SIZE] * episodes
+
+    def step(self):
+        orc = self.orc
+        t0 = time.perf_counter()
+        out = orc.match_product(self.feats, self.supp, self.episodes)
+        t1 = time.perf_counter()
+        res = orc.fcos_postprocess(self.cls, self.reg, self.ctr, orc.FPN_STRIDES, self.sizes, self.params,
+                                   nms_fn=self.nms_fn)
+        t2 = time.perf_counter()
+        assert len(out) == 5 and len(res) == self.episodes
+        return t1 - t0, t2 - t1
+
+    def sample_text(self):
+        nms = ("the reference's own nms_cpu (csrc/cpu/nms_cpu.cpp compiled unmodified, oracle/_ref)"
+               if self.kind == "reference" else "the C port of nms_cpu (oracle/nms_oracle.c)")
+        return (f"{self.episodes} episode(s) of the same workload per step: torch.mul matching on {self.cores} threads + "
+                f"FCOS post-processing restated with the reference's ATen ops + {nms}; nms_cpu is single-threaded by "
+                f"construction (no OpenMP)")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ref = CpuReference(episodes=1)
+    for _ in range(max(args.warmup, 1)):
+        ref.step()
+    times = []
+    budget_s = 150.0   # keep the whole run within a few minutes whatever K is; `steps` reports what was timed
+    for _ in range(args.steps):
+        a, b = ref.step()
+        times.append(a + b)
+        if sum(times) > budget_s:
+            break
+    args.steps = len(times)
+    total = sum(times)
+    value = ref.episodes * args.steps / total
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+                             "sample": ref.sample_text()},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks during the timed region (NVML polling thread)
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.ok = False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def stop(self):
+        if self.ok:
+            self._stop.set()
+            self.t.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read+write of the match kernel per launch from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "match_kernel_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:  # noqa: BLE001
+        return None
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from oneshotdet_b200 import ops
+    from oneshotdet_b200.distributed import gather_detections
+    from oneshotdet_b200.pipeline import EpisodePipeline, PostParams
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    warmup = max(args.warmup, 3)
+    steps = args.steps
+
+    pipe = EpisodePipeline(BATCH, HEIGHT, WIDTH, [IMAGE_SIZE] * BATCH, channels=CHANNELS, shots=SHOTS,
+                           params=PostParams(**PARAMS), match_mode="product", device=dev)
+    fill_inputs(pipe, seed=2000 + rank)
+    ep_off = rank * BATCH
+
+    def step():
+        pipe.match()
+        e_mid.record()
+        res = pipe.post()
+        if world > 1:
+            d, c = pipe.pack_detections(res, ep_off)
+            gather_detections(d, c)
+        return res
+
+    e_mid = torch.cuda.Event(enable_timing=True)
+    for _ in range(warmup):
+        res = step()
+    torch.cuda.synchronize()
+    kept = res.kept_before_cut().cpu().tolist()
+    counts = res.count.cpu().tolist()
+
+    # ---- timed region: exactly `steps` steps, CUDA events on the launching stream, barrier + sync both sides
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ops.reset_launch_count()
+    sampler.start()
+    t_host0 = time.perf_counter()
+    for i in range(steps):
+        ev[i][0].record()
+        pipe.match()
+        ev[i][1].record()
+        r = pipe.post()
+        if world > 1:
+            d, c = pipe.pack_detections(r, ep_off)
+            gather_detections(d, c)
+        ev[i][2].record()
+    torch.cuda.synchronize()
+    t_host1 = time.perf_counter()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    launches = ops.launch_count()
+    total_ms = ev[0][0].elapsed_time(ev[-1][2])
+    match_ms = [ev[i][0].elapsed_time(ev[i][1]) for i in range(steps)]
+    post_ms = [ev[i][1].elapsed_time(ev[i][2]) for i in range(steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = BATCH * n_gpus * steps / (total_ms_max * 1e-3)
+
+    # ---- roofline of the dominant streaming kernel (match_nchw_kernel: one launch per step)
+    locs = sum(h * w for h, w in pipe.shapes)
+    match_bytes = 2 * 4 * CHANNELS * locs * BATCH                     # fp32 in + out, SURVEY section 8(d)
+    match_avg_ms = statistics.mean(match_ms)
+    peak, peak_src = measured_peak_hbm()
+    achieved = match_bytes / (match_avg_ms * 1e-3) / 1e9
+    roofline = {"kernel": "match_nchw_kernel<float, product>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
+                "algorithmic_bytes_per_launch": match_bytes, "avg_launch_ms": match_avg_ms, "peak_source": peak_src,
+                "share_of_step": match_avg_ms / (total_ms / steps)}
+    post_read = 6 * 4 * locs * BATCH
+    stages = {"match_ms": match_avg_ms, "post_ms": statistics.mean(post_ms),
+              "post_algorithmic_read_bytes": post_read,
+              "host_ms_per_step": 1e3 * (t_host1 - t_host0) / steps}
+
+    # ---- end-to-end through the public API with pinned host buffers
+    e2e = None
+    if rank == 0 or world > 1:
+        host_in = pipe.make_host_inputs(pinned=True)
+        for h, d in zip(host_in, pipe.input_tensors()):
+            h.copy_(d)
+        e2e_steps = max(3, min(steps, 10))
+        pipe.run_host(host_in)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            out = pipe.run_host(host_in)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": BATCH * n_gpus * e2e_steps / float(tt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes, "steps": e2e_steps,
+               "api": "EpisodePipeline.run_host (pinned host inputs -> H2D -> match + post-process -> D2H detections)",
+               "check_count0": int(out[2][0])}
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref = CpuReference(episodes=1)
+        ref.step()
+        ts = [sum(ref.step()) for _ in range(4)]
+        cpu = {"value": ref.episodes / statistics.median(ts), "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+               "sample": ref.sample_text() + f"; median of 4 steps, {statistics.median(ts):.3f} s/episode"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(n_gpus),
+                "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(launches), "clocks": clocks,
+                "check": {"detections_per_episode": counts[:4], "kept_before_cut": kept[:4]}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

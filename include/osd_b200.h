@@ -1,0 +1,171 @@
+/*
+ * osd_b200.h -- C ABI of the B200-native OneshotDet hot path (libosd_b200.so).
+ *
+ * Plain C: device/host pointers, sizes and a CUDA stream handle; no torch types.  Every entry
+ * point enqueues work on `stream` (a cudaStream_t passed as void*), never synchronises the device,
+ * never allocates device memory (the caller provides the workspace that the matching *_plan call
+ * sized) and returns 0 on success or a negative osd_status; osd_last_error() returns the message of
+ * the calling thread's last failure.  Floating-point inputs are fp32 unless a dtype field says
+ * otherwise.  All device pointers must belong to the device that is current on the calling thread.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference
+ * repository root, RyanXLi/OneshotDet).
+ */
+#ifndef OSD_B200_H_
+#define OSD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSD_MAX_LEVELS 8
+
+typedef enum {
+  OSD_OK = 0,
+  OSD_ERR_INVALID = -1,    /* bad argument (shape, alignment, null pointer, unsupported mode) */
+  OSD_ERR_WORKSPACE = -2,  /* workspace too small for the plan */
+  OSD_ERR_CUDA = -3,       /* a CUDA runtime call failed; see osd_last_error() */
+  OSD_ERR_UNSUPPORTED = -4 /* device is not sm_100 */
+} osd_status;
+
+/* Library version (major*10000 + minor*100 + patch). */
+int osd_version(void);
+/* Message for the last error raised on this thread ("" if none). */
+const char* osd_last_error(void);
+/* 0 if the current device can run the sm_100a kernels, OSD_ERR_UNSUPPORTED otherwise. */
+int osd_check_device(void);
+/* Number of kernels this library has launched on this thread since the last reset (bench accounting). */
+int64_t osd_launch_count(void);
+void osd_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched NMS.
+ *
+ * Replaces  maskrcnn_benchmark/csrc/nms.h:10-28  (`at::Tensor nms(dets, scores, threshold)`, the
+ *           pybind export `_C.nms` of csrc/vision.cpp:8) with its CPU and CUDA kernels
+ *           csrc/cpu/nms_cpu.cpp:5-75 and csrc/cuda/nms.cu:23-131, as called through
+ *           maskrcnn_benchmark/structures/boxlist_ops.py:10-34 (boxlist_nms).
+ *
+ * E independent problems ("segments" = episodes) are solved in one call: segment e owns rows
+ * [seg_offsets[e], seg_offsets[e+1]) of boxes/scores.  Semantics per segment are exactly
+ * nms_cpu_kernel's: visiting order = score descending (ties: lower index first), legacy +1 box
+ * widths, fp32 IoU = inter / (area_i + area_j - inter) with IEEE rounding of every operation,
+ * suppress when IoU >= threshold (strict = 0, nms_cpu.cpp:60) or IoU > threshold (strict = 1,
+ * nms.cu:60).  Kept rows are written as ascending GLOBAL row indices (int64) to
+ * keep_out[seg_offsets[e] .. seg_offsets[e] + keep_counts[e]).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  size_t workspace_bytes; /* device scratch the call needs */
+  int32_t padded_len;     /* per-segment row capacity (max_seg_len rounded up to 64) */
+  int32_t mask_words;     /* 64-bit words per bitmask row */
+} osd_nms_plan;
+
+int osd_batched_nms_plan(int64_t num_segments, int64_t max_seg_len, osd_nms_plan* plan);
+
+int osd_batched_nms(const float* boxes,          /* device [N,4] xyxy */
+                    const float* scores,         /* device [N] */
+                    const int64_t* seg_offsets,  /* device [E+1], ascending, seg_offsets[0] may be > 0 */
+                    int64_t num_segments,        /* E */
+                    int64_t max_seg_len,         /* host-side upper bound of any segment length */
+                    float threshold, int strict,
+                    void* workspace, size_t workspace_bytes,
+                    int64_t* keep_out,           /* device, same extent as scores */
+                    int32_t* keep_counts,        /* device [E] */
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * FCOS post-processing: score, per-level pre-NMS top-k, ltrb decode, clip, size filter, per-episode
+ * NMS, post-NMS top-n -- one call for all levels and all episodes.
+ *
+ * Replaces  maskrcnn_benchmark/modeling/rpn/fcos/inference.py:251-281 (FCOSPostProcessor.forward at
+ *           eval), i.e. :46-137 (forward_for_single_feature_map), :289-323 (select_over_all_levels),
+ *           the location grid of modeling/rpn/fcos/fcos.py:220-234, BoxList.clip_to_image
+ *           (structures/bounding_box.py:214-224) and remove_small_boxes (structures/boxlist_ops.py:202-216).
+ *
+ * Inputs per level l (NCHW-contiguous fp32, B episodes): cls[l] [B,1,H,W] logits, reg[l] [B,4,H,W]
+ * (already exp'd ltrb distances, fcos.py:95), ctr[l] [B,1,H,W] logits.
+ * score = sigmoid(cls) * sigmoid(ctr); a location is a candidate iff sigmoid(cls) > pre_nms_thresh;
+ * per (episode, level) the pre_nms_top_n best scores survive; boxes are
+ * (x - l, y - t, x + r, y + b) with (x, y) = (j*stride + stride/2, i*stride + stride/2), clipped to
+ * [0, w-1] x [0, h-1] of the episode's image size, dropped unless both sides (+1) >= min_size.
+ * Candidates of an episode are ordered level-major, location-ascending.  Then NMS (nms_thresh <= 0:
+ * none) and, if more than post_nms_top_n > 0 boxes survive, the post_nms_top_n best by score in
+ * descending order, else all survivors in ascending candidate order.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t num_levels;
+  int32_t batch;                   /* B episodes */
+  int32_t height[OSD_MAX_LEVELS];  /* H_l */
+  int32_t width[OSD_MAX_LEVELS];   /* W_l */
+  int32_t stride[OSD_MAX_LEVELS];
+  float pre_nms_thresh;
+  int32_t pre_nms_top_n;
+  float nms_thresh;
+  int32_t post_nms_top_n;          /* fpn_post_nms_top_n; <= 0: unlimited */
+  float min_size;
+  int32_t strict;                  /* 0: IoU >= thr suppresses (nms_cpu), 1: IoU > thr (nms.cu) */
+  int32_t early_exit;              /* 1: stop an episode's NMS once post_nms_top_n + 1 boxes are kept
+                                      (result identical; only meaningful when post_nms_top_n > 0) */
+} osd_fcos_config;
+
+typedef struct {
+  size_t workspace_bytes;
+  int32_t cand_capacity;   /* CAP: candidate slots per episode = sum_l min(H_l*W_l, pre_nms_top_n) */
+  int32_t out_capacity;    /* K: rows per episode in the outputs */
+  int32_t level_slot[OSD_MAX_LEVELS]; /* first candidate slot of each level inside an episode */
+  /* byte offsets into the workspace of the intermediate results (for inspection / tests) */
+  size_t off_cand_boxes;   /* float  [B, CAP, 4]  slotted per level */
+  size_t off_cand_scores;  /* float  [B, CAP] */
+  size_t off_cand_loc;     /* int32  [B, CAP]     location index inside the level */
+  size_t off_level_count;  /* int32  [B, num_levels] candidates per (episode, level) */
+  size_t off_kept_count;   /* int32  [B]          boxes kept by NMS before the post-NMS cut (>= post_nms_top_n + 1 means "more") */
+} osd_fcos_plan;
+
+int osd_fcos_postprocess_plan(const osd_fcos_config* cfg, osd_fcos_plan* plan);
+
+int osd_fcos_postprocess(const osd_fcos_config* cfg,
+                         const float* const* cls,   /* host array of num_levels device pointers */
+                         const float* const* reg,
+                         const float* const* ctr,
+                         const int32_t* image_hw,   /* device int32 [B,2]: (h, w) per episode */
+                         void* workspace, size_t workspace_bytes,
+                         float* out_boxes,          /* device [B, K, 4] */
+                         float* out_scores,         /* device [B, K] */
+                         int32_t* out_index,        /* device [B, K] compact candidate index of each output row */
+                         int32_t* out_count,        /* device [B] */
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Support -> target feature matching on the FPN levels.
+ *
+ * Replaces  maskrcnn_benchmark/modeling/detector/generalized_rcnn.py:100-104 (batch_pooling, K-shot
+ *           mean) and :306-311 (the inline product loop), and offers the concat form of
+ *           modeling/roi_heads/box_head/box_head.py:147 (:144 reversed) on [B,C,H,W] maps.
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum { OSD_MATCH_PRODUCT = 0, OSD_MATCH_CONCAT = 1, OSD_MATCH_CONCAT_REVERSED = 2 } osd_match_mode;
+typedef enum { OSD_LAYOUT_NCHW = 0, OSD_LAYOUT_NHWC = 1 } osd_layout;
+typedef enum { OSD_DTYPE_F32 = 0, OSD_DTYPE_BF16 = 1 } osd_dtype;
+
+typedef struct {
+  int32_t num_levels;
+  int32_t batch;     /* B */
+  int32_t shots;     /* S: supp[l] holds B*S embeddings, episode-major, shot-minor */
+  int32_t channels;  /* C */
+  int32_t mode;      /* osd_match_mode */
+  int32_t layout;    /* osd_layout of feat/out (support vectors are [B*S, C] either way) */
+  int32_t dtype;     /* osd_dtype of feat/out; supp has the same dtype */
+  int32_t hw[OSD_MAX_LEVELS];         /* H_l * W_l */
+  const void* feat[OSD_MAX_LEVELS];   /* device [B,C,H,W] (or [B,H,W,C]) */
+  const void* supp[OSD_MAX_LEVELS];   /* device [B*S, C] */
+  void* out[OSD_MAX_LEVELS];          /* device [B,C,H,W]; concat modes: [B,2C,H,W] */
+} osd_match_desc;
+
+int osd_match_forward(const osd_match_desc* desc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSD_B200_H_ */

@@ -1,0 +1,132 @@
+"""ctypes binding of libosd_b200.so (include/osd_b200.h).  No fallback: if the library is missing or
+the device is not sm_100, every operator raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+OSD_MAX_LEVELS = 8
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libosd_b200.so")
+
+c_f32p = ctypes.c_void_p  # device pointers travel as integers
+c_void_p = ctypes.c_void_p
+
+
+class NmsPlan(ctypes.Structure):
+    _fields_ = [("workspace_bytes", ctypes.c_size_t), ("padded_len", ctypes.c_int32), ("mask_words", ctypes.c_int32)]
+
+
+class FcosConfig(ctypes.Structure):
+    _fields_ = [("num_levels", ctypes.c_int32), ("batch", ctypes.c_int32),
+                ("height", ctypes.c_int32 * OSD_MAX_LEVELS), ("width", ctypes.c_int32 * OSD_MAX_LEVELS),
+                ("stride", ctypes.c_int32 * OSD_MAX_LEVELS),
+                ("pre_nms_thresh", ctypes.c_float), ("pre_nms_top_n", ctypes.c_int32),
+                ("nms_thresh", ctypes.c_float), ("post_nms_top_n", ctypes.c_int32),
+                ("min_size", ctypes.c_float), ("strict", ctypes.c_int32), ("early_exit", ctypes.c_int32)]
+
+
+class FcosPlan(ctypes.Structure):
+    _fields_ = [("workspace_bytes", ctypes.c_size_t), ("cand_capacity", ctypes.c_int32),
+                ("out_capacity", ctypes.c_int32), ("level_slot", ctypes.c_int32 * OSD_MAX_LEVELS),
+                ("off_cand_boxes", ctypes.c_size_t), ("off_cand_scores", ctypes.c_size_t),
+                ("off_cand_loc", ctypes.c_size_t), ("off_level_count", ctypes.c_size_t),
+                ("off_kept_count", ctypes.c_size_t)]
+
+
+class MatchDesc(ctypes.Structure):
+    _fields_ = [("num_levels", ctypes.c_int32), ("batch", ctypes.c_int32), ("shots", ctypes.c_int32),
+                ("channels", ctypes.c_int32), ("mode", ctypes.c_int32), ("layout", ctypes.c_int32),
+                ("dtype", ctypes.c_int32), ("hw", ctypes.c_int32 * OSD_MAX_LEVELS),
+                ("feat", ctypes.c_void_p * OSD_MAX_LEVELS), ("supp", ctypes.c_void_p * OSD_MAX_LEVELS),
+                ("out", ctypes.c_void_p * OSD_MAX_LEVELS)]
+
+
+# every symbol include/osd_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "osd_version": (ctypes.c_int, []),
+    "osd_last_error": (ctypes.c_char_p, []),
+    "osd_check_device": (ctypes.c_int, []),
+    "osd_launch_count": (ctypes.c_int64, []),
+    "osd_reset_launch_count": (None, []),
+    "osd_batched_nms_plan": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(NmsPlan)]),
+    "osd_batched_nms": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_float,
+                                       ctypes.c_int, c_void_p, ctypes.c_size_t, c_void_p, c_void_p, c_void_p]),
+    "osd_fcos_postprocess_plan": (ctypes.c_int, [ctypes.POINTER(FcosConfig), ctypes.POINTER(FcosPlan)]),
+    "osd_fcos_postprocess": (ctypes.c_int, [ctypes.POINTER(FcosConfig), ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                            ctypes.POINTER(c_void_p), c_void_p, c_void_p, ctypes.c_size_t, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_void_p]),
+    "osd_match_forward": (ctypes.c_int, [ctypes.POINTER(MatchDesc), c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_device_ok = set()
+
+
+class OsdError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libosd_b200.so (raises if it has not been built: there is no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise OsdError(
+                    f"{LIB_PATH} is missing. Build it with `python -m oneshotdet_b200.build` "
+                    "(nvcc, sm_100a). oneshotdet_b200 has no CPU or PyTorch fallback.")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(lib, name)  # AttributeError if the export is missing
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().osd_last_error().decode("utf-8", "replace")
+        raise OsdError(f"{what or 'libosd_b200'} failed (status {rc}): {msg}")
+
+
+def require_device(device) -> None:
+    """The tensors must live on an sm_100 GPU; anything else is an error, never a fallback."""
+    import torch
+
+    if device.type != "cuda":
+        raise OsdError(f"oneshotdet_b200 runs on B200 (sm_100a) only; got a tensor on '{device}'. There is no CPU path.")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _device_ok:
+        return
+    with torch.cuda.device(idx):
+        check(load().osd_check_device(), "osd_check_device")
+    _device_ok.add(idx)
+
+
+def current_stream_ptr(device) -> int:
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Workspace:
+    """Grow-only per-device scratch buffer from PyTorch's caching allocator (stream-ordered reuse)."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def get(self, device, nbytes: int):
+        import torch
+
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        buf = self._buf.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._buf[key] = buf
+        return buf

@@ -1,0 +1,334 @@
+// FCOS post-processing for sm_100a: one fused pass per (episode, level) that scores every location,
+// radix-selects the pre-NMS top-k in shared memory and writes decoded, clipped candidates in location
+// order -- then hands the candidates to the batched NMS pipeline (nms.cu).  Replaces the ~25 ATen ops
+// per level, the per-image Python loop and its .item() syncs of
+// maskrcnn_benchmark/modeling/rpn/fcos/inference.py:46-137 and :251-323.
+#include <climits>
+
+#include "osd_common.cuh"
+#include "osd_device_utils.cuh"
+
+namespace osd {
+
+namespace {
+
+constexpr int kSelThreads = 1024;
+constexpr int kRadixBins = 2048;  // 11 + 11 + 10 bit digits
+constexpr int kSmemKeyCap = 48 * 1024;  // locations whose keys fit in shared memory (192 KB)
+
+struct SelectArgs {
+  int nl, B;
+  int H[OSD_MAX_LEVELS], W[OSD_MAX_LEVELS], stride[OSD_MAX_LEVELS];
+  const float* cls[OSD_MAX_LEVELS];
+  const float* reg[OSD_MAX_LEVELS];
+  const float* ctr[OSD_MAX_LEVELS];
+  int slot[OSD_MAX_LEVELS];
+  int gkey_off[OSD_MAX_LEVELS];
+  const int32_t* image_hw;  // [B,2] (h, w)
+  float pre_thr;
+  int top_n;
+  float min_size;
+  int cap;
+  float4* cand_boxes;     // [B, cap]
+  float* cand_scores;     // [B, cap]
+  int32_t* cand_loc;      // [B, cap]
+  int32_t* level_count;   // [B, nl]
+  uint32_t* gkeys;        // [B, gkey_stride] spill for levels with more than kSmemKeyCap locations
+  int gkey_stride;
+};
+
+__device__ __forceinline__ float sigmoidf_precise(float x) {
+  // inference.py:58 / :72  torch.sigmoid in fp32: 1 / (1 + exp(-x))
+  return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+}
+
+__global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(SelectArgs A) {
+  extern __shared__ uint32_t sm_dyn[];
+  __shared__ int warp_tot[33];
+  __shared__ int s_bin, s_kk;
+  int* hist = reinterpret_cast<int*>(sm_dyn);  // [kRadixBins]
+  uint32_t* smem_keys = sm_dyn + kRadixBins;
+
+  const int l = blockIdx.x, e = blockIdx.y, tid = threadIdx.x;
+  const int Wl = A.W[l], HW = A.H[l] * Wl, stride = A.stride[l];
+  const float* cls = A.cls[l] + (size_t)e * HW;
+  const float* ctr = A.ctr[l] + (size_t)e * HW;
+  const float* reg = A.reg[l] + (size_t)e * 4 * HW;
+  uint32_t* keys = (HW <= kSmemKeyCap) ? smem_keys : (A.gkeys + (size_t)e * A.gkey_stride + A.gkey_off[l]);
+
+  // ---- 1. scores -> order-preserving keys (0 = not a candidate)
+  int my_cnt = 0;
+  for (int i = tid; i < HW; i += kSelThreads) {
+    const float p = sigmoidf_precise(cls[i]);
+    const float c = sigmoidf_precise(ctr[i]);
+    const float s = __fmul_rn(p, c);                    // inference.py:79
+    const bool cand = p > A.pre_thr;                    // inference.py:74 (tested before the multiply)
+    keys[i] = cand ? (__float_as_uint(s) + 1u) : 0u;    // s >= 0, so its bit pattern is monotone
+    my_cnt += cand ? 1 : 0;
+  }
+  const int cnt = block_sum(my_cnt, warp_tot);          // (contains the barrier that publishes keys)
+  const int k = min(cnt, A.top_n);                      // inference.py:75-76
+
+  // ---- 2. k-th largest key by 3-digit radix select (only when the level overflows top_n)
+  const bool take_all = (cnt <= k);
+  uint32_t T = 1u;   // threshold key
+  int need_eq = 0;   // how many keys equal to T are taken (lowest locations first)
+  if (!take_all) {
+    uint32_t prefix = 0u, pmask = 0u;
+    int kk = k;
+    const int shifts[3] = {21, 10, 0};
+    const int widths[3] = {11, 11, 10};
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+      const int sh = shifts[pass];
+      const uint32_t dm = (1u << widths[pass]) - 1u;
+      for (int b = tid; b < kRadixBins; b += kSelThreads) hist[b] = 0;
+      __syncthreads();
+      for (int i = tid; i < HW; i += kSelThreads) {
+        const uint32_t key = keys[i];
+        if (key != 0u && (key & pmask) == prefix) atomicAdd(&hist[(key >> sh) & dm], 1);
+      }
+      __syncthreads();
+      // suffix sums: thread tid owns bins (2r, 2r+1) with r = 1023 - tid
+      const int r = kSelThreads - 1 - tid;
+      const int v0 = hist[2 * r], v1 = hist[2 * r + 1];
+      int total;
+      const int above1 = block_exclusive_scan(v0 + v1, warp_tot, total);  // keys in bins > 2r+1
+      const int above0 = above1 + v1;                                     // keys in bins > 2r
+      if (above1 < kk && kk <= above1 + v1) {
+        s_bin = 2 * r + 1;
+        s_kk = kk - above1;
+      } else if (above0 < kk && kk <= above0 + v0) {
+        s_bin = 2 * r;
+        s_kk = kk - above0;
+      }
+      __syncthreads();
+      prefix |= ((uint32_t)s_bin) << sh;
+      pmask |= dm << sh;
+      kk = s_kk;
+      __syncthreads();
+    }
+    T = prefix;
+    need_eq = kk;
+  }
+
+  // ---- 3. decode + clip + size filter + ordered compaction
+  const int img_h = A.image_hw[2 * e], img_w = A.image_hw[2 * e + 1];
+  const float xmax = (float)(img_w - 1), ymax = (float)(img_h - 1);
+  const size_t obase = (size_t)e * A.cap + A.slot[l];
+  int out_base = 0, eq_seen = 0;
+  for (int i0 = 0; i0 < HW; i0 += kSelThreads) {
+    const int i = i0 + tid;
+    const uint32_t key = (i < HW) ? keys[i] : 0u;
+    bool sel;
+    if (take_all) {
+      sel = key != 0u;
+    } else {
+      const bool eq = key == T;
+      int tot_eq;
+      const int eq_rank = eq_seen + block_exclusive_scan(eq ? 1 : 0, warp_tot, tot_eq);
+      eq_seen += tot_eq;
+      sel = key > T || (eq && eq_rank < need_eq);
+    }
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool ok = false;
+    if (sel) {
+      const int row = i / Wl, col = i - row * Wl;
+      const float px = (float)(col * stride + stride / 2);   // fcos.py:220-234
+      const float py = (float)(row * stride + stride / 2);
+      const float dl = reg[i], dt = reg[HW + i], dr = reg[2 * HW + i], db = reg[3 * HW + i];
+      box.x = __fsub_rn(px, dl);                              // inference.py:104-109
+      box.y = __fsub_rn(py, dt);
+      box.z = __fadd_rn(px, dr);
+      box.w = __fadd_rn(py, db);
+      box.x = fminf(fmaxf(box.x, 0.f), xmax);                 // bounding_box.py:214-224
+      box.y = fminf(fmaxf(box.y, 0.f), ymax);
+      box.z = fminf(fmaxf(box.z, 0.f), xmax);
+      box.w = fminf(fmaxf(box.w, 0.f), ymax);
+      const float ws = __fadd_rn(__fsub_rn(box.z, box.x), 1.0f);  // boxlist_ops.py:202-216
+      const float hs = __fadd_rn(__fsub_rn(box.w, box.y), 1.0f);
+      ok = (ws >= A.min_size) && (hs >= A.min_size);
+    }
+    int tot;
+    const int pos = out_base + block_exclusive_scan(ok ? 1 : 0, warp_tot, tot);
+    out_base += tot;
+    if (ok) {
+      A.cand_boxes[obase + pos] = box;
+      A.cand_scores[obase + pos] = __uint_as_float(key - 1u);
+      A.cand_loc[obase + pos] = i;
+    }
+  }
+  if (tid == 0) A.level_count[e * A.nl + l] = out_base;
+}
+
+struct FcosBuffers {
+  float4* cand_boxes;
+  float* cand_scores;
+  int32_t* cand_loc;
+  int32_t* level_count;
+  int32_t* kept_total;
+  uint32_t* gkeys;
+  int gkey_stride;
+  int gkey_off[OSD_MAX_LEVELS];
+  NmsWorkspace nms;
+};
+
+int validate(const osd_fcos_config* cfg) {
+  OSD_REQUIRE(cfg != nullptr, "fcos: config is null");
+  OSD_REQUIRE(cfg->num_levels >= 1 && cfg->num_levels <= OSD_MAX_LEVELS, "fcos: num_levels %d out of range",
+              cfg->num_levels);
+  OSD_REQUIRE(cfg->batch >= 0 && cfg->batch <= 65535, "fcos: batch %d out of range", cfg->batch);
+  OSD_REQUIRE(cfg->pre_nms_top_n >= 1, "fcos: pre_nms_top_n must be >= 1");
+  int64_t cap = 0;
+  for (int l = 0; l < cfg->num_levels; ++l) {
+    OSD_REQUIRE(cfg->height[l] >= 1 && cfg->width[l] >= 1 && cfg->stride[l] >= 1, "fcos: bad level %d geometry", l);
+    const int64_t hw = (int64_t)cfg->height[l] * cfg->width[l];
+    OSD_REQUIRE(hw < (1 << 24), "fcos: level %d has too many locations", l);
+    OSD_REQUIRE(((int64_t)cfg->width[l] + 1) * cfg->stride[l] < (1 << 24) &&
+                ((int64_t)cfg->height[l] + 1) * cfg->stride[l] < (1 << 24), "fcos: level %d coordinates overflow fp32 integers", l);
+    cap += hw < cfg->pre_nms_top_n ? hw : cfg->pre_nms_top_n;
+  }
+  OSD_REQUIRE(cap < (1 << 24), "fcos: %lld candidates per episode is out of range", (long long)cap);
+  return OSD_OK;
+}
+
+void carve(const osd_fcos_config* cfg, Carver& c, FcosBuffers* buf, osd_fcos_plan* plan) {
+  const int B = cfg->batch > 0 ? cfg->batch : 1;
+  int cap = 0, gk = 0;
+  int slot[OSD_MAX_LEVELS] = {0};
+  FcosBuffers b{};
+  for (int l = 0; l < cfg->num_levels; ++l) {
+    const int hw = cfg->height[l] * cfg->width[l];
+    slot[l] = cap;
+    cap += hw < cfg->pre_nms_top_n ? hw : cfg->pre_nms_top_n;
+    b.gkey_off[l] = gk;
+    if (hw > kSmemKeyCap) gk += hw;
+  }
+  b.gkey_stride = gk;
+  const size_t o_boxes = c.offset_of_next();
+  b.cand_boxes = c.take<float4>((size_t)B * cap);
+  const size_t o_scores = c.offset_of_next();
+  b.cand_scores = c.take<float>((size_t)B * cap);
+  const size_t o_loc = c.offset_of_next();
+  b.cand_loc = c.take<int32_t>((size_t)B * cap);
+  const size_t o_lc = c.offset_of_next();
+  b.level_count = c.take<int32_t>((size_t)B * cfg->num_levels);
+  const size_t o_kt = c.offset_of_next();
+  b.kept_total = c.take<int32_t>(B);
+  b.gkeys = gk ? c.take<uint32_t>((size_t)B * gk) : nullptr;
+  nms_workspace_carve(c, B, cap, &b.nms);
+  if (buf) *buf = b;
+  if (plan) {
+    plan->workspace_bytes = c.total();
+    plan->cand_capacity = cap;
+    plan->out_capacity = (cfg->post_nms_top_n > 0 && cfg->post_nms_top_n < cap) ? cfg->post_nms_top_n : cap;
+    for (int l = 0; l < OSD_MAX_LEVELS; ++l) plan->level_slot[l] = l < cfg->num_levels ? slot[l] : 0;
+    plan->off_cand_boxes = o_boxes;
+    plan->off_cand_scores = o_scores;
+    plan->off_cand_loc = o_loc;
+    plan->off_level_count = o_lc;
+    plan->off_kept_count = o_kt;
+  }
+}
+
+}  // namespace
+}  // namespace osd
+
+extern "C" int osd_fcos_postprocess_plan(const osd_fcos_config* cfg, osd_fcos_plan* plan) {
+  OSD_REQUIRE(plan != nullptr, "osd_fcos_postprocess_plan: plan is null");
+  int rc = osd::validate(cfg);
+  if (rc != OSD_OK) return rc;
+  osd::Carver c(nullptr);
+  osd::carve(cfg, c, nullptr, plan);
+  return OSD_OK;
+}
+
+extern "C" int osd_fcos_postprocess(const osd_fcos_config* cfg, const float* const* cls, const float* const* reg,
+                                    const float* const* ctr, const int32_t* image_hw, void* workspace,
+                                    size_t workspace_bytes, float* out_boxes, float* out_scores,
+                                    int32_t* out_index, int32_t* out_count, void* stream_) {
+  using namespace osd;
+  int rc = validate(cfg);
+  if (rc != OSD_OK) return rc;
+  if (cfg->batch == 0) return OSD_OK;
+  OSD_REQUIRE(cls && reg && ctr && image_hw, "osd_fcos_postprocess: null input array");
+  OSD_REQUIRE(out_boxes && out_scores && out_index && out_count, "osd_fcos_postprocess: null output");
+  OSD_REQUIRE((reinterpret_cast<uintptr_t>(out_boxes) & 15) == 0, "osd_fcos_postprocess: out_boxes must be 16-byte aligned");
+  OSD_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+              "osd_fcos_postprocess: workspace must be 256-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  Carver c(workspace);
+  FcosBuffers buf{};
+  osd_fcos_plan plan{};
+  carve(cfg, c, &buf, &plan);
+  if (plan.workspace_bytes > workspace_bytes) {
+    set_error("osd_fcos_postprocess: workspace of %zu bytes needed, %zu given", plan.workspace_bytes, workspace_bytes);
+    return OSD_ERR_WORKSPACE;
+  }
+
+  SelectArgs A{};
+  A.nl = cfg->num_levels;
+  A.B = cfg->batch;
+  int max_hw_smem = 0;
+  for (int l = 0; l < cfg->num_levels; ++l) {
+    OSD_REQUIRE(cls[l] && reg[l] && ctr[l], "osd_fcos_postprocess: null level %d input", l);
+    A.H[l] = cfg->height[l];
+    A.W[l] = cfg->width[l];
+    A.stride[l] = cfg->stride[l];
+    A.cls[l] = cls[l];
+    A.reg[l] = reg[l];
+    A.ctr[l] = ctr[l];
+    A.slot[l] = plan.level_slot[l];
+    A.gkey_off[l] = buf.gkey_off[l];
+    const int hw = cfg->height[l] * cfg->width[l];
+    if (hw <= kSmemKeyCap && hw > max_hw_smem) max_hw_smem = hw;
+  }
+  A.image_hw = image_hw;
+  A.pre_thr = cfg->pre_nms_thresh;
+  A.top_n = cfg->pre_nms_top_n;
+  A.min_size = cfg->min_size;
+  A.cap = plan.cand_capacity;
+  A.cand_boxes = buf.cand_boxes;
+  A.cand_scores = buf.cand_scores;
+  A.cand_loc = buf.cand_loc;
+  A.level_count = buf.level_count;
+  A.gkeys = buf.gkeys;
+  A.gkey_stride = buf.gkey_stride;
+
+  const size_t smem = (size_t)kRadixBins * sizeof(int) + (size_t)max_hw_smem * sizeof(uint32_t);
+  {
+    static thread_local size_t configured = 48 * 1024;
+    if (smem > configured) {
+      OSD_CUDA(cudaFuncSetAttribute(fcos_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(kRadixBins * sizeof(int) + kSmemKeyCap * sizeof(uint32_t))));
+      configured = kRadixBins * sizeof(int) + kSmemKeyCap * sizeof(uint32_t);
+    }
+  }
+  dim3 grid((unsigned)cfg->num_levels, (unsigned)cfg->batch);
+  fcos_select_kernel<<<grid, kSelThreads, smem, stream>>>(A);
+  OSD_LAUNCH_CHECK("fcos_select_kernel");
+
+  CandLayout L{};
+  L.boxes = buf.cand_boxes;
+  L.scores = buf.cand_scores;
+  L.seg = nullptr;
+  L.level_count = buf.level_count;
+  L.nl = cfg->num_levels;
+  L.cap = plan.cand_capacity;
+  for (int l = 0; l < cfg->num_levels; ++l) L.slot[l] = plan.level_slot[l];
+  NmsParams P{};
+  P.thr = cfg->nms_thresh;
+  P.strict = cfg->strict ? 1 : 0;
+  P.post_top_n = cfg->post_nms_top_n;
+  P.early_exit = cfg->early_exit ? 1 : 0;
+  P.max_len = plan.cand_capacity;
+  P.passthrough = !(cfg->nms_thresh > 0.0f);  // boxlist_ops.py:22-23
+  NmsOutputs O{};
+  O.out_boxes = out_boxes;
+  O.out_scores = out_scores;
+  O.out_index = out_index;
+  O.out_count = out_count;
+  O.K = plan.out_capacity;
+  O.kept_total = buf.kept_total;
+  return nms_run(L, buf.nms, P, O, stream);
+}

@@ -1,0 +1,341 @@
+// Support -> target matching on the FPN levels for sm_100a: one launch streams all five levels.
+//   product:  out[b,c,h,w] = feat[b,c,h,w] * mean_s supp[b*S+s, c]      (generalized_rcnn.py:100-104, :306-311)
+//   concat :  out[b, 0:C] = feat[b], out[b, C:2C] = broadcast(mean_s supp)   (box_head.py:147; reversed :144)
+// HBM-bound elementwise stream: 128-bit non-allocating loads / streaming stores, 8 vectors in flight per
+// thread, persistent grid of 148 x k CTAs walking 32 KB output chunks, pooled support scalars staged in
+// shared memory per chunk (NCHW) or read as 128-bit vectors (NHWC).
+// The K-shot mean is the sequential fp32 sum divided by S (what ATen's mean computes on this shape), the
+// multiply a single rounded fp32 product: fp32 results are bit-identical to the reference expression.
+#include <cuda_bf16.h>
+
+#include "osd_common.cuh"
+
+namespace osd {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kVecPerThread = 8;
+constexpr int kChunkVec = kThreads * kVecPerThread;  // 2048 x 16 B = 32 KB of output per chunk
+constexpr int kPlaneCap = 2048;                      // pooled scalars staged per chunk
+
+struct FastDiv {  // exact n / d for 32-bit n, d (Lemire): q = (M * n) >> 64
+  uint64_t M;
+  uint32_t d;
+};
+__host__ FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  f.M = d > 1 ? (0xFFFFFFFFFFFFFFFFull / d + 1ull) : 0ull;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  return f.d > 1 ? (uint32_t)__umul64hi(f.M, (uint64_t)n) : n;
+}
+
+struct Level {
+  const void* feat;
+  const void* supp;
+  void* out;
+  uint32_t hw;
+  uint32_t out_elems;    // B * Cout * HW
+  uint32_t chunk_begin;  // first global chunk index of this level
+  FastDiv div_hw;        // NCHW: plane = g / HW
+  FastDiv div_img;       // NHWC: b = g / (HW * Cout)
+};
+
+struct Args {
+  int nl, B, S, C, Cout, mode;
+  uint32_t total_chunks;
+  FastDiv div_cout;      // q / Cout (NCHW concat: plane -> episode; NHWC: offset -> pixel)
+  Level lv[OSD_MAX_LEVELS];
+};
+
+template <typename T> struct Vec;
+template <> struct Vec<float> { static constexpr int N = 4; };
+template <> struct Vec<__nv_bfloat16> { static constexpr int N = 8; };
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ void from_f(float& d, float v) { d = v; }
+__device__ __forceinline__ void from_f(__nv_bfloat16& d, float v) { d = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(void* p, const uint4& v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// mean over the S shots of channel c of episode b: sequential fp32 sum, one IEEE division
+template <typename T>
+__device__ __forceinline__ float pooled_at(const T* __restrict__ supp, int S, int C, uint32_t q /* b*C + c */,
+                                           const FastDiv& div_c) {
+  if (S == 1) return to_f(supp[q]);
+  const uint32_t b = fdiv(q, div_c), c = q - b * C;
+  const T* p = supp + (size_t)b * S * C + c;
+  float acc = to_f(p[0]);
+  for (int s = 1; s < S; ++s) acc = __fadd_rn(acc, to_f(p[(size_t)s * C]));
+  const float m = __fdiv_rn(acc, (float)S);
+  T rounded;  // the mean is a tensor of the input dtype in the reference (bf16 inputs: rounded to bf16)
+  from_f(rounded, m);
+  return to_f(rounded);
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW.  Output element g of a level lives in plane po = g / HW at offset r.
+//   product: value = feat[g] * pooled(po)
+//   concat : b = po / 2C, co = po % 2C; feature half copies feat[(b*C + cc)*HW + r], support half
+//            writes pooled(b*C + cc)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__device__ __forceinline__ float nchw_value(const Args& A, const Level& L, uint32_t po, uint32_t r,
+                                            const float* sp, uint32_t p_first, bool staged, const FastDiv& div_c) {
+  const T* feat = static_cast<const T*>(L.feat);
+  const T* supp = static_cast<const T*>(L.supp);
+  if (MODE == OSD_MATCH_PRODUCT) {
+    const float s = staged ? sp[po - p_first] : pooled_at(supp, A.S, A.C, po, div_c);
+    return __fmul_rn(to_f(feat[(size_t)po * L.hw + r]), s);
+  }
+  const uint32_t b = fdiv(po, A.div_cout), co = po - b * A.Cout;
+  const bool first_half = co < (uint32_t)A.C;
+  const uint32_t cc = first_half ? co : co - A.C;
+  const bool is_feat = (MODE == OSD_MATCH_CONCAT) ? first_half : !first_half;
+  if (is_feat) return to_f(feat[((size_t)b * A.C + cc) * L.hw + r]);
+  return pooled_at(supp, A.S, A.C, b * A.C + cc, div_c);
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads) match_nchw_kernel(Args A, FastDiv div_c) {
+  constexpr int N = Vec<T>::N;
+  __shared__ float sp[kPlaneCap];
+  for (uint32_t chunk = blockIdx.x; chunk < A.total_chunks; chunk += gridDim.x) {
+    int li = 0;
+#pragma unroll
+    for (int k = 1; k < OSD_MAX_LEVELS; ++k)
+      if (k < A.nl && chunk >= A.lv[k].chunk_begin) li = k;
+    const Level& L = A.lv[li];
+    const uint32_t nvec = (L.out_elems + N - 1) / N;
+    const uint32_t v0 = (chunk - L.chunk_begin) * kChunkVec;
+    const uint32_t v1 = min(v0 + kChunkVec, nvec);
+    const uint32_t g_first = v0 * N, g_last = min(v1 * N, L.out_elems) - 1;
+    const uint32_t p_first = fdiv(g_first, L.div_hw), p_last = fdiv(g_last, L.div_hw);
+    const bool staged = (MODE == OSD_MATCH_PRODUCT) && (p_last - p_first + 1 <= kPlaneCap);
+    if (MODE == OSD_MATCH_PRODUCT) {
+      __syncthreads();  // previous chunk's readers are done with sp
+      if (staged) {
+        for (uint32_t p = p_first + threadIdx.x; p <= p_last; p += kThreads)
+          sp[p - p_first] = pooled_at(static_cast<const T*>(L.supp), A.S, A.C, p, div_c);
+      }
+      __syncthreads();
+    }
+    T* out = static_cast<T*>(L.out);
+    uint4 in[kVecPerThread];
+    uint32_t po[kVecPerThread], rr[kVecPerThread];
+    bool whole[kVecPerThread], is_feat[kVecPerThread];
+    // phase 1: index math + all loads in flight
+#pragma unroll
+    for (int j = 0; j < kVecPerThread; ++j) {
+      const uint32_t v = v0 + j * kThreads + threadIdx.x;
+      whole[j] = false;
+      is_feat[j] = true;
+      if (v < v1) {
+        const uint32_t g = v * N;
+        po[j] = fdiv(g, L.div_hw);
+        rr[j] = g - po[j] * L.hw;
+        whole[j] = (rr[j] + N <= L.hw) && (g + N <= L.out_elems);
+        if (whole[j]) {
+          size_t src = g;
+          if (MODE != OSD_MATCH_PRODUCT) {
+            const uint32_t b = fdiv(po[j], A.div_cout), co = po[j] - b * A.Cout;
+            const bool first_half = co < (uint32_t)A.C;
+            const uint32_t cc = first_half ? co : co - A.C;
+            is_feat[j] = (MODE == OSD_MATCH_CONCAT) ? first_half : !first_half;
+            src = ((size_t)b * A.C + cc) * L.hw + rr[j];
+            po[j] = b * A.C + cc;  // pooled index for the support half
+          }
+          if (is_feat[j]) in[j] = ld_stream(static_cast<const T*>(L.feat) + src);
+        }
+      }
+    }
+    // phase 2: compute + streaming stores
+#pragma unroll
+    for (int j = 0; j < kVecPerThread; ++j) {
+      const uint32_t v = v0 + j * kThreads + threadIdx.x;
+      if (v >= v1) continue;
+      const uint32_t g = v * N;
+      if (whole[j]) {
+        uint4 o;
+        T* ov = reinterpret_cast<T*>(&o);
+        const T* iv = reinterpret_cast<const T*>(&in[j]);
+        if (MODE == OSD_MATCH_PRODUCT) {
+          const float s = staged ? sp[po[j] - p_first] : pooled_at(static_cast<const T*>(L.supp), A.S, A.C, po[j], div_c);
+#pragma unroll
+          for (int k = 0; k < N; ++k) from_f(ov[k], __fmul_rn(to_f(iv[k]), s));
+        } else if (is_feat[j]) {
+          o = in[j];
+        } else {
+          const float s = pooled_at(static_cast<const T*>(L.supp), A.S, A.C, po[j], div_c);
+#pragma unroll
+          for (int k = 0; k < N; ++k) from_f(ov[k], s);
+        }
+        st_stream(out + g, o);
+      } else {
+        // vector straddles a plane boundary (HW not a multiple of the vector width) or the tensor end
+        uint32_t p = fdiv(g, L.div_hw), r = g - p * L.hw;
+        for (int k = 0; k < N && g + k < L.out_elems; ++k) {
+          while (r >= L.hw) {
+            r -= L.hw;
+            ++p;
+          }
+          from_f(out[g + k], nchw_value<T, MODE>(A, L, p, r, sp, p_first, staged, div_c));
+          ++r;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NHWC (channels_last).  Output element g = ((b*HW + pix) * Cout + co); requires C % vector width == 0,
+// so a vector never leaves its pixel nor its half.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads) match_nhwc_kernel(Args A, FastDiv div_c) {
+  constexpr int N = Vec<T>::N;
+  for (uint32_t chunk = blockIdx.x; chunk < A.total_chunks; chunk += gridDim.x) {
+    int li = 0;
+#pragma unroll
+    for (int k = 1; k < OSD_MAX_LEVELS; ++k)
+      if (k < A.nl && chunk >= A.lv[k].chunk_begin) li = k;
+    const Level& L = A.lv[li];
+    const uint32_t nvec = L.out_elems / N;
+    const uint32_t v0 = (chunk - L.chunk_begin) * kChunkVec;
+    const uint32_t v1 = min(v0 + kChunkVec, nvec);
+    const T* feat = static_cast<const T*>(L.feat);
+    const T* supp = static_cast<const T*>(L.supp);
+    T* out = static_cast<T*>(L.out);
+    uint4 in[kVecPerThread];
+    uint32_t bq[kVecPerThread];  // b*C + cc
+    bool is_feat[kVecPerThread];
+#pragma unroll
+    for (int j = 0; j < kVecPerThread; ++j) {
+      const uint32_t v = v0 + j * kThreads + threadIdx.x;
+      is_feat[j] = true;
+      if (v < v1) {
+        const uint32_t g = v * N;
+        const uint32_t b = fdiv(g, L.div_img);
+        const uint32_t off = g - b * (L.hw * A.Cout);
+        const uint32_t pix = fdiv(off, A.div_cout), co = off - pix * A.Cout;
+        uint32_t cc = co;
+        if (MODE != OSD_MATCH_PRODUCT) {
+          const bool first_half = co < (uint32_t)A.C;
+          cc = first_half ? co : co - A.C;
+          is_feat[j] = (MODE == OSD_MATCH_CONCAT) ? first_half : !first_half;
+        }
+        bq[j] = b * A.C + cc;
+        if (is_feat[j]) in[j] = ld_stream(feat + ((size_t)b * L.hw + pix) * A.C + cc);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kVecPerThread; ++j) {
+      const uint32_t v = v0 + j * kThreads + threadIdx.x;
+      if (v >= v1) continue;
+      uint4 o;
+      T* ov = reinterpret_cast<T*>(&o);
+      const T* iv = reinterpret_cast<const T*>(&in[j]);
+      if (MODE == OSD_MATCH_PRODUCT) {
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          from_f(ov[k], __fmul_rn(to_f(iv[k]), pooled_at(supp, A.S, A.C, bq[j] + k, div_c)));
+      } else if (is_feat[j]) {
+        o = in[j];
+      } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) from_f(ov[k], pooled_at(supp, A.S, A.C, bq[j] + k, div_c));
+      }
+      st_stream(out + (size_t)v * N, o);
+    }
+  }
+}
+
+template <typename T, int MODE>
+int launch(const Args& A, int layout, cudaStream_t stream) {
+  const FastDiv div_c = make_fastdiv((uint32_t)A.C);
+  // persistent grid: a multiple of the SM count, capped by the work
+  int ctas = kNumSMs * 8;
+  if ((uint32_t)ctas > A.total_chunks) ctas = (int)A.total_chunks;
+  if (ctas < 1) return OSD_OK;
+  if (layout == OSD_LAYOUT_NCHW) {
+    match_nchw_kernel<T, MODE><<<ctas, kThreads, 0, stream>>>(A, div_c);
+    OSD_LAUNCH_CHECK("match_nchw_kernel");
+  } else {
+    match_nhwc_kernel<T, MODE><<<ctas, kThreads, 0, stream>>>(A, div_c);
+    OSD_LAUNCH_CHECK("match_nhwc_kernel");
+  }
+  return OSD_OK;
+}
+
+template <typename T>
+int dispatch_mode(const Args& A, int layout, cudaStream_t stream) {
+  switch (A.mode) {
+    case OSD_MATCH_PRODUCT: return launch<T, OSD_MATCH_PRODUCT>(A, layout, stream);
+    case OSD_MATCH_CONCAT: return launch<T, OSD_MATCH_CONCAT>(A, layout, stream);
+    case OSD_MATCH_CONCAT_REVERSED: return launch<T, OSD_MATCH_CONCAT_REVERSED>(A, layout, stream);
+  }
+  set_error("osd_match_forward: unknown mode %d", A.mode);
+  return OSD_ERR_INVALID;
+}
+
+}  // namespace
+}  // namespace osd
+
+extern "C" int osd_match_forward(const osd_match_desc* d, void* stream) {
+  using namespace osd;
+  OSD_REQUIRE(d != nullptr, "osd_match_forward: desc is null");
+  OSD_REQUIRE(d->num_levels >= 1 && d->num_levels <= OSD_MAX_LEVELS, "osd_match_forward: num_levels %d out of range", d->num_levels);
+  OSD_REQUIRE(d->batch >= 0 && d->shots >= 1 && d->channels >= 1, "osd_match_forward: bad batch/shots/channels");
+  OSD_REQUIRE(d->mode >= OSD_MATCH_PRODUCT && d->mode <= OSD_MATCH_CONCAT_REVERSED, "osd_match_forward: unknown mode %d", d->mode);
+  OSD_REQUIRE(d->layout == OSD_LAYOUT_NCHW || d->layout == OSD_LAYOUT_NHWC, "osd_match_forward: unknown layout %d", d->layout);
+  OSD_REQUIRE(d->dtype == OSD_DTYPE_F32 || d->dtype == OSD_DTYPE_BF16, "osd_match_forward: unknown dtype %d", d->dtype);
+  if (d->batch == 0) return OSD_OK;
+  const int N = d->dtype == OSD_DTYPE_F32 ? 4 : 8;
+  Args A{};
+  A.nl = d->num_levels;
+  A.B = d->batch;
+  A.S = d->shots;
+  A.C = d->channels;
+  A.Cout = d->mode == OSD_MATCH_PRODUCT ? d->channels : 2 * d->channels;
+  A.mode = d->mode;
+  A.div_cout = make_fastdiv((uint32_t)A.Cout);
+  if (d->layout == OSD_LAYOUT_NHWC)
+    OSD_REQUIRE(d->channels % N == 0, "osd_match_forward: NHWC needs channels %% %d == 0 (got %d)", N, d->channels);
+  uint64_t chunks = 0;
+  for (int l = 0; l < d->num_levels; ++l) {
+    OSD_REQUIRE(d->hw[l] >= 1, "osd_match_forward: level %d is empty", l);
+    OSD_REQUIRE(d->feat[l] && d->supp[l] && d->out[l], "osd_match_forward: null pointer at level %d", l);
+    OSD_REQUIRE(((reinterpret_cast<uintptr_t>(d->feat[l]) | reinterpret_cast<uintptr_t>(d->out[l])) & 15) == 0,
+                "osd_match_forward: level %d feat/out must be 16-byte aligned", l);
+    const uint64_t elems = (uint64_t)d->batch * A.Cout * d->hw[l];
+    OSD_REQUIRE(elems < (1ull << 31), "osd_match_forward: level %d has %llu output elements; split the batch", l,
+                (unsigned long long)elems);
+    Level& L = A.lv[l];
+    L.feat = d->feat[l];
+    L.supp = d->supp[l];
+    L.out = d->out[l];
+    L.hw = (uint32_t)d->hw[l];
+    L.out_elems = (uint32_t)elems;
+    L.chunk_begin = (uint32_t)chunks;
+    L.div_hw = make_fastdiv(L.hw);
+    L.div_img = make_fastdiv((uint32_t)((uint64_t)d->hw[l] * A.Cout));
+    OSD_REQUIRE((uint64_t)d->hw[l] * A.Cout < (1ull << 32), "osd_match_forward: level %d image too large", l);
+    chunks += (elems + (uint64_t)N * kChunkVec - 1) / ((uint64_t)N * kChunkVec);
+  }
+  OSD_REQUIRE(chunks < (1ull << 32), "osd_match_forward: too much work for one call");
+  A.total_chunks = (uint32_t)chunks;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (d->dtype == OSD_DTYPE_F32) return dispatch_mode<float>(A, d->layout, s);
+  return dispatch_mode<__nv_bfloat16>(A, d->layout, s);
+}

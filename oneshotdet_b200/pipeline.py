@@ -1,0 +1,101 @@
+"""EpisodePipeline: the public, fixed-shape entry point for serving a batch of (target, support) episodes --
+matching on P3-P7 followed by the fused FCOS post-processing -- with optional episode sharding over the GPUs of
+one box (one process per GPU, final all-gather of detections over NCCL).
+
+    pipe = EpisodePipeline(batch=16, height=800, width=1344, image_sizes=[(800, 1333)] * 16)
+    det = pipe.run_host(host_inputs)        # pinned host buffers in, host detections out  (end-to-end)
+    res = pipe.run()                        # inputs already resident in pipe.features / pipe.cls ... (device)
+
+The FCOS head itself (cuDNN convolutions between the two stages, modeling/rpn/fcos/fcos.py:12-99) is outside
+the accelerated path: ``run`` consumes head outputs the caller provides."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+
+FPN_STRIDES = (8, 16, 32, 64, 128)
+
+
+def level_shapes(height: int, width: int, strides=FPN_STRIDES):
+    return [(-(-height // s), -(-width // s)) for s in strides]
+
+
+@dataclass
+class PostParams:
+    pre_nms_thresh: float = 0.0     # two-stage values of inference.py:337-351 / the shipped yaml :20-26
+    pre_nms_top_n: int = 6000
+    nms_thresh: float = 0.8
+    fpn_post_nms_top_n: int = 2000
+    min_size: float = 0.0
+
+
+class EpisodePipeline:
+    def __init__(self, batch: int, height: int, width: int, image_sizes, channels: int = 256, shots: int = 1,
+                 strides=FPN_STRIDES, params: PostParams | None = None, match_mode: str = "product",
+                 device="cuda", dtype=torch.float32, early_exit: bool = True, strict_iou: bool = False):
+        self.device = torch.device(device)
+        self.batch, self.channels, self.shots = batch, channels, shots
+        self.params = params or PostParams()
+        self.shapes = level_shapes(height, width, strides)
+        self.strides = tuple(strides)
+        dev = self.device
+        # device-resident inputs (the caller writes into these, or uses run_host)
+        self.features = [torch.empty((batch, channels, h, w), dtype=dtype, device=dev) for h, w in self.shapes]
+        self.supp = [torch.empty((batch * shots, channels, 1, 1), dtype=dtype, device=dev) for _ in self.shapes]
+        self.cls = [torch.empty((batch, 1, h, w), dtype=torch.float32, device=dev) for h, w in self.shapes]
+        self.reg = [torch.empty((batch, 4, h, w), dtype=torch.float32, device=dev) for h, w in self.shapes]
+        self.ctr = [torch.empty((batch, 1, h, w), dtype=torch.float32, device=dev) for h, w in self.shapes]
+        self.match = ops.PreparedMatch(self.features, self.supp, batch, match_mode)
+        self.combined = self.match.outs
+        p = self.params
+        self.post = ops.PreparedFcos(self.cls, self.reg, self.ctr, self.strides, image_sizes, p.pre_nms_thresh,
+                                     p.pre_nms_top_n, p.nms_thresh, p.fpn_post_nms_top_n, p.min_size, strict_iou,
+                                     early_exit, private_workspace=True)
+        self._host_out = None
+
+    # ---- device-resident step -------------------------------------------------------------------
+    def run(self) -> ops.FcosResult:
+        """One pass of the hot path over the resident batch: 1 matching launch + the post-processing launches."""
+        self.match()
+        return self.post()
+
+    def input_tensors(self):
+        return self.features + self.supp + self.cls + self.reg + self.ctr
+
+    # ---- end-to-end step (host buffers in, host detections out) ----------------------------------
+    def make_host_inputs(self, pinned: bool = True):
+        return [torch.empty(t.shape, dtype=t.dtype, pin_memory=pinned) for t in self.input_tensors()]
+
+    def run_host(self, host_inputs):
+        """H2D copies of every input, the device step, D2H of (boxes, scores, count); returns host tensors after
+        synchronising the stream.  Bytes moved are in ``h2d_bytes`` / ``d2h_bytes``."""
+        for dst, src in zip(self.input_tensors(), host_inputs):
+            dst.copy_(src, non_blocking=True)
+        res = self.run()
+        if self._host_out is None:
+            self._host_out = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                                   for t in (res.boxes, res.scores, res.count))
+        for dst, src in zip(self._host_out, (res.boxes, res.scores, res.count)):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._host_out
+
+    @property
+    def h2d_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.input_tensors())
+
+    @property
+    def d2h_bytes(self) -> int:
+        r = self.post.result
+        return sum(t.numel() * t.element_size() for t in (r.boxes, r.scores, r.count))
+
+    # ---- multi-GPU: episodes are sharded, detections gathered --------------------------------------
+    def pack_detections(self, res: ops.FcosResult, episode_offset: int = 0):
+        """[B, K, 6] fp32 rows (x1, y1, x2, y2, score, global episode id) + counts: the fixed-shape payload that
+        replaces the reference's pickled-BoxList all_gather (utils/comm.py:48-88)."""
+        b, k = res.scores.shape
+        eid = torch.arange(episode_offset, episode_offset + b, device=res.scores.device, dtype=torch.float32)
+        return torch.cat((res.boxes, res.scores.unsqueeze(-1), eid.view(b, 1, 1).expand(b, k, 1)), dim=-1), res.count

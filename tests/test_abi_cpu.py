@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library builds, loads without a GPU and exports every symbol include/osd_b200.h declares;
+host-side argument validation works without touching a device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from oneshotdet_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "osd_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(osd_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in osd_b200.h but not exported"
+    assert sorted(_lib.SYMBOLS) == names  # the ctypes table covers the header, nothing more
+
+
+def test_version_and_error_string(lib):
+    assert lib.osd_version() >= 100
+    assert isinstance(lib.osd_last_error(), bytes)
+
+
+def test_plans_need_no_gpu(lib):
+    plan = _lib.NmsPlan()
+    assert lib.osd_batched_nms_plan(16, 11600, ctypes.byref(plan)) == 0
+    assert plan.padded_len == 11648 and plan.mask_words == 182
+    assert plan.workspace_bytes > 16 * 11648 * 182 * 8
+    cfg = _lib.FcosConfig()
+    cfg.num_levels, cfg.batch = 5, 16
+    for l, ((h, w), s) in enumerate(zip([(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)], (8, 16, 32, 64, 128))):
+        cfg.height[l], cfg.width[l], cfg.stride[l] = h, w, s
+    cfg.pre_nms_thresh, cfg.pre_nms_top_n, cfg.nms_thresh, cfg.post_nms_top_n = 0.0, 6000, 0.8, 2000
+    fp = _lib.FcosPlan()
+    assert lib.osd_fcos_postprocess_plan(ctypes.byref(cfg), ctypes.byref(fp)) == 0
+    assert fp.cand_capacity == 6000 + 4200 + 1050 + 273 + 77 == 11600
+    assert fp.out_capacity == 2000
+    assert [fp.level_slot[i] for i in range(5)] == [0, 6000, 10200, 11250, 11523]
+
+
+def test_invalid_arguments_are_reported(lib):
+    cfg = _lib.FcosConfig()
+    cfg.num_levels = 0
+    fp = _lib.FcosPlan()
+    assert lib.osd_fcos_postprocess_plan(ctypes.byref(cfg), ctypes.byref(fp)) == -1
+    assert b"num_levels" in lib.osd_last_error()
+    d = _lib.MatchDesc()
+    d.num_levels, d.batch, d.shots, d.channels, d.mode = 1, 1, 1, 8, 7
+    assert lib.osd_match_forward(ctypes.byref(d), None) == -1
+    assert b"mode" in lib.osd_last_error()
+
+
+def test_product_path_refuses_cpu_tensors():
+    import torch
+
+    import oneshotdet_b200 as osd
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        osd.nms(torch.zeros(4, 4), torch.zeros(4), 0.5)
+    with pytest.raises(RuntimeError, match="B200"):
+        osd.match_forward([torch.zeros(1, 8, 2, 2)], [torch.zeros(1, 8, 1, 1)], 1)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "oneshotdet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
