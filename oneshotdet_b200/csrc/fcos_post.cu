@@ -42,29 +42,64 @@ __device__ __forceinline__ float sigmoidf_precise(float x) {
   return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
 }
 
+struct Decoded {
+  float4 box;
+  bool ok;
+};
+
+// inference.py:104-109 decode, bounding_box.py:214-224 clip, boxlist_ops.py:202-216 size filter
+__device__ __forceinline__ Decoded decode_clip(float dl, float dt, float dr, float db, int i, int Wl, int stride,
+                                               float xmax, float ymax, float min_size) {
+  const int row = i / Wl, col = i - row * Wl;
+  const float px = (float)(col * stride + stride / 2);  // fcos.py:220-234
+  const float py = (float)(row * stride + stride / 2);
+  Decoded d;
+  d.box.x = fminf(fmaxf(__fsub_rn(px, dl), 0.f), xmax);
+  d.box.y = fminf(fmaxf(__fsub_rn(py, dt), 0.f), ymax);
+  d.box.z = fminf(fmaxf(__fadd_rn(px, dr), 0.f), xmax);
+  d.box.w = fminf(fmaxf(__fadd_rn(py, db), 0.f), ymax);
+  const float ws = __fadd_rn(__fsub_rn(d.box.z, d.box.x), 1.0f);
+  const float hs = __fadd_rn(__fsub_rn(d.box.w, d.box.y), 1.0f);
+  d.ok = (ws >= min_size) && (hs >= min_size);
+  return d;
+}
+
 __global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(SelectArgs A) {
   extern __shared__ uint32_t sm_dyn[];
   __shared__ int warp_tot[33];
-  __shared__ int s_bin, s_kk;
+  __shared__ int s_bin, s_kk, s_eq;
   int* hist = reinterpret_cast<int*>(sm_dyn);  // [kRadixBins]
   uint32_t* smem_keys = sm_dyn + kRadixBins;
 
   const int l = blockIdx.x, e = blockIdx.y, tid = threadIdx.x;
   const int Wl = A.W[l], HW = A.H[l] * Wl, stride = A.stride[l];
-  const float* cls = A.cls[l] + (size_t)e * HW;
-  const float* ctr = A.ctr[l] + (size_t)e * HW;
-  const float* reg = A.reg[l] + (size_t)e * 4 * HW;
+  const float* __restrict__ cls = A.cls[l] + (size_t)e * HW;
+  const float* __restrict__ ctr = A.ctr[l] + (size_t)e * HW;
+  const float* __restrict__ reg = A.reg[l] + (size_t)e * 4 * HW;
   uint32_t* keys = (HW <= kSmemKeyCap) ? smem_keys : (A.gkeys + (size_t)e * A.gkey_stride + A.gkey_off[l]);
 
-  // ---- 1. scores -> order-preserving keys (0 = not a candidate)
+  // ---- 1. scores -> order-preserving keys (0 = not a candidate); 4 independent loads in flight per array
   int my_cnt = 0;
-  for (int i = tid; i < HW; i += kSelThreads) {
-    const float p = sigmoidf_precise(cls[i]);
-    const float c = sigmoidf_precise(ctr[i]);
-    const float s = __fmul_rn(p, c);                    // inference.py:79
-    const bool cand = p > A.pre_thr;                    // inference.py:74 (tested before the multiply)
-    keys[i] = cand ? (__float_as_uint(s) + 1u) : 0u;    // s >= 0, so its bit pattern is monotone
-    my_cnt += cand ? 1 : 0;
+  for (int i0 = tid; i0 < HW; i0 += 4 * kSelThreads) {
+    float xc[4], xt[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kSelThreads;
+      xc[u] = (i < HW) ? cls[i] : 0.f;
+      xt[u] = (i < HW) ? ctr[i] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kSelThreads;
+      if (i < HW) {
+        const float p = sigmoidf_precise(xc[u]);
+        const float c = sigmoidf_precise(xt[u]);
+        const float s = __fmul_rn(p, c);                    // inference.py:79
+        const bool cand = p > A.pre_thr;                    // inference.py:74 (tested before the multiply)
+        keys[i] = cand ? (__float_as_uint(s) + 1u) : 0u;    // s >= 0, so its bit pattern is monotone
+        my_cnt += cand ? 1 : 0;
+      }
+    }
   }
   const int cnt = block_sum(my_cnt, warp_tot);          // (contains the barrier that publishes keys)
   const int k = min(cnt, A.top_n);                      // inference.py:75-76
@@ -73,6 +108,7 @@ __global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(SelectArgs A) 
   const bool take_all = (cnt <= k);
   uint32_t T = 1u;   // threshold key
   int need_eq = 0;   // how many keys equal to T are taken (lowest locations first)
+  int eq_total = 0;  // how many keys equal T
   if (!take_all) {
     uint32_t prefix = 0u, pmask = 0u;
     int kk = k;
@@ -98,67 +134,103 @@ __global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(SelectArgs A) 
       if (above1 < kk && kk <= above1 + v1) {
         s_bin = 2 * r + 1;
         s_kk = kk - above1;
+        s_eq = v1;
       } else if (above0 < kk && kk <= above0 + v0) {
         s_bin = 2 * r;
         s_kk = kk - above0;
+        s_eq = v0;
       }
       __syncthreads();
       prefix |= ((uint32_t)s_bin) << sh;
       pmask |= dm << sh;
       kk = s_kk;
+      eq_total = s_eq;   // after the last pass: number of keys equal to the threshold key
       __syncthreads();
     }
     T = prefix;
     need_eq = kk;
   }
 
-  // ---- 3. decode + clip + size filter + ordered compaction
+  // ---- 3. decode + clip + size filter + ordered compaction.  Each thread owns a contiguous run of `per`
+  //         locations (per is odd: conflict-free shared-memory reads), so location order is thread order and one
+  //         block scan positions everything.
   const int img_h = A.image_hw[2 * e], img_w = A.image_hw[2 * e + 1];
   const float xmax = (float)(img_w - 1), ymax = (float)(img_h - 1);
   const size_t obase = (size_t)e * A.cap + A.slot[l];
-  int out_base = 0, eq_seen = 0;
-  for (int i0 = 0; i0 < HW; i0 += kSelThreads) {
-    const int i = i0 + tid;
-    const uint32_t key = (i < HW) ? keys[i] : 0u;
-    bool sel;
-    if (take_all) {
-      sel = key != 0u;
-    } else {
-      const bool eq = key == T;
-      int tot_eq;
-      const int eq_rank = eq_seen + block_exclusive_scan(eq ? 1 : 0, warp_tot, tot_eq);
-      eq_seen += tot_eq;
-      sel = key > T || (eq && eq_rank < need_eq);
+  // per <= 63 so a run's flags fit one 64-bit mask; levels beyond 63 * 1024 locations take several rounds
+  const int per = min(((HW + kSelThreads - 1) / kSelThreads) | 1, 63);
+  const int round = per * kSelThreads;
+  const bool ties = !take_all && need_eq < eq_total;  // ties at the top-k boundary: the lowest locations win
+  int level_total = 0, eq_seen = 0;
+  for (int seg0 = 0; seg0 < HW; seg0 += round) {
+    const int first = seg0 + tid * per;
+    const int run_end = min(min(HW, seg0 + round), first + per);  // this thread owns [first, run_end)
+    int eq_rank = 0;
+    if (ties) {
+      int my_eq = 0;
+      for (int i = first; i < run_end; ++i) my_eq += (keys[i] == T) ? 1 : 0;
+      int tot;
+      eq_rank = eq_seen + block_exclusive_scan(my_eq, warp_tot, tot);
+      eq_seen += tot;
     }
-    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool ok = false;
-    if (sel) {
-      const int row = i / Wl, col = i - row * Wl;
-      const float px = (float)(col * stride + stride / 2);   // fcos.py:220-234
-      const float py = (float)(row * stride + stride / 2);
-      const float dl = reg[i], dt = reg[HW + i], dr = reg[2 * HW + i], db = reg[3 * HW + i];
-      box.x = __fsub_rn(px, dl);                              // inference.py:104-109
-      box.y = __fsub_rn(py, dt);
-      box.z = __fadd_rn(px, dr);
-      box.w = __fadd_rn(py, db);
-      box.x = fminf(fmaxf(box.x, 0.f), xmax);                 // bounding_box.py:214-224
-      box.y = fminf(fmaxf(box.y, 0.f), ymax);
-      box.z = fminf(fmaxf(box.z, 0.f), xmax);
-      box.w = fminf(fmaxf(box.w, 0.f), ymax);
-      const float ws = __fadd_rn(__fsub_rn(box.z, box.x), 1.0f);  // boxlist_ops.py:202-216
-      const float hs = __fadd_rn(__fsub_rn(box.w, box.y), 1.0f);
-      ok = (ws >= A.min_size) && (hs >= A.min_size);
+    unsigned long long selmask = 0ull;
+    for (int q = 0; first + q < run_end; ++q) {
+      const int i = first + q;
+      const uint32_t key = keys[i];
+      bool sel;
+      if (take_all) sel = key != 0u;
+      else if (key > T) sel = true;
+      else if (key == T) sel = !ties || (eq_rank++ < need_eq);
+      else sel = false;
+      if (sel) selmask |= 1ull << q;
+    }
+    // count pass: which selected locations survive the size filter (4 locations' loads in flight at a time)
+    unsigned long long okmask = 0ull, m = selmask;
+    while (m) {
+      int qs[4];
+      float v[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        qs[u] = m ? (__ffsll((long long)m) - 1) : -1;
+        if (m) m &= m - 1ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (qs[u] >= 0) {
+          const int i = first + qs[u];
+          v[u][0] = reg[i];
+          v[u][1] = reg[HW + i];
+          v[u][2] = reg[2 * HW + i];
+          v[u][3] = reg[3 * HW + i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (qs[u] >= 0) {
+          const Decoded d = decode_clip(v[u][0], v[u][1], v[u][2], v[u][3], first + qs[u], Wl, stride, xmax, ymax,
+                                        A.min_size);
+          if (d.ok) okmask |= 1ull << qs[u];
+        }
+      }
     }
     int tot;
-    const int pos = out_base + block_exclusive_scan(ok ? 1 : 0, warp_tot, tot);
-    out_base += tot;
-    if (ok) {
-      A.cand_boxes[obase + pos] = box;
-      A.cand_scores[obase + pos] = __uint_as_float(key - 1u);
+    int pos = level_total + block_exclusive_scan(__popcll(okmask), warp_tot, tot);
+    level_total += tot;
+    // write pass (the same loads now hit L1)
+    m = okmask;
+    while (m) {
+      const int q = __ffsll((long long)m) - 1;
+      m &= m - 1ull;
+      const int i = first + q;
+      const Decoded d = decode_clip(reg[i], reg[HW + i], reg[2 * HW + i], reg[3 * HW + i], i, Wl, stride, xmax, ymax,
+                                    A.min_size);
+      A.cand_boxes[obase + pos] = d.box;
+      A.cand_scores[obase + pos] = __uint_as_float(keys[i] - 1u);
       A.cand_loc[obase + pos] = i;
+      ++pos;
     }
   }
-  if (tid == 0) A.level_count[e * A.nl + l] = out_base;
+  if (tid == 0) A.level_count[e * A.nl + l] = level_total;
 }
 
 struct FcosBuffers {

@@ -1,9 +1,9 @@
 // Support -> target matching on the FPN levels for sm_100a: one launch streams all five levels.
 //   product:  out[b,c,h,w] = feat[b,c,h,w] * mean_s supp[b*S+s, c]      (generalized_rcnn.py:100-104, :306-311)
 //   concat :  out[b, 0:C] = feat[b], out[b, C:2C] = broadcast(mean_s supp)   (box_head.py:147; reversed :144)
-// HBM-bound elementwise stream: 128-bit non-allocating loads / streaming stores, 8 vectors in flight per
-// thread, persistent grid of 148 x k CTAs walking 32 KB output chunks, pooled support scalars staged in
-// shared memory per chunk (NCHW) or read as 128-bit vectors (NHWC).
+// HBM-bound elementwise stream: 128-bit non-allocating loads / streaming stores, 4 vectors in flight per
+// thread and up to 2048 threads per SM, persistent grid of 148 x k CTAs walking 16 KB output chunks, no
+// barriers; pooled support scalars come from L1.
 // The K-shot mean is the sequential fp32 sum divided by S (what ATen's mean computes on this shape), the
 // multiply a single rounded fp32 product: fp32 results are bit-identical to the reference expression.
 #include <cuda_bf16.h>
@@ -14,9 +14,8 @@ namespace osd {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kVecPerThread = 8;
-constexpr int kChunkVec = kThreads * kVecPerThread;  // 2048 x 16 B = 32 KB of output per chunk
-constexpr int kPlaneCap = 2048;                      // pooled scalars staged per chunk
+constexpr int kVecPerThread = 4;                     // independent 128-bit loads in flight per thread
+constexpr int kChunkVec = kThreads * kVecPerThread;  // 1024 x 16 B = 16 KB of output per chunk
 
 struct FastDiv {  // exact n / d for 32-bit n, d (Lemire): q = (M * n) >> 64
   uint64_t M;
@@ -92,12 +91,11 @@ __device__ __forceinline__ float pooled_at(const T* __restrict__ supp, int S, in
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE>
 __device__ __forceinline__ float nchw_value(const Args& A, const Level& L, uint32_t po, uint32_t r,
-                                            const float* sp, uint32_t p_first, bool staged, const FastDiv& div_c) {
+                                            const FastDiv& div_c) {
   const T* feat = static_cast<const T*>(L.feat);
   const T* supp = static_cast<const T*>(L.supp);
   if (MODE == OSD_MATCH_PRODUCT) {
-    const float s = staged ? sp[po - p_first] : pooled_at(supp, A.S, A.C, po, div_c);
-    return __fmul_rn(to_f(feat[(size_t)po * L.hw + r]), s);
+    return __fmul_rn(to_f(feat[(size_t)po * L.hw + r]), pooled_at(supp, A.S, A.C, po, div_c));
   }
   const uint32_t b = fdiv(po, A.div_cout), co = po - b * A.Cout;
   const bool first_half = co < (uint32_t)A.C;
@@ -108,9 +106,10 @@ __device__ __forceinline__ float nchw_value(const Args& A, const Level& L, uint3
 }
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads) match_nchw_kernel(Args A, FastDiv div_c) {
+__global__ void __launch_bounds__(kThreads, 5) match_nchw_kernel(Args A, FastDiv div_c) {
   constexpr int N = Vec<T>::N;
-  __shared__ float sp[kPlaneCap];
+  // no shared memory, no barriers: every warp streams independently; the pooled support scalar of a plane is a
+  // 4-byte read that stays in L1 (B*C*S values per level)
   for (uint32_t chunk = blockIdx.x; chunk < A.total_chunks; chunk += gridDim.x) {
     int li = 0;
 #pragma unroll
@@ -120,17 +119,6 @@ __global__ void __launch_bounds__(kThreads) match_nchw_kernel(Args A, FastDiv di
     const uint32_t nvec = (L.out_elems + N - 1) / N;
     const uint32_t v0 = (chunk - L.chunk_begin) * kChunkVec;
     const uint32_t v1 = min(v0 + kChunkVec, nvec);
-    const uint32_t g_first = v0 * N, g_last = min(v1 * N, L.out_elems) - 1;
-    const uint32_t p_first = fdiv(g_first, L.div_hw), p_last = fdiv(g_last, L.div_hw);
-    const bool staged = (MODE == OSD_MATCH_PRODUCT) && (p_last - p_first + 1 <= kPlaneCap);
-    if (MODE == OSD_MATCH_PRODUCT) {
-      __syncthreads();  // previous chunk's readers are done with sp
-      if (staged) {
-        for (uint32_t p = p_first + threadIdx.x; p <= p_last; p += kThreads)
-          sp[p - p_first] = pooled_at(static_cast<const T*>(L.supp), A.S, A.C, p, div_c);
-      }
-      __syncthreads();
-    }
     T* out = static_cast<T*>(L.out);
     uint4 in[kVecPerThread];
     uint32_t po[kVecPerThread], rr[kVecPerThread];
@@ -171,7 +159,7 @@ __global__ void __launch_bounds__(kThreads) match_nchw_kernel(Args A, FastDiv di
         T* ov = reinterpret_cast<T*>(&o);
         const T* iv = reinterpret_cast<const T*>(&in[j]);
         if (MODE == OSD_MATCH_PRODUCT) {
-          const float s = staged ? sp[po[j] - p_first] : pooled_at(static_cast<const T*>(L.supp), A.S, A.C, po[j], div_c);
+          const float s = pooled_at(static_cast<const T*>(L.supp), A.S, A.C, po[j], div_c);
 #pragma unroll
           for (int k = 0; k < N; ++k) from_f(ov[k], __fmul_rn(to_f(iv[k]), s));
         } else if (is_feat[j]) {
@@ -190,7 +178,7 @@ __global__ void __launch_bounds__(kThreads) match_nchw_kernel(Args A, FastDiv di
             r -= L.hw;
             ++p;
           }
-          from_f(out[g + k], nchw_value<T, MODE>(A, L, p, r, sp, p_first, staged, div_c));
+          from_f(out[g + k], nchw_value<T, MODE>(A, L, p, r, div_c));
           ++r;
         }
       }
@@ -203,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) match_nchw_kernel(Args A, FastDiv di
 // so a vector never leaves its pixel nor its half.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads) match_nhwc_kernel(Args A, FastDiv div_c) {
+__global__ void __launch_bounds__(kThreads, 5) match_nhwc_kernel(Args A, FastDiv div_c) {
   constexpr int N = Vec<T>::N;
   for (uint32_t chunk = blockIdx.x; chunk < A.total_chunks; chunk += gridDim.x) {
     int li = 0;
@@ -265,7 +253,7 @@ template <typename T, int MODE>
 int launch(const Args& A, int layout, cudaStream_t stream) {
   const FastDiv div_c = make_fastdiv((uint32_t)A.C);
   // persistent grid: a multiple of the SM count, capped by the work
-  int ctas = kNumSMs * 8;
+  int ctas = kNumSMs * 16;
   if ((uint32_t)ctas > A.total_chunks) ctas = (int)A.total_chunks;
   if (ctas < 1) return OSD_OK;
   if (layout == OSD_LAYOUT_NCHW) {

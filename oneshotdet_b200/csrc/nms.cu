@@ -24,11 +24,12 @@ namespace osd {
 
 namespace {
 
-constexpr int kSortThreads = 1024;
-constexpr int kSortMaxSmemKeys = 16384;  // 128 KB of 64-bit keys
-constexpr int kMaskRows = 256;           // rows per CTA (one thread per row)
-constexpr int kMaskCols = 512;           // columns per CTA (8 tiles of 64)
+constexpr int kChunk = 2048;         // keys per sort chunk (one CTA each)
+constexpr int kChunkThreads = 512;
+constexpr int kMaskRows = 128;       // rows per mask tile (one thread per row)
+constexpr int kMaskCols = 256;       // columns per mask tile (4 words of 64)
 constexpr int kSweepThreads = 1024;
+constexpr int kSweepNear = 64;       // mask words per row prefetched into shared memory by the sweep
 
 typedef unsigned long long u64;
 
@@ -85,7 +86,10 @@ __device__ __forceinline__ bool box_is_regular(const float4& b, float area) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// 1. sort: one CTA per episode, bitonic network over 64-bit keys (score key << 32 | index) in smem
+// 1. sort: (a) every 2048-key chunk of an episode is sorted by its own CTA (bitonic network in shared memory,
+//    64-bit keys = score key << 32 | candidate index, so keys are unique), (b) every key finds its final
+//    position as  own rank + sum over the other chunks of #keys smaller  (branch-free binary searches) and
+//    scatters its box there.  E x ceil(n/2048) CTAs per kernel: the whole chip works on the sort.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void write_sorted(const CandLayout& L, const NmsWorkspace& W, int e, int pos,
                                              int idx, const int* lvl_prefix, bool& regular) {
@@ -100,111 +104,110 @@ __device__ __forceinline__ void write_sorted(const CandLayout& L, const NmsWorks
   regular = regular && box_is_regular(b, a);
 }
 
-__global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(CandLayout L, NmsWorkspace W) {
-  extern __shared__ u64 skeys[];
+__global__ void __launch_bounds__(kChunkThreads) nms_chunk_sort_kernel(CandLayout L, NmsWorkspace W) {
+  __shared__ u64 sk[kChunk];
   __shared__ int lvl_prefix[OSD_MAX_LEVELS + 1];
-  const int e = blockIdx.x;
-  const int tid = threadIdx.x;
-  int n = episode_count(L, e);
-  n = min(n, W.NP);
+  const int e = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
   fill_level_prefix(L, e, lvl_prefix);
-  int P = 1;
-  while (P < n) P <<= 1;
-  for (int i = tid; i < P; i += kSortThreads) {
-    u64 k = ~0ull;
-    if (i < n) {
-      float s = L.scores[cand_row(L, e, i, lvl_prefix)];
-      k = ((u64)score_key_desc(s) << 32) | (uint32_t)i;
-    }
-    skeys[i] = k;
-  }
-  __syncthreads();
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < (P >> 1); t += kSortThreads) {
-        int i = 2 * t - (t & (j - 1));  // index with bit j clear
-        int l = i + j;
-        u64 a = skeys[i], b = skeys[l];
-        bool up = (i & k) == 0;
-        if ((a > b) == up) {
-          skeys[i] = b;
-          skeys[l] = a;
-        }
-      }
-      __syncthreads();
-    }
-  }
-  bool regular = true;
-  for (int i = tid; i < n; i += kSortThreads)
-    write_sorted(L, W, e, i, (int)(skeys[i] & 0xffffffffu), lvl_prefix, regular);
-  int all_regular = __syncthreads_and(regular ? 1 : 0);
-  if (tid == 0) {
-    W.n[e] = n;
-    W.flags[e] = all_regular ? 1 : 0;
-    W.done[e] = 0;
-    W.kcount[e] = 0;
-  }
-}
-
-// large-N fallback (n > 16384): keys to global, rank by counting (keys are unique, so ranks are a
-// permutation).  O(n^2) compares spread over the whole chip.
-__global__ void __launch_bounds__(256) nms_make_keys_kernel(CandLayout L, NmsWorkspace W) {
-  __shared__ int lvl_prefix[OSD_MAX_LEVELS + 1];
-  const int e = blockIdx.y;
-  fill_level_prefix(L, e, lvl_prefix);
-  int n = min(episode_count(L, e), W.NP);
-  int i = blockIdx.x * 256 + threadIdx.x;
-  if (i < n) {
-    float s = L.scores[cand_row(L, e, i, lvl_prefix)];
-    W.sortkeys[(size_t)e * W.NP + i] = ((u64)score_key_desc(s) << 32) | (uint32_t)i;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  const int n = min(episode_count(L, e), W.NP);
+  if (c == 0 && tid == 0) {
     W.n[e] = n;
     W.flags[e] = 1;
     W.done[e] = 0;
     W.kcount[e] = 0;
   }
+  const int base = c * kChunk;
+  if (base >= n) return;
+  const int len = min(kChunk, n - base);
+  int P = 1;
+  while (P < len) P <<= 1;
+  for (int i = tid; i < P; i += kChunkThreads) {
+    u64 k = ~0ull;
+    if (i < len) {
+      float s = L.scores[cand_row(L, e, base + i, lvl_prefix)];
+      k = ((u64)score_key_desc(s) << 32) | (uint32_t)(base + i);
+    }
+    sk[i] = k;
+  }
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (P >> 1); t += kChunkThreads) {
+        const int i = 2 * t - (t & (j - 1));  // index with bit j clear
+        const int l = i + j;
+        const u64 a = sk[i], b = sk[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) {
+          sk[i] = b;
+          sk[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  u64* out = W.sortkeys + (size_t)e * W.NP + base;
+  for (int i = tid; i < len; i += kChunkThreads) out[i] = sk[i];
 }
 
-__global__ void __launch_bounds__(256) nms_rank_sort_kernel(CandLayout L, NmsWorkspace W) {
-  __shared__ u64 tile[256];
+__global__ void __launch_bounds__(kChunkThreads) nms_merge_kernel(CandLayout L, NmsWorkspace W) {
   __shared__ int lvl_prefix[OSD_MAX_LEVELS + 1];
-  const int e = blockIdx.y;
-  const int n = min(episode_count(L, e), W.NP);
-  if (blockIdx.x * 256 >= n) return;
+  const int e = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
+  const int n = W.n[e];
+  const int base = c * kChunk;
+  if (base >= n) return;
   fill_level_prefix(L, e, lvl_prefix);
-  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int len = min(kChunk, n - base);
+  const int nchunks = (n + kChunk - 1) / kChunk;
   const u64* keys = W.sortkeys + (size_t)e * W.NP;
-  u64 mine = (i < n) ? keys[i] : ~0ull;
-  int rank = 0;
-  for (int j0 = 0; j0 < n; j0 += 256) {
-    int j = j0 + threadIdx.x;
-    tile[threadIdx.x] = (j < n) ? keys[j] : ~0ull;
-    __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < 256; ++k) rank += (tile[k] < mine) ? 1 : 0;
-    __syncthreads();
-  }
   bool regular = true;
-  if (i < n) write_sorted(L, W, e, rank, i, lvl_prefix, regular);
+  for (int i = tid; i < len; i += kChunkThreads) {
+    const u64 key = keys[base + i];
+    int rank = i;
+    for (int c0 = 0; c0 < nchunks; c0 += 8) {
+      int pos[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pos[q] = 0;
+      // lower_bound in up to 8 other chunks at once (independent loads in flight)
+#pragma unroll 1
+      for (int step = kChunk; step >= 1; step >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int c2 = c0 + q;
+          if (c2 < nchunks && c2 != c) {
+            const int len2 = min(kChunk, n - c2 * kChunk);
+            const int probe = pos[q] + step;
+            if (probe <= len2 && keys[c2 * kChunk + probe - 1] < key) pos[q] = probe;
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) rank += pos[q];
+    }
+    write_sorted(L, W, e, rank, (int)(key & 0xffffffffu), lvl_prefix, regular);
+  }
   if (!regular) atomicAnd(&W.flags[e], 0);
 }
 
 // ------------------------------------------------------------------------------------------------
-// 2. IoU bitmask: CTA = 256 rows x 512 columns; thread = one row, 64 pairs per 64-bit word
+// 2. IoU bitmask.  Persistent CTAs walk (row block of 128) x (column group of 256) tiles of all episodes;
+//    thread = one row, 64 pairs per 64-bit word, column boxes broadcast from shared memory.
+//    The inner loop is branch-free: two masks are built per word -- `sub` (inter > thr_hi*u: certainly
+//    suppressed) and `sup` (inter >= thr_lo*u: possibly suppressed); only bits in sup & ~sub (IoU within
+//    4e-6 of the threshold) take the IEEE division afterwards.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool iou_hit_fast(const float4& a, float aa, const float4& b, float ba,
-                                             const IouTest& T) {
-  float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
-  float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
-  float w = fmaxf(__fadd_rn(__fsub_rn(xx2, xx1), 1.0f), 0.0f);
-  float h = fmaxf(__fadd_rn(__fsub_rn(yy2, yy1), 1.0f), 0.0f);
-  float inter = __fmul_rn(w, h);
-  float u = __fsub_rn(__fadd_rn(aa, ba), inter);
-  if (inter > __fmul_rn(T.thr_hi, u)) return true;
-  if (inter < __fmul_rn(T.thr_lo, u)) return false;
-  float q = __fdiv_rn(inter, u);
-  return T.strict ? (q > T.thr) : (q >= T.thr);
+struct PairTerms {
+  float inter, uni;
+};
+
+__device__ __forceinline__ PairTerms pair_terms(const float4& a, float aa, const float4& b, float ba) {
+  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  const float w = fmaxf(__fadd_rn(__fsub_rn(xx2, xx1), 1.0f), 0.0f);
+  const float h = fmaxf(__fadd_rn(__fsub_rn(yy2, yy1), 1.0f), 0.0f);
+  PairTerms t;
+  t.inter = __fmul_rn(w, h);
+  t.uni = __fsub_rn(__fadd_rn(aa, ba), t.inter);
+  return t;
 }
 
 // std::max / std::min semantics of nms_cpu.cpp:51-57, `a` is the earlier (suppressing) box
@@ -222,83 +225,118 @@ __device__ __forceinline__ bool iou_hit_exact(const float4& a, float aa, const f
   return T.strict ? (q > T.thr) : (q >= T.thr);
 }
 
+// Both compares become integer subtractions whose sign bit is funnel-shifted into the mask (1 IADD + 1 SHF per
+// compare instead of FSETP + SEL + LOP3): every operand is a non-negative finite float in a regular episode, so
+// the float order equals the order of the bit patterns.  Bits arrive MSB-first and are reversed per 32 pairs.
+__device__ __forceinline__ void pair_bits(const float4& rb, float ra, const float4& cb, float ca, const IouTest& T,
+                                          uint32_t& sub, uint32_t& sup) {
+  const PairTerms t = pair_terms(rb, ra, cb, ca);
+  const int ib = __float_as_int(t.inter);
+  const int d_hi = __float_as_int(__fmul_rn(T.thr_hi, t.uni)) - ib;      // < 0  <=>  inter >  thr_hi * u
+  const int d_lo = __float_as_int(__fmul_rn(T.thr_lo, t.uni)) - ib - 1;  // < 0  <=>  inter >= thr_lo * u
+  sub = __funnelshift_l((uint32_t)d_hi, sub, 1);
+  sup = __funnelshift_l((uint32_t)d_lo, sup, 1);
+}
+
+__device__ __forceinline__ u64 row_word_fast(const float4& rb, float ra, const float4* __restrict__ cb,
+                                             const float* __restrict__ ca, const IouTest& T) {
+  uint32_t sub_lo = 0, sub_hi = 0, sup_lo = 0, sup_hi = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) pair_bits(rb, ra, cb[j], ca[j], T, sub_lo, sup_lo);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) pair_bits(rb, ra, cb[32 + j], ca[32 + j], T, sub_hi, sup_hi);
+  u64 sub = ((u64)__brev(sub_hi) << 32) | __brev(sub_lo);
+  u64 amb = (((u64)__brev(sup_hi) << 32) | __brev(sup_lo)) & ~sub;
+  while (amb) {  // rare: IoU within 2^-18 of the threshold -> decide with the IEEE division
+    const int j = __ffsll((long long)amb) - 1;
+    amb &= amb - 1ull;
+    const PairTerms t = pair_terms(rb, ra, cb[j], ca[j]);
+    const float q = __fdiv_rn(t.inter, t.uni);
+    if (T.strict ? (q > T.thr) : (q >= T.thr)) sub |= (1ull << j);
+  }
+  return sub;
+}
+
 struct MaskArgs {
   int row_begin, row_end;  // rows (visiting positions) this launch covers, multiples of 64
   int col_begin, col_end;  // columns this launch covers, multiples of 64
+  int tiles_r, tiles_c;    // tile grid per episode
   IouTest test;
 };
 
 __global__ void __launch_bounds__(kMaskRows) nms_mask_kernel(NmsWorkspace W, MaskArgs A) {
   __shared__ float4 cbox[kMaskCols];
   __shared__ float carea[kMaskCols];
-  const int e = blockIdx.z;
-  if (W.done[e]) return;
-  const int n = W.n[e];
-  const int row0 = A.row_begin + blockIdx.y * kMaskRows;
-  const int col0 = A.col_begin + blockIdx.x * kMaskCols;
-  const int row_end = min(n, A.row_end);
-  const int col_end = min(n, A.col_end);
-  if (row0 >= row_end || col0 >= col_end) return;
-  if (col0 + kMaskCols <= row0) return;  // every column precedes every row of this CTA
-  const float4* sbox = W.sbox + (size_t)e * W.NP;
-  const float* sarea = W.sarea + (size_t)e * W.NP;
-  const int ncols = min(kMaskCols, col_end - col0);
-  for (int c = threadIdx.x; c < ncols; c += kMaskRows) {
-    cbox[c] = sbox[col0 + c];
-    carea[c] = sarea[col0 + c];
-  }
-  __syncthreads();
-  const int i = row0 + threadIdx.x;
-  if (i >= row_end) return;
-  const float4 rb = sbox[i];
-  const float ra = sarea[i];
-  const bool exact = A.test.force_exact || !(W.flags[e] & 1);
-  const int row_tile0 = i & ~63;
-  const int il = i & 63;
-  u64* mrow = W.mask + ((size_t)e * W.NP + i) * W.NW;
-  for (int t = 0; t < kMaskCols / 64; ++t) {
-    const int ct0 = col0 + 64 * t;
-    if (ct0 >= col_end) break;
-    if (ct0 < row_tile0) continue;  // warp-uniform: 32 consecutive rows share a 64-row tile
-    const int nc = min(64, col_end - ct0);
-    const bool diag = (ct0 == row_tile0);
-    uint32_t lo = 0, hi = 0;
-    if (!exact) {
-#pragma unroll 16
-      for (int j = 0; j < 32; ++j) {
-        if (iou_hit_fast(rb, ra, cbox[64 * t + j], carea[64 * t + j], A.test)) lo |= (1u << j);
-      }
-#pragma unroll 16
-      for (int j = 0; j < 32; ++j) {
-        if (iou_hit_fast(rb, ra, cbox[64 * t + 32 + j], carea[64 * t + 32 + j], A.test)) hi |= (1u << j);
-      }
-    } else {
-      for (int j = 0; j < 64; ++j) {
-        const float4 cb = cbox[64 * t + j];
-        const float ca = carea[64 * t + j];
-        // below the diagonal the column box is the earlier one
-        bool hit = (diag && j < il) ? iou_hit_exact(cb, ca, rb, ra, A.test)
-                                    : iou_hit_exact(rb, ra, cb, ca, A.test);
-        if (hit) {
-          if (j < 32) lo |= (1u << j);
-          else hi |= (1u << (j - 32));
+  const int total = W.E * A.tiles_r * A.tiles_c;
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    // episode fastest: neighbouring CTAs work on tiles of equal cost
+    const int e = t % W.E;
+    const int rc = t / W.E;
+    const int rbi = rc / A.tiles_c, cgi = rc - rbi * A.tiles_c;
+    if (W.done[e]) continue;
+    const int n = W.n[e];
+    const int row0 = A.row_begin + rbi * kMaskRows;
+    const int col0 = A.col_begin + cgi * kMaskCols;
+    const int row_end = min(n, A.row_end);
+    const int col_end = min(n, A.col_end);
+    if (row0 >= row_end || col0 >= col_end) continue;
+    if (col0 + kMaskCols <= row0) continue;  // every column precedes every row of this tile
+    const float4* sbox = W.sbox + (size_t)e * W.NP;
+    const float* sarea = W.sarea + (size_t)e * W.NP;
+    const int ncols = min(kMaskCols, col_end - col0);
+    __syncthreads();  // the previous tile's readers are done with cbox
+    for (int c = threadIdx.x; c < kMaskCols; c += kMaskRows) {
+      // columns past the end are padded with the first column (finite, regular; their bits are masked off)
+      const int cc = col0 + (c < ncols ? c : 0);
+      cbox[c] = sbox[cc];
+      carea[c] = sarea[cc];
+    }
+    __syncthreads();
+    const int i = row0 + threadIdx.x;
+    if (i >= row_end) continue;
+    const float4 rb = sbox[i];
+    const float ra = sarea[i];
+    const bool exact = A.test.force_exact || !(W.flags[e] & 1);
+    const int row_tile0 = i & ~63;
+    const int il = i & 63;
+    u64* mrow = W.mask + ((size_t)e * W.NP + i) * W.NW;
+    for (int tt = 0; tt < kMaskCols / 64; ++tt) {
+      const int ct0 = col0 + 64 * tt;
+      if (ct0 >= col_end) break;
+      if (ct0 < row_tile0) continue;  // warp-uniform: 32 consecutive rows share a 64-row tile
+      const int nc = min(64, col_end - ct0);
+      const bool diag = (ct0 == row_tile0);
+      u64 bits = 0ull;
+      if (!exact) {
+        bits = row_word_fast(rb, ra, cbox + 64 * tt, carea + 64 * tt, A.test);
+      } else {
+        for (int j = 0; j < nc; ++j) {
+          const float4 cb = cbox[64 * tt + j];
+          const float ca = carea[64 * tt + j];
+          // below the diagonal the column box is the earlier one
+          const bool hit = (diag && j < il) ? iou_hit_exact(cb, ca, rb, ra, A.test)
+                                            : iou_hit_exact(rb, ra, cb, ca, A.test);
+          if (hit) bits |= (1ull << j);
         }
       }
+      if (nc < 64) bits &= (1ull << nc) - 1ull;
+      if (diag) {
+        const u64 below = (il == 0) ? 0ull : (bits & ((1ull << il) - 1ull));
+        const u64 above = (il == 63) ? 0ull : (bits & ~((2ull << il) - 1ull));
+        W.diagcol[(size_t)e * W.NP + i] = below;
+        bits = above;
+      }
+      mrow[ct0 >> 6] = bits;
     }
-    u64 bits = ((u64)hi << 32) | lo;
-    if (nc < 64) bits &= (1ull << nc) - 1ull;  // smem beyond ncols is stale
-    if (diag) {
-      const u64 below = (il == 0) ? 0ull : (bits & ((1ull << il) - 1ull));
-      const u64 above = (il == 63) ? 0ull : (bits & ~((2ull << il) - 1ull));
-      W.diagcol[(size_t)e * W.NP + i] = below;
-      bits = above;
-    }
-    mrow[ct0 >> 6] = bits;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// 3. sweep: one CTA per episode walks the 64-box blocks in visiting order
+// 3. sweep: one CTA per episode walks the 64-box blocks in visiting order.  Per block: warp 0 resolves the
+//    64 boxes against each other (ballot fixpoint on the transposed diagonal bits), then all threads OR the
+//    mask rows of the kept boxes into the suppression words of the later blocks.  The rows of the next two
+//    blocks are prefetched into shared memory with cp.async while the current block is resolved, so the
+//    serial chain never waits for L2.
 // ------------------------------------------------------------------------------------------------
 struct SweepArgs {
   int blk_begin;  // first 64-box block of this pass
@@ -308,8 +346,31 @@ struct SweepArgs {
   int passthrough;
 };
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void sweep_prefetch(const u64* __restrict__ mask, const u64* __restrict__ dc, int NW,
+                                               int blk, int wlim, u64* rowbuf, u64* dcb) {
+  const int nnear = min(kSweepNear, wlim - (blk + 1));
+  const int total = 64 * nnear;  // <= 0 when there is no later word
+  for (int idx = threadIdx.x; idx < total; idx += kSweepThreads) {
+    const int r = idx / nnear, wi = idx - r * nnear;
+    cp_async8(&rowbuf[r * kSweepNear + wi], &mask[(size_t)(64 * blk + r) * NW + blk + 1 + wi]);
+  }
+  if (threadIdx.x < 64) cp_async8(&dcb[threadIdx.x], &dc[64 * blk + threadIdx.x]);
+}
+
 __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W, SweepArgs A) {
-  extern __shared__ u64 rem[];  // NW words: boxes already suppressed
+  extern __shared__ u64 sweep_smem[];
+  // layout: rem[NW] | rowbuf[3][64][kSweepNear] | dcb[3][64]
+  u64* rem = sweep_smem;
+  u64* rowbuf = sweep_smem + W.NW;
+  u64* dcb = rowbuf + 3 * 64 * kSweepNear;
   __shared__ int s_rows[64];
   __shared__ int s_nk;
   const int e = blockIdx.x;
@@ -337,11 +398,17 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W
   const u64* dc = W.diagcol + (size_t)e * W.NP;
   const int wlim = min(A.word_end, nblk);
   const int blim = min(A.blk_end, nblk);
+  const int nb = blim - A.blk_begin;  // blocks swept by this pass (may be <= 0)
+  // start the prefetch pipeline (two blocks deep) before anything else
+  if (nb > 0) sweep_prefetch(mask, dc, W.NW, A.blk_begin, wlim, rowbuf, dcb);
+  cp_async_commit();
+  if (nb > 1) sweep_prefetch(mask, dc, W.NW, A.blk_begin + 1, wlim, rowbuf + 64 * kSweepNear, dcb + 64);
+  cp_async_commit();
   for (int w = tid; w < W.NW; w += kSweepThreads) rem[w] = 0ull;
   __syncthreads();
   int count = W.kcount[e];
   if (A.blk_begin > 0) {
-    // rebuild the suppression state of columns >= blk_begin from the boxes kept by the earlier pass
+    // rebuild the suppression state of columns >= blk_begin from the boxes kept by the earlier passes
     for (int r = warp; r < A.blk_begin * 64; r += kSweepThreads / 32) {
       if ((kb[r >> 6] >> (r & 63)) & 1ull) {
         const u64* mrow = mask + (size_t)r * W.NW;
@@ -351,24 +418,30 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W
         }
       }
     }
-    __syncthreads();
   }
-  int blk = A.blk_begin;
-  for (; blk < blim; ++blk) {
+  int it = 0;
+  for (; it < nb; ++it) {
+    const int blk = A.blk_begin + it;
+    const int cur = it % 3;
+    cp_async_wait<1>();  // this block's rows (committed two groups ago) have landed
+    __syncthreads();     // ... for every thread; the previous block's ORs into rem[] are complete
+    if (it + 2 < nb)
+      sweep_prefetch(mask, dc, W.NW, blk + 2, wlim, rowbuf + ((it + 2) % 3) * 64 * kSweepNear, dcb + ((it + 2) % 3) * 64);
+    cp_async_commit();
     if (warp == 0) {
       const int nv = min(64, n - 64 * blk);
       const u64 vmask = nv == 64 ? ~0ull : ((1ull << nv) - 1ull);
       const u64 free_ = ~rem[blk] & vmask;
-      const u64 c_lo = dc[64 * blk + lane];
-      const u64 c_hi = dc[64 * blk + 32 + lane];
+      const u64 c_lo = dcb[cur * 64 + lane];
+      const u64 c_hi = dcb[cur * 64 + 32 + lane];
       u64 kept = free_;
       uint32_t lo, hi;
       while (true) {
-        bool a = ((free_ >> lane) & 1ull) && ((c_lo & kept) == 0ull);
-        bool b = ((free_ >> (lane + 32)) & 1ull) && ((c_hi & kept) == 0ull);
+        const bool a = ((free_ >> lane) & 1ull) && ((c_lo & kept) == 0ull);
+        const bool b = ((free_ >> (lane + 32)) & 1ull) && ((c_hi & kept) == 0ull);
         lo = __ballot_sync(0xffffffffu, a);
         hi = __ballot_sync(0xffffffffu, b);
-        u64 nk = ((u64)hi << 32) | lo;
+        const u64 nk = ((u64)hi << 32) | lo;
         if (nk == kept) break;
         kept = nk;
       }
@@ -385,22 +458,32 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W
     count += nk;
     {
       const int g = tid >> 8, wl = tid & 255;
-      for (int w = blk + 1 + wl; w < wlim; w += 256) {
+      const int nnear = min(kSweepNear, wlim - (blk + 1));
+      const u64* rb = rowbuf + cur * 64 * kSweepNear;
+      for (int wi = wl; wi < nnear; wi += 256) {
+        u64 acc = 0ull;
+        for (int r = g; r < nk; r += 4) acc |= rb[s_rows[r] * kSweepNear + wi];
+        if (acc) atomicOr(&rem[blk + 1 + wi], acc);
+      }
+      // words beyond the prefetched window come straight from L2
+      for (int w = blk + 1 + kSweepNear + wl; w < wlim; w += 256) {
         u64 acc = 0ull;
 #pragma unroll 4
         for (int r = g; r < nk; r += 4) acc |= mask[(size_t)(64 * blk + s_rows[r]) * W.NW + w];
         if (acc) atomicOr(&rem[w], acc);
       }
     }
-    __syncthreads();
     if (count >= A.stop) {
-      ++blk;
+      ++it;
       break;
     }
   }
-  const bool finished = (count >= A.stop) || (blk >= nblk);
+  cp_async_wait<0>();
+  __syncthreads();
+  const int blk_next = A.blk_begin + (nb > 0 ? it : 0);
+  const bool finished = (count >= A.stop) || (blk_next >= nblk);
   if (finished) {
-    for (int w = blk + tid; w < W.NW; w += kSweepThreads) kb[w] = 0ull;
+    for (int w = blk_next + tid; w < W.NW; w += kSweepThreads) kb[w] = 0ull;
   }
   if (tid == 0) {
     W.kcount[e] = count;
@@ -518,16 +601,10 @@ size_t nms_workspace_carve(Carver& c, int64_t E, int64_t max_len, NmsWorkspace* 
   w.kcount = c.take<int32_t>(E);
   w.diagcol = c.take<unsigned long long>(E * NP);
   w.keptbits = c.take<unsigned long long>(E * NW);
-  w.sortkeys = (max_len > kSortMaxSmemKeys) ? c.take<unsigned long long>(E * NP) : nullptr;
+  w.sortkeys = c.take<unsigned long long>(E * NP);
   w.mask = c.take<unsigned long long>(E * NP * NW);
   if (ws) *ws = w;
   return c.total();
-}
-
-static int next_pow2(int v) {
-  int p = 1;
-  while (p < v) p <<= 1;
-  return p;
 }
 
 int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, const NmsOutputs& O,
@@ -538,33 +615,23 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
   OSD_REQUIRE(max_len <= W.NP, "nms: max_len %d exceeds the planned capacity %d", max_len, W.NP);
   OSD_REQUIRE(E <= 65535, "nms: at most 65535 segments per call (got %d)", E);
 
-  // ---- sort
-  if (max_len <= kSortMaxSmemKeys) {
-    const int Pmax = next_pow2(max_len > 1 ? max_len : 1);
-    const size_t smem = (size_t)Pmax * sizeof(u64);
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      OSD_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(kSortMaxSmemKeys * sizeof(u64))));
-      configured = kSortMaxSmemKeys * sizeof(u64);
-    }
-    nms_sort_kernel<<<E, kSortThreads, smem, stream>>>(L, W);
-    OSD_LAUNCH_CHECK("nms_sort_kernel");
-  } else {
-    dim3 g((unsigned)ceil_div(max_len, 256), (unsigned)E);
-    nms_make_keys_kernel<<<g, 256, 0, stream>>>(L, W);
-    OSD_LAUNCH_CHECK("nms_make_keys_kernel");
-    nms_rank_sort_kernel<<<g, 256, 0, stream>>>(L, W);
-    OSD_LAUNCH_CHECK("nms_rank_sort_kernel");
+  // ---- sort: chunk sort + merge by rank
+  {
+    dim3 g((unsigned)ceil_div(max_len > 0 ? max_len : 1, kChunk), (unsigned)E);
+    nms_chunk_sort_kernel<<<g, kChunkThreads, 0, stream>>>(L, W);
+    OSD_LAUNCH_CHECK("nms_chunk_sort_kernel");
+    nms_merge_kernel<<<g, kChunkThreads, 0, stream>>>(L, W);
+    OSD_LAUNCH_CHECK("nms_merge_kernel");
   }
 
-  // ---- mask + sweep (one pass, or a short first pass when an early exit is likely)
-  const size_t sweep_smem = (size_t)W.NW * sizeof(u64);
+  // ---- mask + sweep, in passes over growing prefixes of the visiting order.  Without early exit there is one
+  //      pass; with it, the first pass covers just enough boxes to keep post_top_n + 1 if little is suppressed,
+  //      the second a 30 % larger prefix, the last everything.  Finished episodes skip later passes on the device.
+  const size_t sweep_smem = ((size_t)W.NW + 3 * 64 * kSweepNear + 3 * 64) * sizeof(u64);
   {
     static thread_local size_t configured = 48 * 1024;
     if (sweep_smem > configured) {
-      OSD_REQUIRE(sweep_smem <= 200 * 1024, "nms: %d candidates per episode exceed the sweep capacity",
-                  max_len);
+      OSD_REQUIRE(sweep_smem <= 220 * 1024, "nms: %d candidates per episode exceed the sweep capacity", max_len);
       OSD_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sweep_smem));
       configured = sweep_smem;
@@ -589,38 +656,36 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
     const int NPu = (int)align_up((size_t)(max_len > 0 ? max_len : 1), 64);
     const bool early = P.early_exit && P.post_top_n > 0;
     S.stop = early ? P.post_top_n + 1 : INT_MAX;
-    int R1 = NPu;
+    int bounds[3];
+    int npass = 0;
     if (early) {
-      int64_t guess = (int64_t)P.post_top_n + P.post_top_n / 4 + 128;
-      R1 = (int)std::min<int64_t>(NPu, (int64_t)align_up((size_t)guess, 64));
+      const int b1 = (int)align_up((size_t)P.post_top_n + 1, 64) + 64;
+      const int b2 = (int)align_up((size_t)((int64_t)P.post_top_n + (3 * (int64_t)P.post_top_n) / 10 + 128), 64);
+      if (b1 < NPu) bounds[npass++] = b1;
+      if (b2 < NPu && b2 > b1) bounds[npass++] = b2;
     }
-    // pass 1: boxes [0, R1) against each other
-    M.row_begin = 0;
-    M.row_end = R1;
-    M.col_begin = 0;
-    M.col_end = R1;
-    dim3 g1((unsigned)ceil_div(R1, kMaskCols), (unsigned)ceil_div(R1, kMaskRows), (unsigned)E);
-    nms_mask_kernel<<<g1, kMaskRows, 0, stream>>>(W, M);
-    OSD_LAUNCH_CHECK("nms_mask_kernel");
-    S.blk_begin = 0;
-    S.blk_end = R1 / 64;
-    S.word_end = R1 / 64;
-    nms_sweep_kernel<<<E, kSweepThreads, sweep_smem, stream>>>(W, S);
-    OSD_LAUNCH_CHECK("nms_sweep_kernel");
-    if (R1 < NPu) {
-      // pass 2 (skipped on the device for episodes that already finished): all rows against columns >= R1
+    bounds[npass++] = NPu;
+    int prev = 0;
+    for (int p = 0; p < npass; ++p) {
+      const int hi = bounds[p];
+      // boxes [0, hi) against the new columns [prev, hi)
       M.row_begin = 0;
-      M.row_end = NPu;
-      M.col_begin = R1;
-      M.col_end = NPu;
-      dim3 g2((unsigned)ceil_div(NPu - R1, kMaskCols), (unsigned)ceil_div(NPu, kMaskRows), (unsigned)E);
-      nms_mask_kernel<<<g2, kMaskRows, 0, stream>>>(W, M);
+      M.row_end = hi;
+      M.col_begin = prev;
+      M.col_end = hi;
+      M.tiles_r = (int)ceil_div(hi, kMaskRows);
+      M.tiles_c = (int)ceil_div(hi - prev, kMaskCols);
+      const int64_t tiles = (int64_t)E * M.tiles_r * M.tiles_c;
+      OSD_REQUIRE(tiles < (1ll << 31), "nms: too many mask tiles");
+      const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * 12);
+      nms_mask_kernel<<<grid, kMaskRows, 0, stream>>>(W, M);
       OSD_LAUNCH_CHECK("nms_mask_kernel");
-      S.blk_begin = R1 / 64;
-      S.blk_end = INT_MAX;
-      S.word_end = INT_MAX;
+      S.blk_begin = prev / 64;
+      S.blk_end = hi / 64;
+      S.word_end = hi / 64;
       nms_sweep_kernel<<<E, kSweepThreads, sweep_smem, stream>>>(W, S);
       OSD_LAUNCH_CHECK("nms_sweep_kernel");
+      prev = hi;
     }
   }
 

@@ -1,0 +1,80 @@
+"""CPU, world_size 2 over gloo: the episode sharding and the fixed-shape detection all-gather that replace the
+reference's pickle all_gather (maskrcnn_benchmark/utils/comm.py:48-88, engine/inference.py:133-152)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oneshotdet_b200.distributed import gather_detections, shard_range, unpack_detections
+
+
+def test_shard_range_partitions_contiguously():
+    for n in (0, 1, 7, 16, 128, 129):
+        for ws in (1, 2, 3, 8):
+            spans = [shard_range(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, total_eps, k, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard_range(total_eps, rank, world)
+        e_local = -(-total_eps // world)           # padded so that every rank sends the same shape
+        g = torch.Generator().manual_seed(1234)    # same stream on every rank: global ground truth
+        all_boxes = torch.rand(total_eps, k, 4, generator=g)
+        all_scores = torch.rand(total_eps, k, generator=g)
+        all_counts = torch.randint(0, k + 1, (total_eps,), generator=g, dtype=torch.int32)
+        dets = torch.full((e_local, k, 6), -1.0)
+        counts = torch.zeros(e_local, dtype=torch.int32)
+        n = hi - lo
+        dets[:n, :, :4] = all_boxes[lo:hi]
+        dets[:n, :, 4] = all_scores[lo:hi]
+        dets[:n, :, 5] = torch.arange(lo, hi, dtype=torch.float32).view(n, 1)
+        counts[:n] = all_counts[lo:hi]
+        gd, gc = gather_detections(dets, counts)
+        assert gd.shape == (world * e_local, k, 6) and gc.shape == (world * e_local,)
+        out = unpack_detections(gd, gc, total_eps)
+        ok = len(out) == total_eps
+        for e, (b, s) in enumerate(out):
+            c = int(all_counts[e])
+            ok = ok and torch.equal(b, all_boxes[e, :c]) and torch.equal(s, all_scores[e, :c])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total_eps", [8, 7])
+def test_gather_detections_world_size_2(total_eps):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, total_eps, 5, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_single_process_is_identity():
+    d = torch.zeros(3, 4, 6)
+    c = torch.zeros(3, dtype=torch.int32)
+    gd, gc = gather_detections(d, c)
+    assert gd is d and gc is c
