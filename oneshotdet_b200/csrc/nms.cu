@@ -26,9 +26,10 @@ namespace {
 
 constexpr int kChunk = 2048;         // keys per sort chunk (one CTA each)
 constexpr int kChunkThreads = 512;
+constexpr int kMergeStage = 6 * kChunk;   // keys staged per window by the merge kernel (96 KB)
 constexpr int kMaskRows = 128;       // rows per mask tile (one thread per row)
 constexpr int kMaskCols = 256;       // columns per mask tile (4 words of 64)
-constexpr int kSweepThreads = 1024;
+constexpr int kSweepThreads = 512;
 constexpr int kSweepNear = 64;       // mask words per row prefetched into shared memory by the sweep
 
 typedef unsigned long long u64;
@@ -104,6 +105,15 @@ __device__ __forceinline__ void write_sorted(const CandLayout& L, const NmsWorks
   regular = regular && box_is_regular(b, a);
 }
 
+// Bitonic network over the 2048 keys of a chunk; thread t holds elements 4t..4t+3 in registers.  Exchange
+// distances 1-2 stay inside the thread, 4-64 are warp shuffles, only distances >= 128 go through shared memory
+// (10 of the 66 stages).
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int lane_mask) {
+  const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, lane_mask);
+  const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), lane_mask);
+  return ((u64)hi << 32) | lo;
+}
+
 __global__ void __launch_bounds__(kChunkThreads) nms_chunk_sort_kernel(CandLayout L, NmsWorkspace W) {
   __shared__ u64 sk[kChunk];
   __shared__ int lvl_prefix[OSD_MAX_LEVELS + 1];
@@ -115,41 +125,99 @@ __global__ void __launch_bounds__(kChunkThreads) nms_chunk_sort_kernel(CandLayou
     W.flags[e] = 1;
     W.done[e] = 0;
     W.kcount[e] = 0;
+    if (e == 0) {
+      W.sched[0] = 0;  // episodes finished
+      W.sched[1] = W.sched[2] = W.sched[3] = 0;  // mask tile counters of the passes
+    }
   }
   const int base = c * kChunk;
   if (base >= n) return;
   const int len = min(kChunk, n - base);
-  int P = 1;
-  while (P < len) P <<= 1;
-  for (int i = tid; i < P; i += kChunkThreads) {
+  u64 r[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int i = 4 * tid + s;
     u64 k = ~0ull;
     if (i < len) {
-      float s = L.scores[cand_row(L, e, base + i, lvl_prefix)];
-      k = ((u64)score_key_desc(s) << 32) | (uint32_t)(base + i);
+      const float sc = L.scores[cand_row(L, e, base + i, lvl_prefix)];
+      k = ((u64)score_key_desc(sc) << 32) | (uint32_t)(base + i);
     }
-    sk[i] = k;
+    r[s] = k;
   }
-  __syncthreads();
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < (P >> 1); t += kChunkThreads) {
-        const int i = 2 * t - (t & (j - 1));  // index with bit j clear
-        const int l = i + j;
-        const u64 a = sk[i], b = sk[l];
-        const bool up = (i & k) == 0;
-        if ((a > b) == up) {
-          sk[i] = b;
-          sk[l] = a;
-        }
-      }
+  for (int k = 2; k <= kChunk; k <<= 1) {
+    int j = k >> 1;
+    if (j >= 128) {
+      // wide exchanges through shared memory
+#pragma unroll
+      for (int s = 0; s < 4; ++s) sk[4 * tid + s] = r[s];
       __syncthreads();
+      for (; j >= 128; j >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int t = tid + u * kChunkThreads;
+          const int i = 2 * t - (t & (j - 1));
+          const int l = i + j;
+          const u64 a = sk[i], b = sk[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            sk[i] = b;
+            sk[l] = a;
+          }
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) r[s] = sk[4 * tid + s];
+      __syncthreads();  // sk is rewritten by the next wide phase
+    }
+    for (; j >= 4; j >>= 1) {
+      // partner element lives in lane ^ (j/4), same register slot
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int i = 4 * tid + s;
+        const u64 other = shfl_xor_u64(r[s], j >> 2);
+        const bool up = (i & k) == 0;
+        const bool lower = (i & j) == 0;
+        const bool take_min = (lower == up);
+        const u64 mn = r[s] < other ? r[s] : other;
+        const u64 mx = r[s] < other ? other : r[s];
+        r[s] = take_min ? mn : mx;
+      }
+    }
+    // distances 2 and 1 stay inside the thread (static register indices)
+    if (k >= 4) {
+      const bool up = ((4 * tid) & k) == 0;
+      if ((r[0] > r[2]) == up) { const u64 t0 = r[0]; r[0] = r[2]; r[2] = t0; }
+      if ((r[1] > r[3]) == up) { const u64 t1 = r[1]; r[1] = r[3]; r[3] = t1; }
+    }
+    {
+      const bool up01 = ((4 * tid) & k) == 0;      // element 4t   (bit 1 clear)
+      const bool up23 = ((4 * tid + 2) & k) == 0;  // element 4t+2
+      if ((r[0] > r[1]) == up01) { const u64 t0 = r[0]; r[0] = r[1]; r[1] = t0; }
+      if ((r[2] > r[3]) == up23) { const u64 t1 = r[2]; r[2] = r[3]; r[3] = t1; }
     }
   }
   u64* out = W.sortkeys + (size_t)e * W.NP + base;
-  for (int i = tid; i < len; i += kChunkThreads) out[i] = sk[i];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int i = 4 * tid + s;
+    if (i < len) out[i] = r[s];
+  }
+}
+
+// lower_bound (number of keys < key) in a sorted run of `len2` <= kChunk keys; fixed 12 probes, no branches
+__device__ __forceinline__ int count_less(const u64* __restrict__ run, int len2, u64 key) {
+  int pos = 0;
+#pragma unroll
+  for (int step = kChunk; step >= 1; step >>= 1) {
+    const int probe = pos + step;
+    if (probe <= len2 && run[probe - 1] < key) pos = probe;
+  }
+  return pos;
 }
 
 __global__ void __launch_bounds__(kChunkThreads) nms_merge_kernel(CandLayout L, NmsWorkspace W) {
+  extern __shared__ u64 staged[];  // up to kMergeStage sorted keys of the other chunks
   __shared__ int lvl_prefix[OSD_MAX_LEVELS + 1];
   const int e = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
   const int n = W.n[e];
@@ -157,33 +225,34 @@ __global__ void __launch_bounds__(kChunkThreads) nms_merge_kernel(CandLayout L, 
   if (base >= n) return;
   fill_level_prefix(L, e, lvl_prefix);
   const int len = min(kChunk, n - base);
-  const int nchunks = (n + kChunk - 1) / kChunk;
   const u64* keys = W.sortkeys + (size_t)e * W.NP;
-  bool regular = true;
-  for (int i = tid; i < len; i += kChunkThreads) {
-    const u64 key = keys[base + i];
-    int rank = i;
-    for (int c0 = 0; c0 < nchunks; c0 += 8) {
-      int pos[8];
+  // own keys (4 per thread) and their running ranks
+  u64 mine[4];
+  int rank[4];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) pos[q] = 0;
-      // lower_bound in up to 8 other chunks at once (independent loads in flight)
-#pragma unroll 1
-      for (int step = kChunk; step >= 1; step >>= 1) {
+  for (int s = 0; s < 4; ++s) {
+    const int i = tid + s * kChunkThreads;
+    mine[s] = (i < len) ? keys[base + i] : ~0ull;
+    rank[s] = i;
+  }
+  // walk the episode's keys in windows that fit in shared memory; every window holds whole chunks
+  for (int w0 = 0; w0 < n; w0 += kMergeStage) {
+    const int wn = min(kMergeStage, n - w0);
+    __syncthreads();
+    for (int i = tid; i < wn; i += kChunkThreads) staged[i] = keys[w0 + i];
+    __syncthreads();
+    for (int c2off = 0; c2off < wn; c2off += kChunk) {
+      if (w0 + c2off == base) continue;  // own chunk
+      const int len2 = min(kChunk, wn - c2off);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int c2 = c0 + q;
-          if (c2 < nchunks && c2 != c) {
-            const int len2 = min(kChunk, n - c2 * kChunk);
-            const int probe = pos[q] + step;
-            if (probe <= len2 && keys[c2 * kChunk + probe - 1] < key) pos[q] = probe;
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) rank += pos[q];
+      for (int s = 0; s < 4; ++s) rank[s] += count_less(staged + c2off, len2, mine[s]);
     }
-    write_sorted(L, W, e, rank, (int)(key & 0xffffffffu), lvl_prefix, regular);
+  }
+  bool regular = true;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int i = tid + s * kChunkThreads;
+    if (i < len) write_sorted(L, W, e, rank[s], (int)(mine[s] & 0xffffffffu), lvl_prefix, regular);
   }
   if (!regular) atomicAnd(&W.flags[e], 0);
 }
@@ -261,15 +330,25 @@ struct MaskArgs {
   int row_begin, row_end;  // rows (visiting positions) this launch covers, multiples of 64
   int col_begin, col_end;  // columns this launch covers, multiples of 64
   int tiles_r, tiles_c;    // tile grid per episode
+  int pass;                // which tile counter to use
   IouTest test;
 };
 
 __global__ void __launch_bounds__(kMaskRows) nms_mask_kernel(NmsWorkspace W, MaskArgs A) {
   __shared__ float4 cbox[kMaskCols];
   __shared__ float carea[kMaskCols];
+  __shared__ int s_tile;
+  if (W.sched[0] >= W.E) return;  // every episode already finished (early exit): nothing to do
   const int total = W.E * A.tiles_r * A.tiles_c;
-  for (int t = blockIdx.x; t < total; t += gridDim.x) {
-    // episode fastest: neighbouring CTAs work on tiles of equal cost
+  int* counter = W.sched + 1 + A.pass;
+  while (true) {
+    // dynamic tile scheduler: tiles differ in cost (diagonal / skipped / full), CTAs pull the next one
+    __syncthreads();  // the previous tile's readers are done with cbox and s_tile
+    if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1);
+    __syncthreads();
+    const int t = s_tile;
+    if (t >= total) break;
+    // episode fastest: concurrently running CTAs work on tiles of equal cost
     const int e = t % W.E;
     const int rc = t / W.E;
     const int rbi = rc / A.tiles_c, cgi = rc - rbi * A.tiles_c;
@@ -284,7 +363,6 @@ __global__ void __launch_bounds__(kMaskRows) nms_mask_kernel(NmsWorkspace W, Mas
     const float4* sbox = W.sbox + (size_t)e * W.NP;
     const float* sarea = W.sarea + (size_t)e * W.NP;
     const int ncols = min(kMaskCols, col_end - col0);
-    __syncthreads();  // the previous tile's readers are done with cbox
     for (int c = threadIdx.x; c < kMaskCols; c += kMaskRows) {
       // columns past the end are padded with the first column (finite, regular; their bits are masked off)
       const int cc = col0 + (c < ncols ? c : 0);
@@ -391,6 +469,7 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W
     if (tid == 0) {
       W.kcount[e] = n;
       W.done[e] = 1;
+      atomicAdd(&W.sched[0], 1);
     }
     return;
   }
@@ -457,19 +536,22 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W
     const int nk = s_nk;
     count += nk;
     {
-      const int g = tid >> 8, wl = tid & 255;
+      // thread (g, wl): word wl of the window, kept rows g, g+G, ... ; G = kSweepThreads / 64 row groups
+      constexpr int G = kSweepThreads / 64;
+      const int g = tid >> 6, wl = tid & 63;
       const int nnear = min(kSweepNear, wlim - (blk + 1));
       const u64* rb = rowbuf + cur * 64 * kSweepNear;
-      for (int wi = wl; wi < nnear; wi += 256) {
-        u64 acc = 0ull;
-        for (int r = g; r < nk; r += 4) acc |= rb[s_rows[r] * kSweepNear + wi];
-        if (acc) atomicOr(&rem[blk + 1 + wi], acc);
-      }
-      // words beyond the prefetched window come straight from L2
-      for (int w = blk + 1 + kSweepNear + wl; w < wlim; w += 256) {
+      if (wl < nnear) {
         u64 acc = 0ull;
 #pragma unroll 4
-        for (int r = g; r < nk; r += 4) acc |= mask[(size_t)(64 * blk + s_rows[r]) * W.NW + w];
+        for (int r = g; r < nk; r += G) acc |= rb[s_rows[r] * kSweepNear + wl];
+        if (acc) atomicOr(&rem[blk + 1 + wl], acc);
+      }
+      // words beyond the prefetched window come straight from L2
+      for (int w = blk + 1 + kSweepNear + wl; w < wlim; w += 64) {
+        u64 acc = 0ull;
+#pragma unroll 4
+        for (int r = g; r < nk; r += G) acc |= mask[(size_t)(64 * blk + s_rows[r]) * W.NW + w];
         if (acc) atomicOr(&rem[w], acc);
       }
     }
@@ -487,7 +569,10 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W
   }
   if (tid == 0) {
     W.kcount[e] = count;
-    if (finished) W.done[e] = 1;
+    if (finished) {
+      W.done[e] = 1;
+      atomicAdd(&W.sched[0], 1);
+    }
   }
 }
 
@@ -599,6 +684,7 @@ size_t nms_workspace_carve(Carver& c, int64_t E, int64_t max_len, NmsWorkspace* 
   w.flags = c.take<int32_t>(E);
   w.done = c.take<int32_t>(E);
   w.kcount = c.take<int32_t>(E);
+  w.sched = c.take<int32_t>(8);
   w.diagcol = c.take<unsigned long long>(E * NP);
   w.keptbits = c.take<unsigned long long>(E * NW);
   w.sortkeys = c.take<unsigned long long>(E * NP);
@@ -620,7 +706,14 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
     dim3 g((unsigned)ceil_div(max_len > 0 ? max_len : 1, kChunk), (unsigned)E);
     nms_chunk_sort_kernel<<<g, kChunkThreads, 0, stream>>>(L, W);
     OSD_LAUNCH_CHECK("nms_chunk_sort_kernel");
-    nms_merge_kernel<<<g, kChunkThreads, 0, stream>>>(L, W);
+    const size_t merge_smem = (size_t)std::min<int64_t>(kMergeStage, (int64_t)align_up((size_t)(max_len > 0 ? max_len : 1), kChunk)) * sizeof(u64);
+    static thread_local bool merge_configured = false;
+    if (!merge_configured) {
+      OSD_CUDA(cudaFuncSetAttribute(nms_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(kMergeStage * sizeof(u64))));
+      merge_configured = true;
+    }
+    nms_merge_kernel<<<g, kChunkThreads, merge_smem, stream>>>(L, W);
     OSD_LAUNCH_CHECK("nms_merge_kernel");
   }
 
@@ -675,6 +768,7 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
       M.col_end = hi;
       M.tiles_r = (int)ceil_div(hi, kMaskRows);
       M.tiles_c = (int)ceil_div(hi - prev, kMaskCols);
+      M.pass = p;
       const int64_t tiles = (int64_t)E * M.tiles_r * M.tiles_c;
       OSD_REQUIRE(tiles < (1ll << 31), "nms: too many mask tiles");
       const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * 12);
