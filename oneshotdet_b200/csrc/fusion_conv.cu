@@ -1,0 +1,703 @@
+// 1x1 fusion conv of the matching module on tcgen05 tensor cores (sm_100a), hand-written: no CUTLASS.
+//
+// Reference: `compress_dim_conv` (maskrcnn_benchmark/modeling/roi_heads/box_head/box_head.py:43-54) applied to
+// cat((x, support.expand_as(x)), dim=1) (:147-149):
+//     Conv1x1(2C -> 2C) + GroupNorm(32, 2C) + LeakyReLU(0.2) + Conv1x1(2C -> C) + GroupNorm(32, C) + LeakyReLU(0.2)
+// here on the FPN maps [B, C, H, W] (north_star), bf16 operands / fp32 accumulation.
+//
+//  * The concat is never materialised:  W1 . [x ; s] = W1x . x + (W1s . s + b1).  The support half folds into a
+//    per-(episode, level) bias vector (fusion_bias_kernel, fp32), so conv1 is a [2C x C] GEMM per pixel tile.
+//  * One GEMM kernel serves both convs (conv1x1_tc_kernel).  Output channels are the UMMA M dimension (A = bf16
+//    weights, K-major, TMA with 128-byte swizzle), pixels are N (B = activations).  NCHW activations are already
+//    "N-major": producer warps read fp32 rows, apply the input transform (identity, or GroupNorm+LeakyReLU of the
+//    previous conv), convert to bf16 and store straight into the MN-major 128B-swizzled canonical layout the
+//    tensor core reads -- no transpose, no extra pass over HBM.
+//  * Accumulators live in TMEM: (Cout/128) tiles of 128 x 64 fp32, double buffered (512 columns for Cout = 512),
+//    so the epilogue of tile i overlaps the MMAs of tile i+1.  Epilogue warps read TMEM (tcgen05.ld 32x32b), add
+//    the bias, accumulate GroupNorm statistics (fp64 atomics per (episode, group)) and store NCHW rows.
+//  * Warp roles (320 threads, 1 CTA/SM, persistent over pixel tiles): warps 0-3 epilogue, 4-7 activation
+//    producers, warp 8 TMA producer (weights), warp 9 MMA issuer + TMEM owner.  All hand-offs are mbarriers.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "osd_common.cuh"
+
+namespace osd {
+namespace {
+
+constexpr int kBlockN = 64;   // pixels per tile (UMMA N)
+constexpr int kBlockK = 64;   // K elements per weight stage (128 bytes of bf16 = one swizzle row)
+constexpr int kUmmaM = 128;
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 320;
+constexpr int kEpiWarps = 4, kProdWarps = 4;
+constexpr int kMaxStages = 4;
+constexpr uint32_t kSpinLimit = 1u << 26;  // a lost arrival traps instead of hanging the GPU
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] . B[smem], bf16 x bf16 -> fp32, issued by one thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (sm_100 format, cf. cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |
+//   [46,48) version = 1 | [61,64) layout type (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+
+// Instruction descriptor for kind::f16 (cute/arch/mma_sm100_desc.hpp InstrDescriptor):
+//   [4,6) D format (1 = F32) | [7,10) A format (1 = BF16) | [10,13) B format (1 = BF16) | 15 A major (0 = K) |
+//   16 B major (1 = MN) | [17,23) N >> 3 | [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel arguments
+// ------------------------------------------------------------------------------------------------
+struct ConvLevel {
+  const float* in;     // [B, Cin, HW] fp32
+  float* out;          // [B, Cout, HW] fp32
+  int hw;
+  int tiles_per_img;   // ceil(hw / 64)
+  int tile_begin;      // first global tile index of this level
+};
+
+struct ConvArgs {
+  int nl, B, Cin, Cout;
+  int num_mt;           // ceil(Cout / 128)
+  int num_kc;           // Cin / 64
+  int stages;           // weight stages in shared memory
+  int total_tiles;
+  int xform;            // 0: identity; 1: GroupNorm(32, Cin) + LeakyReLU on the input (stats_in)
+  float eps, slope;
+  const float* bias;    // [nl, B, Cout] (bias_level_stride / bias_img_stride may be 0)
+  int bias_level_stride, bias_img_stride;
+  const double* stats_in;   // [nl, B, 32, 2] sum / sum of squares of the input's producer conv
+  const float* gn_in_w;     // [Cin]
+  const float* gn_in_b;     // [Cin]
+  double* stats_out;        // [nl, B, 32, 2]
+  ConvLevel lv[OSD_MAX_LEVELS];
+};
+
+struct TileInfo {
+  int level, img, px0, nvalid;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const ConvArgs& A, int tile) {
+  int li = 0;
+#pragma unroll
+  for (int k = 1; k < OSD_MAX_LEVELS; ++k)
+    if (k < A.nl && tile >= A.lv[k].tile_begin) li = k;
+  const int local = tile - A.lv[li].tile_begin;
+  const int tpi = A.lv[li].tiles_per_img;
+  TileInfo t;
+  t.level = li;
+  t.img = local / tpi;
+  t.px0 = (local - t.img * tpi) * kBlockN;
+  t.nvalid = min(kBlockN, A.lv[li].hw - t.px0);
+  return t;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the GEMM kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [B buffers: 2 x (Cin x 128 B)] [A stages: stages x (num_mt x 16 KB)] [barriers]
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)A.Cin * 128u;
+  const uint32_t a_stage_bytes = (uint32_t)A.num_mt * 16384u;
+  const uint32_t sB = smem_base;
+  const uint32_t sA = sB + 2u * b_bytes;
+  const uint32_t sBar = sA + (uint32_t)A.stages * a_stage_bytes;
+  // barrier slots (8 bytes each)
+  const uint32_t a_full = sBar, a_empty = sBar + 8u * kMaxStages;
+  const uint32_t b_full = sBar + 16u * kMaxStages, b_empty = b_full + 16u;
+  const uint32_t t_full = b_full + 32u, t_empty = t_full + 16u;
+  const uint32_t tmem_slot = t_full + 32u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = (A.num_mt * 2 * kBlockN <= 128) ? 128u : (A.num_mt * 2 * kBlockN <= 256 ? 256u : 512u);
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < A.stages; ++s) {
+      mbar_init(a_full + 8u * s, 1);
+      mbar_init(a_empty + 8u * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(b_full + 8u * s, kProdWarps);
+      mbar_init(b_empty + 8u * s, 1);
+      mbar_init(t_full + 8u * s, 1);
+      mbar_init(t_empty + 8u * s, kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+
+  if (warp == 8) {
+    // ===================== TMA producer: weight chunks [Cout x 64] =====================
+    if (lane == 0) {
+      uint32_t c = 0;
+      for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < A.num_kc; ++kc, ++c) {
+          const uint32_t s = c % A.stages, ph = (c / A.stages) & 1u;
+          mbar_wait(a_empty + 8u * s, ph ^ 1u);
+          mbar_expect_tx(a_full + 8u * s, a_stage_bytes);
+          for (int mt = 0; mt < A.num_mt; ++mt)
+            tma_load_2d(sA + s * a_stage_bytes + mt * 16384u, &tmap_w, kc * kBlockK, mt * kUmmaM, a_full + 8u * s);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kUmmaM, kBlockN);
+      uint32_t c = 0, it = 0;
+      for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+        mbar_wait(t_empty + 8u * buf, ph ^ 1u);   // epilogue drained this accumulator stage
+        mbar_wait(b_full + 8u * buf, ph);         // activations converted
+        tc_fence_after();
+        const uint32_t acc_col = buf * (uint32_t)(A.num_mt * kBlockN);
+        for (int kc = 0; kc < A.num_kc; ++kc, ++c) {
+          const uint32_t s = c % A.stages, aph = (c / A.stages) & 1u;
+          mbar_wait(a_full + 8u * s, aph);
+          tc_fence_after();
+#pragma unroll
+          for (int k16 = 0; k16 < kBlockK / kUmmaK; ++k16) {
+            // B: MN-major SW128; 8-channel groups are 1024 B apart (SBO); one 64-pixel block (LBO unused)
+            const uint32_t kgrp = (uint32_t)(kc * kBlockK + k16 * kUmmaK) >> 3;
+            const uint64_t bdesc = make_smem_desc(sB + buf * b_bytes + kgrp * 1024u, b_bytes, 1024u);
+            for (int mt = 0; mt < A.num_mt; ++mt) {
+              // A: K-major SW128; 8-row groups are 1024 B apart (SBO), K advances by 32 B inside the swizzle row
+              const uint64_t adesc = make_smem_desc(sA + s * a_stage_bytes + mt * 16384u + k16 * 32u, 16u, 1024u);
+              umma_bf16(tmem_base + acc_col + mt * kBlockN, adesc, bdesc, idesc, (kc | k16) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(a_empty + 8u * s);  // weights of this stage consumed
+        }
+        umma_commit(t_full + 8u * buf);   // accumulators ready for the epilogue
+        umma_commit(b_empty + 8u * buf);  // activation buffer may be refilled
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== activation producers (warps 4-7) =====================
+    const int pw = warp - 4;
+    const int rsub = lane >> 3;   // row inside a group of 4
+    const int j = lane & 7;       // 16-byte chunk (8 pixels) inside the 128-byte row
+    const int gs_in = A.Cin / 32; // channels per GroupNorm group of the input
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+      mbar_wait(b_empty + 8u * buf, ph ^ 1u);
+      const TileInfo t = decode_tile(A, tile);
+      const ConvLevel& L = A.lv[t.level];
+      const float* src = L.in + (size_t)t.img * A.Cin * L.hw + t.px0 + j * 8;
+      const bool vec_ok = ((L.hw & 3) == 0) && (t.px0 + j * 8 + 8 <= L.hw);
+      const int nleft = L.hw - (t.px0 + j * 8);  // valid pixels from this chunk's start (may be <= 0)
+      const double* st = A.xform ? A.stats_in + ((size_t)t.level * A.B + t.img) * 64 : nullptr;
+      const double inv_cnt = A.xform ? 1.0 / ((double)gs_in * (double)L.hw) : 0.0;
+      for (int k0 = pw * 4 + rsub; k0 < A.Cin; k0 += 16 * 4) {
+        // 4 rows in flight per thread
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u * 16;
+          const float* p = src + (size_t)k * L.hw;
+          if (k < A.Cin) {
+            if (vec_ok) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+              v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
+              v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[u][q] = (q < nleft) ? __ldg(p + q) : 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u * 16;
+          if (k < A.Cin) {
+            if (A.xform) {
+              // GroupNorm (biased variance, as torch) + LeakyReLU of the producer conv's output
+              const int g = k / gs_in;
+              const double mean = st[2 * g] * inv_cnt;
+              const double var = fmax(st[2 * g + 1] * inv_cnt - mean * mean, 0.0);
+              const float rstd = (float)(1.0 / sqrt(var + (double)A.eps));
+              const float sc = A.gn_in_w[k] * rstd;
+              const float sh = A.gn_in_b[k] - (float)mean * sc;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float y = fmaf(v[u][q], sc, sh);
+                y = y > 0.f ? y : y * A.slope;
+                v[u][q] = (q < nleft) ? y : 0.f;   // padded pixels stay exactly zero
+              }
+            }
+            const uint32_t dst = sB + buf * b_bytes + (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u +
+                                 (uint32_t)((j ^ (k & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16x2(v[u][0], v[u][1])),
+                         "r"(pack_bf16x2(v[u][2], v[u][3])), "r"(pack_bf16x2(v[u][4], v[u][5])),
+                         "r"(pack_bf16x2(v[u][6], v[u][7]))
+                         : "memory");
+          }
+        }
+      }
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_full + 8u * buf);
+    }
+  } else {
+    // ===================== epilogue (warps 0-3; warp q owns TMEM lanes 32q..32q+31) =====================
+    const int q = warp;
+    const int gs_out = A.Cout / 32;  // channels per GroupNorm group of the output (power of two <= 16)
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+      const TileInfo t = decode_tile(A, tile);
+      const ConvLevel& L = A.lv[t.level];
+      mbar_wait(t_full + 8u * buf, ph);
+      tc_fence_after();
+      const bool vec_ok = (L.hw & 3) == 0;
+      for (int mt = 0; mt < A.num_mt; ++mt) {
+        const int oc = mt * kUmmaM + q * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(A.num_mt * kBlockN) + mt * kBlockN;
+        float s1 = 0.f, s2 = 0.f;
+        const bool oc_ok = oc < A.Cout;
+        const float bias = oc_ok ? A.bias[(size_t)t.level * A.bias_level_stride + (size_t)t.img * A.bias_img_stride + oc] : 0.f;
+        float* dst = L.out + ((size_t)t.img * A.Cout + (oc_ok ? oc : 0)) * L.hw + t.px0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld32(taddr + half * 32, r);
+          tmem_ld_wait();
+          if (oc_ok) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              const int px = half * 32 + c;
+              float y0 = __uint_as_float(r[c]) + bias, y1 = __uint_as_float(r[c + 1]) + bias;
+              float y2 = __uint_as_float(r[c + 2]) + bias, y3 = __uint_as_float(r[c + 3]) + bias;
+              if (vec_ok) {
+                if (px < t.nvalid) {  // hw % 4 == 0 and px % 4 == 0: the group is entirely valid
+                  *reinterpret_cast<float4*>(dst + px) = make_float4(y0, y1, y2, y3);
+                  s1 += (y0 + y1) + (y2 + y3);
+                  s2 += (y0 * y0 + y1 * y1) + (y2 * y2 + y3 * y3);
+                }
+              } else {
+                const float ys[4] = {y0, y1, y2, y3};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (px + e < t.nvalid) {
+                    dst[px + e] = ys[e];
+                    s1 += ys[e];
+                    s2 += ys[e] * ys[e];
+                  }
+                }
+              }
+            }
+          }
+        }
+        if (A.stats_out) {
+          // GroupNorm statistics of this conv's output: reduce over the gs_out consecutive channels (lanes) of a group
+          for (int o = 1; o < gs_out; o <<= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          if (oc_ok && (lane & (gs_out - 1)) == 0) {
+            double* so = A.stats_out + ((size_t)t.level * A.B + t.img) * 64 + 2 * (oc / gs_out);
+            atomicAdd(so, (double)s1);
+            atomicAdd(so + 1, (double)s2);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + 8u * buf);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels around the GEMMs
+// ------------------------------------------------------------------------------------------------
+// bias_eff[l, b, oc] = b1[oc] + sum_c W1s_t[c, oc] * mean_s supp[l][b*S + s, c]      (fp32)
+struct BiasArgs {
+  int nl, B, S, C, Cout;
+  const float* supp[OSD_MAX_LEVELS];  // [B*S, C]
+  const float* w1s_t;                 // [C, Cout]
+  const float* b1;                    // [Cout]
+  float* bias_eff;                    // [nl, B, Cout]
+};
+
+__global__ void __launch_bounds__(512) fusion_bias_kernel(BiasArgs A) {
+  extern __shared__ float pooled[];  // [C]
+  const int l = blockIdx.x / A.B, b = blockIdx.x % A.B;
+  const float* s = A.supp[l] + (size_t)b * A.S * A.C;
+  for (int c = threadIdx.x; c < A.C; c += blockDim.x) {
+    float acc = s[c];
+    for (int k = 1; k < A.S; ++k) acc = __fadd_rn(acc, s[(size_t)k * A.C + c]);
+    pooled[c] = A.S == 1 ? acc : __fdiv_rn(acc, (float)A.S);
+  }
+  __syncthreads();
+  for (int oc = threadIdx.x; oc < A.Cout; oc += blockDim.x) {
+    float acc = A.b1[oc];
+    for (int c = 0; c < A.C; ++c) acc = fmaf(A.w1s_t[(size_t)c * A.Cout + oc], pooled[c], acc);
+    A.bias_eff[((size_t)l * A.B + b) * A.Cout + oc] = acc;
+  }
+}
+
+// out = LeakyReLU(GroupNorm(32, C)(y)) in place, per (level, episode, channel) plane
+struct GnArgs {
+  int nl, B, C;
+  float eps, slope;
+  const double* stats;  // [nl, B, 32, 2]
+  const float* gn_w;
+  const float* gn_b;
+  float* y[OSD_MAX_LEVELS];
+  int hw[OSD_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(256) fusion_gn_lrelu_kernel(GnArgs A) {
+  const int l = blockIdx.z, plane = blockIdx.y;  // plane = b * C + c
+  const int b = plane / A.C, c = plane - b * A.C;
+  const int hw = A.hw[l];
+  const int gs = A.C / 32;
+  const double* st = A.stats + ((size_t)l * A.B + b) * 64 + 2 * (c / gs);
+  const double inv_cnt = 1.0 / ((double)gs * (double)hw);
+  const double mean = st[0] * inv_cnt;
+  const double var = fmax(st[1] * inv_cnt - mean * mean, 0.0);
+  const float rstd = (float)(1.0 / sqrt(var + (double)A.eps));
+  const float sc = A.gn_w[c] * rstd;
+  const float sh = A.gn_b[c] - (float)mean * sc;
+  float* y = A.y[l] + (size_t)plane * hw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    float v = fmaf(y[i], sc, sh);
+    y[i] = v > 0.f ? v : v * A.slope;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    OSD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) {
+      set_error("cuTensorMapEncodeTiled is not available from the driver");
+      return OSD_ERR_CUDA;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *out = fn;
+  return OSD_OK;
+}
+
+// bf16 weights [rows, cols] row-major -> 2-D tensor map, box = 64 (K) x 128 (rows), 128-byte swizzle;
+// rows past the end (Cout < 128) are zero-filled by the TMA unit
+int make_weight_map(const void* w, int rows, int cols, CUtensorMap* map) {
+  EncodeTiledFn fn;
+  int rc = get_encode_fn(&fn);
+  if (rc != OSD_OK) return rc;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kUmmaM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return OSD_ERR_CUDA;
+  }
+  return OSD_OK;
+}
+
+struct ConvPlan {
+  int stages;
+  size_t smem;
+};
+
+int plan_conv(int Cin, int Cout, ConvPlan* p) {
+  OSD_REQUIRE(Cin % 64 == 0 && Cin >= 64 && Cin <= 512, "fusion: input channels %d must be a multiple of 64 in [64, 512]", Cin);
+  OSD_REQUIRE(Cout == 64 || Cout == 128 || Cout == 256 || Cout == 512, "fusion: output channels %d must be 64, 128, 256 or 512", Cout);
+  const int num_mt = (Cout + kUmmaM - 1) / kUmmaM;
+  const size_t b_bytes = 2 * (size_t)Cin * 128;
+  const size_t a_stage = (size_t)num_mt * 16384;
+  const size_t budget = 220 * 1024;
+  int stages = (int)((budget - b_bytes - 1024 - 256) / a_stage);
+  if (stages > kMaxStages) stages = kMaxStages;
+  OSD_REQUIRE(stages >= 2, "fusion: %d -> %d channels does not fit in shared memory", Cin, Cout);
+  p->stages = stages;
+  p->smem = 1024 + b_bytes + stages * a_stage + 256;
+  return OSD_OK;
+}
+
+int launch_conv(const CUtensorMap& map, ConvArgs& A, cudaStream_t stream) {
+  ConvPlan p;
+  int rc = plan_conv(A.Cin, A.Cout, &p);
+  if (rc != OSD_OK) return rc;
+  A.stages = p.stages;
+  A.num_mt = (A.Cout + kUmmaM - 1) / kUmmaM;
+  A.num_kc = A.Cin / kBlockK;
+  static thread_local size_t configured = 0;
+  if (p.smem > configured) {
+    OSD_CUDA(cudaFuncSetAttribute(conv1x1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    configured = 225 * 1024;
+  }
+  if (A.total_tiles <= 0) return OSD_OK;
+  const int grid = A.total_tiles < kNumSMs ? A.total_tiles : kNumSMs;
+  conv1x1_tc_kernel<<<grid, kThreads, p.smem, stream>>>(map, A);
+  OSD_LAUNCH_CHECK("conv1x1_tc_kernel");
+  return OSD_OK;
+}
+
+}  // namespace
+}  // namespace osd
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+static size_t fusion_carve(const osd_fusion_desc* d, osd::Carver& c, float** y1, double** stats1, double** stats2,
+                           float** bias_eff) {
+  size_t elems = 0;
+  for (int l = 0; l < d->num_levels; ++l) elems += (size_t)d->batch * 2 * d->channels * d->hw[l];
+  *stats1 = c.take<double>((size_t)d->num_levels * d->batch * 64);
+  *stats2 = c.take<double>((size_t)d->num_levels * d->batch * 64);
+  *bias_eff = c.take<float>((size_t)d->num_levels * d->batch * 2 * d->channels);
+  *y1 = d->stage == OSD_FUSION_CONV1 ? nullptr : c.take<float>(elems);
+  return c.total();
+}
+
+static int fusion_validate(const osd_fusion_desc* d) {
+  OSD_REQUIRE(d != nullptr, "osd_fusion: desc is null");
+  OSD_REQUIRE(d->num_levels >= 1 && d->num_levels <= OSD_MAX_LEVELS, "osd_fusion: num_levels %d out of range", d->num_levels);
+  OSD_REQUIRE(d->batch >= 0 && d->shots >= 1, "osd_fusion: bad batch / shots");
+  OSD_REQUIRE(d->channels == 64 || d->channels == 128 || d->channels == 256,
+              "osd_fusion: channels must be 64, 128 or 256 (got %d)", d->channels);
+  OSD_REQUIRE(d->stage == OSD_FUSION_CONV1 || d->stage == OSD_FUSION_FULL, "osd_fusion: unknown stage %d", d->stage);
+  for (int l = 0; l < d->num_levels; ++l) {
+    OSD_REQUIRE(d->hw[l] >= 1, "osd_fusion: level %d is empty", l);
+    OSD_REQUIRE((int64_t)d->batch * 2 * d->channels * d->hw[l] < (1ll << 31), "osd_fusion: level %d too large; split the batch", l);
+  }
+  return OSD_OK;
+}
+
+extern "C" int osd_fusion_workspace_bytes(const osd_fusion_desc* d, size_t* bytes) {
+  int rc = fusion_validate(d);
+  if (rc != OSD_OK) return rc;
+  OSD_REQUIRE(bytes != nullptr, "osd_fusion_workspace_bytes: bytes is null");
+  osd::Carver c(nullptr);
+  float *y1, *be;
+  double *s1, *s2;
+  *bytes = fusion_carve(d, c, &y1, &s1, &s2, &be);
+  return OSD_OK;
+}
+
+extern "C" int osd_fusion_forward(const osd_fusion_desc* d, void* workspace, size_t workspace_bytes, void* stream_) {
+  using namespace osd;
+  int rc = fusion_validate(d);
+  if (rc != OSD_OK) return rc;
+  if (d->batch == 0) return OSD_OK;
+  OSD_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "osd_fusion_forward: workspace must be 256-byte aligned");
+  OSD_REQUIRE(d->w1x_bf16 && d->w1s_t && d->b1, "osd_fusion_forward: conv1 weights are null");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  Carver c(workspace);
+  float *y1, *bias_eff;
+  double *stats1, *stats2;
+  const size_t need = fusion_carve(d, c, &y1, &stats1, &stats2, &bias_eff);
+  if (need > workspace_bytes) {
+    set_error("osd_fusion_forward: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+    return OSD_ERR_WORKSPACE;
+  }
+  const int C = d->channels, C2 = 2 * C, B = d->batch, nl = d->num_levels;
+  const bool full = d->stage == OSD_FUSION_FULL;
+  if (full)
+    OSD_REQUIRE(d->w2_bf16 && d->b2 && d->gn1_w && d->gn1_b && d->gn2_w && d->gn2_b, "osd_fusion_forward: conv2 / GroupNorm parameters are null");
+  OSD_CUDA(cudaMemsetAsync(stats1, 0, sizeof(double) * (size_t)nl * B * 64 * 2, stream));  // stats1 and stats2 are adjacent? no: zero both
+  OSD_CUDA(cudaMemsetAsync(stats2, 0, sizeof(double) * (size_t)nl * B * 64, stream));
+
+  // ---- folded bias
+  BiasArgs BA{};
+  BA.nl = nl; BA.B = B; BA.S = d->shots; BA.C = C; BA.Cout = C2;
+  for (int l = 0; l < nl; ++l) {
+    OSD_REQUIRE(d->feat[l] && d->supp[l] && d->out[l], "osd_fusion_forward: null pointer at level %d", l);
+    BA.supp[l] = static_cast<const float*>(d->supp[l]);
+  }
+  BA.w1s_t = d->w1s_t; BA.b1 = d->b1; BA.bias_eff = bias_eff;
+  fusion_bias_kernel<<<nl * B, 512, C * sizeof(float), stream>>>(BA);
+  OSD_LAUNCH_CHECK("fusion_bias_kernel");
+
+  // ---- conv1: x [B,C,HW] -> y1 [B,2C,HW] (+ folded bias, GroupNorm-1 statistics)
+  CUtensorMap map1;
+  rc = make_weight_map(d->w1x_bf16, C2, C, &map1);
+  if (rc != OSD_OK) return rc;
+  ConvArgs A1{};
+  A1.nl = nl; A1.B = B; A1.Cin = C; A1.Cout = C2; A1.xform = 0; A1.eps = d->gn_eps; A1.slope = d->lrelu_slope;
+  A1.bias = bias_eff; A1.bias_level_stride = B * C2; A1.bias_img_stride = C2;
+  A1.stats_out = stats1;
+  int tiles = 0;
+  size_t y1_off = 0;
+  for (int l = 0; l < nl; ++l) {
+    ConvLevel& L = A1.lv[l];
+    L.in = static_cast<const float*>(d->feat[l]);
+    L.out = full ? y1 + y1_off : static_cast<float*>(d->out[l]);
+    L.hw = d->hw[l];
+    L.tiles_per_img = (d->hw[l] + kBlockN - 1) / kBlockN;
+    L.tile_begin = tiles;
+    tiles += B * L.tiles_per_img;
+    y1_off += (size_t)B * C2 * d->hw[l];
+  }
+  A1.total_tiles = tiles;
+  rc = launch_conv(map1, A1, stream);
+  if (rc != OSD_OK || !full) return rc;
+
+  // ---- conv2: LeakyReLU(GN1(y1)) [B,2C,HW] -> y2 [B,C,HW] (+ b2, GroupNorm-2 statistics)
+  CUtensorMap map2;
+  rc = make_weight_map(d->w2_bf16, C, C2, &map2);
+  if (rc != OSD_OK) return rc;
+  ConvArgs A2{};
+  A2.nl = nl; A2.B = B; A2.Cin = C2; A2.Cout = C; A2.xform = 1; A2.eps = d->gn_eps; A2.slope = d->lrelu_slope;
+  A2.bias = d->b2; A2.bias_level_stride = 0; A2.bias_img_stride = 0;
+  A2.stats_in = stats1; A2.gn_in_w = d->gn1_w; A2.gn_in_b = d->gn1_b;
+  A2.stats_out = stats2;
+  for (int l = 0; l < nl; ++l) {
+    ConvLevel& L = A2.lv[l];
+    L.in = A1.lv[l].out;
+    L.out = static_cast<float*>(d->out[l]);
+    L.hw = d->hw[l];
+    L.tiles_per_img = A1.lv[l].tiles_per_img;
+    L.tile_begin = A1.lv[l].tile_begin;
+  }
+  A2.total_tiles = tiles;
+  rc = launch_conv(map2, A2, stream);
+  if (rc != OSD_OK) return rc;
+
+  // ---- GroupNorm-2 + LeakyReLU in place
+  GnArgs G{};
+  G.nl = nl; G.B = B; G.C = C; G.eps = d->gn_eps; G.slope = d->lrelu_slope;
+  G.stats = stats2; G.gn_w = d->gn2_w; G.gn_b = d->gn2_b;
+  int max_hw = 1;
+  for (int l = 0; l < nl; ++l) {
+    G.y[l] = static_cast<float*>(d->out[l]);
+    G.hw[l] = d->hw[l];
+    if (d->hw[l] > max_hw) max_hw = d->hw[l];
+  }
+  dim3 grid((unsigned)((max_hw + 2047) / 2048), (unsigned)(B * C), (unsigned)nl);
+  fusion_gn_lrelu_kernel<<<grid, 256, 0, stream>>>(G);
+  OSD_LAUNCH_CHECK("fusion_gn_lrelu_kernel");
+  return OSD_OK;
+}

@@ -28,9 +28,9 @@ constexpr int kChunk = 2048;         // keys per sort chunk (one CTA each)
 constexpr int kChunkThreads = 512;
 constexpr int kMergeStage = 6 * kChunk;   // keys staged per window by the merge kernel (96 KB)
 constexpr int kMaskRows = 128;       // rows per mask tile (one thread per row)
-constexpr int kMaskCols = 256;       // columns per mask tile (4 words of 64)
+constexpr int kMaskCols = 128;       // columns per mask tile (2 words of 64)
 constexpr int kSweepThreads = 512;
-constexpr int kSweepNear = 64;       // mask words per row prefetched into shared memory by the sweep
+constexpr int kSweepPre = 8;         // mask words per thread the sweep keeps in flight for the next column
 
 typedef unsigned long long u64;
 
@@ -239,7 +239,19 @@ __global__ void __launch_bounds__(kChunkThreads) nms_merge_kernel(CandLayout L, 
   for (int w0 = 0; w0 < n; w0 += kMergeStage) {
     const int wn = min(kMergeStage, n - w0);
     __syncthreads();
-    for (int i = tid; i < wn; i += kChunkThreads) staged[i] = keys[w0 + i];
+    for (int i = tid; i < wn; i += 4 * kChunkThreads) {  // 4 independent loads in flight
+      u64 t4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = i + u * kChunkThreads;
+        t4[u] = idx < wn ? keys[w0 + idx] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = i + u * kChunkThreads;
+        if (idx < wn) staged[idx] = t4[u];
+      }
+    }
     __syncthreads();
     for (int c2off = 0; c2off < wn; c2off += kChunk) {
       if (w0 + c2off == base) continue;  // own chunk
@@ -377,7 +389,7 @@ __global__ void __launch_bounds__(kMaskRows) nms_mask_kernel(NmsWorkspace W, Mas
     const bool exact = A.test.force_exact || !(W.flags[e] & 1);
     const int row_tile0 = i & ~63;
     const int il = i & 63;
-    u64* mrow = W.mask + ((size_t)e * W.NP + i) * W.NW;
+    u64* mcol = W.mask + (size_t)e * W.NW * W.NP + i;  // word-major: mask[e][w][row], coalesced over rows
     for (int tt = 0; tt < kMaskCols / 64; ++tt) {
       const int ct0 = col0 + 64 * tt;
       if (ct0 >= col_end) break;
@@ -404,52 +416,34 @@ __global__ void __launch_bounds__(kMaskRows) nms_mask_kernel(NmsWorkspace W, Mas
         W.diagcol[(size_t)e * W.NP + i] = below;
         bits = above;
       }
-      mrow[ct0 >> 6] = bits;
+      mcol[(size_t)(ct0 >> 6) * W.NP] = bits;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// 3. sweep: one CTA per episode walks the 64-box blocks in visiting order.  Per block: warp 0 resolves the
-//    64 boxes against each other (ballot fixpoint on the transposed diagonal bits), then all threads OR the
-//    mask rows of the kept boxes into the suppression words of the later blocks.  The rows of the next two
-//    blocks are prefetched into shared memory with cp.async while the current block is resolved, so the
-//    serial chain never waits for L2.
+// 3. sweep: one CTA per episode walks the 64-box blocks in visiting order.  The suppression word of block b is
+//    *pulled*: OR over all kept earlier boxes i of mask[b][i] -- a coalesced column read (the mask is word-major)
+//    and a tree reduction, no atomics.  The column of block b+1 is loaded before block b is resolved (it does not
+//    depend on the outcome; the kept bits are applied as a predicate afterwards), so the serial chain per block is
+//    reduce -> barrier -> warp-0 ballot fixpoint on the transposed diagonal tile -> barrier.
 // ------------------------------------------------------------------------------------------------
 struct SweepArgs {
   int blk_begin;  // first 64-box block of this pass
   int blk_end;    // blocks [blk_begin, blk_end) are swept (clipped to the episode)
-  int word_end;   // mask words [.., word_end) are valid for the rows touched by this pass
   int stop;       // finish the episode once this many boxes are kept
   int passthrough;
 };
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void sweep_prefetch(const u64* __restrict__ mask, const u64* __restrict__ dc, int NW,
-                                               int blk, int wlim, u64* rowbuf, u64* dcb) {
-  const int nnear = min(kSweepNear, wlim - (blk + 1));
-  const int total = 64 * nnear;  // <= 0 when there is no later word
-  for (int idx = threadIdx.x; idx < total; idx += kSweepThreads) {
-    const int r = idx / nnear, wi = idx - r * nnear;
-    cp_async8(&rowbuf[r * kSweepNear + wi], &mask[(size_t)(64 * blk + r) * NW + blk + 1 + wi]);
-  }
-  if (threadIdx.x < 64) cp_async8(&dcb[threadIdx.x], &dc[64 * blk + threadIdx.x]);
+__device__ __forceinline__ u64 warp_or_u64(u64 v) {
+  const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
+  const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
+  return ((u64)hi << 32) | lo;
 }
 
 __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W, SweepArgs A) {
-  extern __shared__ u64 sweep_smem[];
-  // layout: rem[NW] | rowbuf[3][64][kSweepNear] | dcb[3][64]
-  u64* rem = sweep_smem;
-  u64* rowbuf = sweep_smem + W.NW;
-  u64* dcb = rowbuf + 3 * 64 * kSweepNear;
-  __shared__ int s_rows[64];
+  extern __shared__ u64 kw[];  // [NW] kept bits of the blocks swept so far
+  __shared__ u64 partial[kSweepThreads / 32];
   __shared__ int s_nk;
   const int e = blockIdx.x;
   if (W.done[e]) return;
@@ -473,46 +467,62 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W
     }
     return;
   }
-  const u64* mask = W.mask + (size_t)e * W.NP * W.NW;
-  const u64* dc = W.diagcol + (size_t)e * W.NP;
-  const int wlim = min(A.word_end, nblk);
+  const u64* __restrict__ maskT = W.mask + (size_t)e * W.NW * W.NP;  // [word][row]
+  const u64* __restrict__ dc = W.diagcol + (size_t)e * W.NP;
   const int blim = min(A.blk_end, nblk);
   const int nb = blim - A.blk_begin;  // blocks swept by this pass (may be <= 0)
-  // start the prefetch pipeline (two blocks deep) before anything else
-  if (nb > 0) sweep_prefetch(mask, dc, W.NW, A.blk_begin, wlim, rowbuf, dcb);
-  cp_async_commit();
-  if (nb > 1) sweep_prefetch(mask, dc, W.NW, A.blk_begin + 1, wlim, rowbuf + 64 * kSweepNear, dcb + 64);
-  cp_async_commit();
-  for (int w = tid; w < W.NW; w += kSweepThreads) rem[w] = 0ull;
-  __syncthreads();
+  for (int w = tid; w < W.NW; w += kSweepThreads) kw[w] = (w < A.blk_begin) ? kb[w] : 0ull;
   int count = W.kcount[e];
-  if (A.blk_begin > 0) {
-    // rebuild the suppression state of columns >= blk_begin from the boxes kept by the earlier passes
-    for (int r = warp; r < A.blk_begin * 64; r += kSweepThreads / 32) {
-      if ((kb[r >> 6] >> (r & 63)) & 1ull) {
-        const u64* mrow = mask + (size_t)r * W.NW;
-        for (int w = A.blk_begin + lane; w < wlim; w += 32) {
-          u64 v = mrow[w];
-          if (v) atomicOr(&rem[w], v);
-        }
-      }
+  // rows of a pass that ends within 4096 boxes fit in registers, kSweepPre per thread: prefetch one column ahead
+  const bool small = 64 * blim <= kSweepThreads * kSweepPre;
+  u64 cur[kSweepPre], nxt[kSweepPre];
+#pragma unroll
+  for (int v = 0; v < kSweepPre; ++v) cur[v] = nxt[v] = 0ull;
+  if (small && nb > 0) {
+#pragma unroll
+    for (int v = 0; v < kSweepPre; ++v) {
+      const int row = tid + v * kSweepThreads;
+      if (row < 64 * A.blk_begin) cur[v] = maskT[(size_t)A.blk_begin * W.NP + row];
     }
   }
+  __syncthreads();
   int it = 0;
   for (; it < nb; ++it) {
     const int blk = A.blk_begin + it;
-    const int cur = it % 3;
-    cp_async_wait<1>();  // this block's rows (committed two groups ago) have landed
-    __syncthreads();     // ... for every thread; the previous block's ORs into rem[] are complete
-    if (it + 2 < nb)
-      sweep_prefetch(mask, dc, W.NW, blk + 2, wlim, rowbuf + ((it + 2) % 3) * 64 * kSweepNear, dcb + ((it + 2) % 3) * 64);
-    cp_async_commit();
+    u64 c_lo = 0ull, c_hi = 0ull;
     if (warp == 0) {
+      c_lo = dc[64 * blk + lane];
+      c_hi = dc[64 * blk + 32 + lane];
+    }
+    if (small && it + 1 < nb) {
+#pragma unroll
+      for (int v = 0; v < kSweepPre; ++v) {
+        const int row = tid + v * kSweepThreads;
+        nxt[v] = (row < 64 * (blk + 1)) ? maskT[(size_t)(blk + 1) * W.NP + row] : 0ull;
+      }
+    }
+    // suppression word of this block: OR over the kept earlier boxes
+    u64 acc = 0ull;
+    if (small) {
+#pragma unroll
+      for (int v = 0; v < kSweepPre; ++v) {
+        const int row = tid + v * kSweepThreads;
+        if (row < 64 * blk && ((kw[row >> 6] >> (row & 63)) & 1ull)) acc |= cur[v];
+      }
+    } else {
+      const u64* col = maskT + (size_t)blk * W.NP;
+#pragma unroll 4
+      for (int row = tid; row < 64 * blk; row += kSweepThreads)
+        if ((kw[row >> 6] >> (row & 63)) & 1ull) acc |= col[row];
+    }
+    acc = warp_or_u64(acc);
+    if (lane == 0) partial[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      const u64 rem = warp_or_u64(lane < kSweepThreads / 32 ? partial[lane] : 0ull);
       const int nv = min(64, n - 64 * blk);
       const u64 vmask = nv == 64 ? ~0ull : ((1ull << nv) - 1ull);
-      const u64 free_ = ~rem[blk] & vmask;
-      const u64 c_lo = dcb[cur * 64 + lane];
-      const u64 c_hi = dcb[cur * 64 + 32 + lane];
+      const u64 free_ = ~rem & vmask;
       u64 kept = free_;
       uint32_t lo, hi;
       while (true) {
@@ -524,44 +534,21 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W
         if (nk == kept) break;
         kept = nk;
       }
-      const uint32_t lt = (1u << lane) - 1u;
-      if ((lo >> lane) & 1u) s_rows[__popc(lo & lt)] = lane;
-      if ((hi >> lane) & 1u) s_rows[__popc(lo) + __popc(hi & lt)] = lane + 32;
       if (lane == 0) {
         s_nk = __popc(lo) + __popc(hi);
+        kw[blk] = kept;
         kb[blk] = kept;
       }
     }
     __syncthreads();
-    const int nk = s_nk;
-    count += nk;
-    {
-      // thread (g, wl): word wl of the window, kept rows g, g+G, ... ; G = kSweepThreads / 64 row groups
-      constexpr int G = kSweepThreads / 64;
-      const int g = tid >> 6, wl = tid & 63;
-      const int nnear = min(kSweepNear, wlim - (blk + 1));
-      const u64* rb = rowbuf + cur * 64 * kSweepNear;
-      if (wl < nnear) {
-        u64 acc = 0ull;
-#pragma unroll 4
-        for (int r = g; r < nk; r += G) acc |= rb[s_rows[r] * kSweepNear + wl];
-        if (acc) atomicOr(&rem[blk + 1 + wl], acc);
-      }
-      // words beyond the prefetched window come straight from L2
-      for (int w = blk + 1 + kSweepNear + wl; w < wlim; w += 64) {
-        u64 acc = 0ull;
-#pragma unroll 4
-        for (int r = g; r < nk; r += G) acc |= mask[(size_t)(64 * blk + s_rows[r]) * W.NW + w];
-        if (acc) atomicOr(&rem[w], acc);
-      }
-    }
+    count += s_nk;
+#pragma unroll
+    for (int v = 0; v < kSweepPre; ++v) cur[v] = nxt[v];
     if (count >= A.stop) {
       ++it;
       break;
     }
   }
-  cp_async_wait<0>();
-  __syncthreads();
   const int blk_next = A.blk_begin + (nb > 0 ? it : 0);
   const bool finished = (count >= A.stop) || (blk_next >= nblk);
   if (finished) {
@@ -720,7 +707,7 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
   // ---- mask + sweep, in passes over growing prefixes of the visiting order.  Without early exit there is one
   //      pass; with it, the first pass covers just enough boxes to keep post_top_n + 1 if little is suppressed,
   //      the second a 30 % larger prefix, the last everything.  Finished episodes skip later passes on the device.
-  const size_t sweep_smem = ((size_t)W.NW + 3 * 64 * kSweepNear + 3 * 64) * sizeof(u64);
+  const size_t sweep_smem = (size_t)W.NW * sizeof(u64);
   {
     static thread_local size_t configured = 48 * 1024;
     if (sweep_smem > configured) {
@@ -735,7 +722,6 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
   if (P.passthrough) {
     S.blk_begin = 0;
     S.blk_end = INT_MAX;
-    S.word_end = INT_MAX;
     S.stop = INT_MAX;
     nms_sweep_kernel<<<E, kSweepThreads, sweep_smem, stream>>>(W, S);
     OSD_LAUNCH_CHECK("nms_sweep_kernel");
@@ -776,7 +762,6 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
       OSD_LAUNCH_CHECK("nms_mask_kernel");
       S.blk_begin = prev / 64;
       S.blk_end = hi / 64;
-      S.word_end = hi / 64;
       nms_sweep_kernel<<<E, kSweepThreads, sweep_smem, stream>>>(W, S);
       OSD_LAUNCH_CHECK("nms_sweep_kernel");
       prev = hi;

@@ -91,7 +91,7 @@ struct NmsWorkspace {
   int32_t* done;      // [E] episode finished (early exit or all blocks swept)
   int32_t* kcount;    // [E] boxes kept so far
   int32_t* sched;     // [8] [0]: episodes finished; [1..3]: dynamic tile counters of the mask passes
-  unsigned long long* mask;     // [E, NP, NW] bit j of word w of row i: box 64w+j suppressed by i (j > i)
+  unsigned long long* mask;     // [E, NW, NP] word-major: bit j of mask[e][w][i]: box 64w+j suppressed by box i (64w+j > i)
   unsigned long long* diagcol;  // [E, NP] for box i: which earlier boxes of its own 64-block suppress it
   unsigned long long* keptbits; // [E, NW]
   unsigned long long* sortkeys; // [E, NP] scratch for the large-N rank sort
