@@ -165,6 +165,45 @@ typedef struct {
 
 int osd_match_forward(const osd_match_desc* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * 1x1 fusion conv matching mode on tcgen05 tensor cores (bf16 operands, fp32 accumulation).
+ *
+ * Replaces  `compress_dim_conv` of maskrcnn_benchmark/modeling/roi_heads/box_head/box_head.py:43-54 applied to
+ *           cat((x, support.expand_as(x)), dim=1) (:147-149), here on the FPN maps [B,C,H,W] (NCHW fp32):
+ *           Conv1x1(2C->2C) + GroupNorm(32,2C) + LeakyReLU + Conv1x1(2C->C) + GroupNorm(32,C) + LeakyReLU.
+ * The support half of conv1 is folded into a per-episode bias (W1 = [W1x | W1s]).  Weight operands are prepared
+ * once by the host: w1x_bf16 = bf16(W1[:, :C]) [2C, C]; w1s_t = W1[:, C:]^T fp32 [C, 2C]; w2_bf16 = bf16(W2) [C, 2C].
+ * stage OSD_FUSION_CONV1 writes the first convolution only (out[l] is [B,2C,H,W]); OSD_FUSION_FULL writes
+ * the module output (out[l] is [B,C,H,W]).
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum { OSD_FUSION_CONV1 = 0, OSD_FUSION_FULL = 1 } osd_fusion_stage;
+
+typedef struct {
+  int32_t num_levels;
+  int32_t batch;     /* B */
+  int32_t shots;     /* S */
+  int32_t channels;  /* C: 64, 128 or 256 */
+  int32_t stage;     /* osd_fusion_stage */
+  float gn_eps;      /* GroupNorm epsilon (torch default 1e-5) */
+  float lrelu_slope; /* 0.2 */
+  int32_t hw[OSD_MAX_LEVELS];
+  const void* feat[OSD_MAX_LEVELS];  /* device fp32 [B,C,H,W] */
+  const void* supp[OSD_MAX_LEVELS];  /* device fp32 [B*S, C] */
+  void* out[OSD_MAX_LEVELS];         /* device fp32 [B,2C,H,W] (CONV1) or [B,C,H,W] (FULL) */
+  const void* w1x_bf16;  /* device bf16 [2C, C] */
+  const float* w1s_t;    /* device fp32 [C, 2C] */
+  const float* b1;       /* device fp32 [2C] */
+  const float* gn1_w;    /* device fp32 [2C] */
+  const float* gn1_b;
+  const void* w2_bf16;   /* device bf16 [C, 2C] */
+  const float* b2;       /* device fp32 [C] */
+  const float* gn2_w;    /* device fp32 [C] */
+  const float* gn2_b;
+} osd_fusion_desc;
+
+int osd_fusion_workspace_bytes(const osd_fusion_desc* desc, size_t* bytes);
+int osd_fusion_forward(const osd_fusion_desc* desc, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

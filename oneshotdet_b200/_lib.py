@@ -43,6 +43,17 @@ class MatchDesc(ctypes.Structure):
                 ("out", ctypes.c_void_p * OSD_MAX_LEVELS)]
 
 
+class FusionDesc(ctypes.Structure):
+    _fields_ = [("num_levels", ctypes.c_int32), ("batch", ctypes.c_int32), ("shots", ctypes.c_int32),
+                ("channels", ctypes.c_int32), ("stage", ctypes.c_int32), ("gn_eps", ctypes.c_float),
+                ("lrelu_slope", ctypes.c_float), ("hw", ctypes.c_int32 * OSD_MAX_LEVELS),
+                ("feat", ctypes.c_void_p * OSD_MAX_LEVELS), ("supp", ctypes.c_void_p * OSD_MAX_LEVELS),
+                ("out", ctypes.c_void_p * OSD_MAX_LEVELS),
+                ("w1x_bf16", ctypes.c_void_p), ("w1s_t", ctypes.c_void_p), ("b1", ctypes.c_void_p),
+                ("gn1_w", ctypes.c_void_p), ("gn1_b", ctypes.c_void_p), ("w2_bf16", ctypes.c_void_p),
+                ("b2", ctypes.c_void_p), ("gn2_w", ctypes.c_void_p), ("gn2_b", ctypes.c_void_p)]
+
+
 # every symbol include/osd_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "osd_version": (ctypes.c_int, []),
@@ -58,6 +69,8 @@ SYMBOLS = {
                                             ctypes.POINTER(c_void_p), c_void_p, c_void_p, ctypes.c_size_t, c_void_p,
                                             c_void_p, c_void_p, c_void_p, c_void_p]),
     "osd_match_forward": (ctypes.c_int, [ctypes.POINTER(MatchDesc), c_void_p]),
+    "osd_fusion_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(FusionDesc), ctypes.POINTER(ctypes.c_size_t)]),
+    "osd_fusion_forward": (ctypes.c_int, [ctypes.POINTER(FusionDesc), c_void_p, ctypes.c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -627,7 +627,7 @@ extern "C" int osd_fusion_forward(const osd_fusion_desc* d, void* workspace, siz
   const bool full = d->stage == OSD_FUSION_FULL;
   if (full)
     OSD_REQUIRE(d->w2_bf16 && d->b2 && d->gn1_w && d->gn1_b && d->gn2_w && d->gn2_b, "osd_fusion_forward: conv2 / GroupNorm parameters are null");
-  OSD_CUDA(cudaMemsetAsync(stats1, 0, sizeof(double) * (size_t)nl * B * 64 * 2, stream));  // stats1 and stats2 are adjacent? no: zero both
+  OSD_CUDA(cudaMemsetAsync(stats1, 0, sizeof(double) * (size_t)nl * B * 64, stream));
   OSD_CUDA(cudaMemsetAsync(stats2, 0, sizeof(double) * (size_t)nl * B * 64, stream));
 
   // ---- folded bias
