@@ -15,12 +15,15 @@
 //  * Accumulators live in TMEM: (Cout/128) tiles of 128 x 64 fp32, double buffered (512 columns for Cout = 512),
 //    so the epilogue of tile i overlaps the MMAs of tile i+1.  Epilogue warps read TMEM (tcgen05.ld 32x32b), add
 //    the bias, accumulate GroupNorm statistics (fp64 atomics per (episode, group)) and store NCHW rows.
-//  * Warp roles (320 threads, 1 CTA/SM, persistent over pixel tiles): warps 0-3 epilogue, 4-7 activation
-//    producers, warp 8 TMA producer (weights), warp 9 MMA issuer + TMEM owner.  All hand-offs are mbarriers.
+//  * Warp roles (576 threads, 1 CTA/SM, persistent over pixel tiles): warps 0-7 epilogue, 8-15 activation
+//    producers, warp 16 TMA producer (weights), warp 17 MMA issuer + TMEM owner.  All hand-offs are mbarriers.
+//    The epilogue transposes each 32x32 accumulator block through a swizzled shared-memory stage so that global
+//    stores are 128-byte row segments (4 rows per warp instruction) instead of 32 scattered 16-byte pieces.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "osd_common.cuh"
+#include "osd_device_utils.cuh"
 
 namespace osd {
 namespace {
@@ -29,8 +32,10 @@ constexpr int kBlockN = 64;   // pixels per tile (UMMA N)
 constexpr int kBlockK = 64;   // K elements per weight stage (128 bytes of bf16 = one swizzle row)
 constexpr int kUmmaM = 128;
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 320;
-constexpr int kEpiWarps = 4, kProdWarps = 4;
+constexpr int kEpiWarps = 8, kProdWarps = 8;          // warps 0-7 epilogue, 8-15 activation producers
+constexpr int kTmaWarp = 16, kMmaWarp = 17;
+constexpr int kThreads = 32 * 18;
+constexpr int kStageBytesPerWarp = 4096;              // epilogue transpose buffer: 32 rows x 32 fp32
 constexpr int kMaxStages = 4;
 constexpr uint32_t kSpinLimit = 1u << 26;  // a lost arrival traps instead of hanging the GPU
 
@@ -159,9 +164,7 @@ struct ConvArgs {
   float eps, slope;
   const float* bias;    // [nl, B, Cout] (bias_level_stride / bias_img_stride may be 0)
   int bias_level_stride, bias_img_stride;
-  const double* stats_in;   // [nl, B, 32, 2] sum / sum of squares of the input's producer conv
-  const float* gn_in_w;     // [Cin]
-  const float* gn_in_b;     // [Cin]
+  const float2* coef_in;    // [nl, B, Cin] (scale, shift) of the input's GroupNorm (xform = 1)
   double* stats_out;        // [nl, B, 32, 2]
   ConvLevel lv[OSD_MAX_LEVELS];
 };
@@ -202,7 +205,8 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) 
   const uint32_t a_stage_bytes = (uint32_t)A.num_mt * 16384u;
   const uint32_t sB = smem_base;
   const uint32_t sA = sB + 2u * b_bytes;
-  const uint32_t sBar = sA + (uint32_t)A.stages * a_stage_bytes;
+  const uint32_t sStage = sA + (uint32_t)A.stages * a_stage_bytes;   // epilogue transpose buffers
+  const uint32_t sBar = sStage + kEpiWarps * kStageBytesPerWarp;
   // barrier slots (8 bytes each)
   const uint32_t a_full = sBar, a_empty = sBar + 8u * kMaxStages;
   const uint32_t b_full = sBar + 16u * kMaxStages, b_empty = b_full + 16u;
@@ -213,7 +217,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = (A.num_mt * 2 * kBlockN <= 128) ? 128u : (A.num_mt * 2 * kBlockN <= 256 ? 256u : 512u);
 
-  if (warp == 8 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_w);
     for (int s = 0; s < A.stages; ++s) {
       mbar_init(a_full + 8u * s, 1);
@@ -227,13 +231,13 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) 
     }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
 
-  if (warp == 8) {
+  if (warp == kTmaWarp) {
     // ===================== TMA producer: weight chunks [Cout x 64] =====================
     if (lane == 0) {
       uint32_t c = 0;
@@ -247,7 +251,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) 
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(kUmmaM, kBlockN);
@@ -279,12 +283,11 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) 
         umma_commit(b_empty + 8u * buf);  // activation buffer may be refilled
       }
     }
-  } else if (warp >= 4) {
-    // ===================== activation producers (warps 4-7) =====================
-    const int pw = warp - 4;
+  } else if (warp >= kEpiWarps) {
+    // ===================== activation producers (warps 8-15) =====================
+    const int pw = warp - kEpiWarps;
     const int rsub = lane >> 3;   // row inside a group of 4
     const int j = lane & 7;       // 16-byte chunk (8 pixels) inside the 128-byte row
-    const int gs_in = A.Cin / 32; // channels per GroupNorm group of the input
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
@@ -294,14 +297,13 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) 
       const float* src = L.in + (size_t)t.img * A.Cin * L.hw + t.px0 + j * 8;
       const bool vec_ok = ((L.hw & 3) == 0) && (t.px0 + j * 8 + 8 <= L.hw);
       const int nleft = L.hw - (t.px0 + j * 8);  // valid pixels from this chunk's start (may be <= 0)
-      const double* st = A.xform ? A.stats_in + ((size_t)t.level * A.B + t.img) * 64 : nullptr;
-      const double inv_cnt = A.xform ? 1.0 / ((double)gs_in * (double)L.hw) : 0.0;
-      for (int k0 = pw * 4 + rsub; k0 < A.Cin; k0 += 16 * 4) {
-        // 4 rows in flight per thread
+      const float2* coef = A.xform ? A.coef_in + ((size_t)t.level * A.B + t.img) * A.Cin : nullptr;
+      for (int k0 = pw * 4 + rsub; k0 < A.Cin; k0 += 32 * 4) {
+        // 4 rows (8 x 128-bit loads) in flight per thread, 32 KB per SM
         float v[4][8];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int k = k0 + u * 16;
+          const int k = k0 + u * 32;
           const float* p = src + (size_t)k * L.hw;
           if (k < A.Cin) {
             if (vec_ok) {
@@ -317,19 +319,14 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) 
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int k = k0 + u * 16;
+          const int k = k0 + u * 32;
           if (k < A.Cin) {
             if (A.xform) {
-              // GroupNorm (biased variance, as torch) + LeakyReLU of the producer conv's output
-              const int g = k / gs_in;
-              const double mean = st[2 * g] * inv_cnt;
-              const double var = fmax(st[2 * g + 1] * inv_cnt - mean * mean, 0.0);
-              const float rstd = (float)(1.0 / sqrt(var + (double)A.eps));
-              const float sc = A.gn_in_w[k] * rstd;
-              const float sh = A.gn_in_b[k] - (float)mean * sc;
+              // GroupNorm + LeakyReLU of the producer conv's output: y = x * scale + shift
+              const float2 cf = __ldg(coef + k);
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                float y = fmaf(v[u][q], sc, sh);
+                float y = fmaf(v[u][q], cf.x, cf.y);
                 y = y > 0.f ? y : y * A.slope;
                 v[u][q] = (q < nleft) ? y : 0.f;   // padded pixels stay exactly zero
               }
@@ -348,9 +345,13 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) 
       if (lane == 0) mbar_arrive(b_full + 8u * buf);
     }
   } else {
-    // ===================== epilogue (warps 0-3; warp q owns TMEM lanes 32q..32q+31) =====================
-    const int q = warp;
+    // ===================== epilogue (warps 0-7) =====================
+    // warp w reads TMEM lanes 32q..32q+31 (q = w & 3: the hardware's lane quadrant of the warp) and the 32-pixel
+    // column half h = w >> 2 of every 128-channel accumulator tile
+    const int q = warp & 3, h = warp >> 2;
     const int gs_out = A.Cout / 32;  // channels per GroupNorm group of the output (power of two <= 16)
+    const uint32_t stage = sStage + (uint32_t)warp * kStageBytesPerWarp;
+    float* stage_gen = reinterpret_cast<float*>(gen_base + (stage - smem_base));
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
@@ -359,51 +360,62 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) 
       mbar_wait(t_full + 8u * buf, ph);
       tc_fence_after();
       const bool vec_ok = (L.hw & 3) == 0;
+      const int pxh = h * 32;                       // first pixel of this warp's half inside the tile
+      const int nval = min(32, t.nvalid - pxh);     // valid pixels in the half (may be <= 0)
       for (int mt = 0; mt < A.num_mt; ++mt) {
-        const int oc = mt * kUmmaM + q * 32 + lane;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(A.num_mt * kBlockN) + mt * kBlockN;
-        float s1 = 0.f, s2 = 0.f;
+        const int oc0 = mt * kUmmaM + q * 32;       // first channel of this warp's 32 rows
+        const int oc = oc0 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(A.num_mt * kBlockN) +
+                               mt * kBlockN + pxh;
         const bool oc_ok = oc < A.Cout;
         const float bias = oc_ok ? A.bias[(size_t)t.level * A.bias_level_stride + (size_t)t.img * A.bias_img_stride + oc] : 0.f;
-        float* dst = L.out + ((size_t)t.img * A.Cout + (oc_ok ? oc : 0)) * L.hw + t.px0;
+        uint32_t r[32];
+        tmem_ld32(taddr, r);
+        tmem_ld_wait();
+        float s1 = 0.f, s2 = 0.f;
+        // bias, statistics, and the row (channel) of this lane into the swizzled stage: 16-byte chunk c of row
+        // `lane` lives at chunk (c ^ (lane & 7))
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld32(taddr + half * 32, r);
-          tmem_ld_wait();
-          if (oc_ok) {
+        for (int c = 0; c < 8; ++c) {
+          float y[4];
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              const int px = half * 32 + c;
-              float y0 = __uint_as_float(r[c]) + bias, y1 = __uint_as_float(r[c + 1]) + bias;
-              float y2 = __uint_as_float(r[c + 2]) + bias, y3 = __uint_as_float(r[c + 3]) + bias;
-              if (vec_ok) {
-                if (px < t.nvalid) {  // hw % 4 == 0 and px % 4 == 0: the group is entirely valid
-                  *reinterpret_cast<float4*>(dst + px) = make_float4(y0, y1, y2, y3);
-                  s1 += (y0 + y1) + (y2 + y3);
-                  s2 += (y0 * y0 + y1 * y1) + (y2 * y2 + y3 * y3);
-                }
-              } else {
-                const float ys[4] = {y0, y1, y2, y3};
+          for (int e = 0; e < 4; ++e) {
+            y[e] = __uint_as_float(r[4 * c + e]) + bias;
+            if (4 * c + e < nval) {
+              s1 += y[e];
+              s2 += y[e] * y[e];
+            }
+          }
+          const uint32_t a = stage + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(y[0]), "f"(y[1]), "f"(y[2]), "f"(y[3]) : "memory");
+        }
+        __syncwarp();
+        // read back transposed: 8 lanes cover the 128 bytes of one row, 4 rows per instruction
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  if (px + e < t.nvalid) {
-                    dst[px + e] = ys[e];
-                    s1 += ys[e];
-                    s2 += ys[e] * ys[e];
-                  }
-                }
-              }
+        for (int i = 0; i < 8; ++i) {
+          const int row = 4 * i + (lane >> 3), c = lane & 7;
+          const int orow = oc0 + row;
+          const float4 v = *reinterpret_cast<const float4*>(stage_gen + row * 32 + ((c ^ (row & 7)) << 2));
+          if (orow < A.Cout) {
+            float* dst = L.out + ((size_t)t.img * A.Cout + orow) * L.hw + t.px0 + pxh + 4 * c;
+            if (vec_ok) {
+              if (4 * c < nval) *reinterpret_cast<float4*>(dst) = v;   // hw % 4 == 0: a chunk is all-valid or all-padding
+            } else {
+              const float vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (4 * c + e < nval) dst[e] = vs[e];
             }
           }
         }
+        __syncwarp();  // the stage is rewritten by the next accumulator tile
         if (A.stats_out) {
           // GroupNorm statistics of this conv's output: reduce over the gs_out consecutive channels (lanes) of a group
           for (int o = 1; o < gs_out; o <<= 1) {
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
           }
-          if (oc_ok && (lane & (gs_out - 1)) == 0) {
+          if (oc_ok && (lane & (gs_out - 1)) == 0 && nval > 0) {
             double* so = A.stats_out + ((size_t)t.level * A.B + t.img) * 64 + 2 * (oc / gs_out);
             atomicAdd(so, (double)s1);
             atomicAdd(so + 1, (double)s2);
@@ -418,7 +430,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -436,8 +448,11 @@ struct BiasArgs {
   float* bias_eff;                    // [nl, B, Cout]
 };
 
-__global__ void __launch_bounds__(512) fusion_bias_kernel(BiasArgs A) {
-  extern __shared__ float pooled[];  // [C]
+// grid (nl*B, Cout/64): 256 threads = 64 output channels x 4 slices of the C inputs, reduced through shared memory
+__global__ void __launch_bounds__(256) fusion_bias_kernel(BiasArgs A) {
+  extern __shared__ float bias_smem[];  // pooled[C] | partial[4][64]
+  float* pooled = bias_smem;
+  float* part = bias_smem + A.C;
   const int l = blockIdx.x / A.B, b = blockIdx.x % A.B;
   const float* s = A.supp[l] + (size_t)b * A.S * A.C;
   for (int c = threadIdx.x; c < A.C; c += blockDim.x) {
@@ -446,40 +461,110 @@ __global__ void __launch_bounds__(512) fusion_bias_kernel(BiasArgs A) {
     pooled[c] = A.S == 1 ? acc : __fdiv_rn(acc, (float)A.S);
   }
   __syncthreads();
-  for (int oc = threadIdx.x; oc < A.Cout; oc += blockDim.x) {
-    float acc = A.b1[oc];
-    for (int c = 0; c < A.C; ++c) acc = fmaf(A.w1s_t[(size_t)c * A.Cout + oc], pooled[c], acc);
-    A.bias_eff[((size_t)l * A.B + b) * A.Cout + oc] = acc;
+  const int ocl = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int oc = blockIdx.y * 64 + ocl;
+  const int per = A.C / 4;
+  float acc = 0.f;
+  if (oc < A.Cout) {
+    const float* w = A.w1s_t + (size_t)(slice * per) * A.Cout + oc;
+#pragma unroll 8
+    for (int c = 0; c < per; ++c) acc = fmaf(w[(size_t)c * A.Cout], pooled[slice * per + c], acc);
   }
+  part[slice * 64 + ocl] = acc;
+  __syncthreads();
+  if (slice == 0 && oc < A.Cout)
+    A.bias_eff[((size_t)l * A.B + b) * A.Cout + oc] = A.b1[oc] + ((part[ocl] + part[64 + ocl]) + (part[128 + ocl] + part[192 + ocl]));
 }
 
-// out = LeakyReLU(GroupNorm(32, C)(y)) in place, per (level, episode, channel) plane
-struct GnArgs {
+// (scale, shift) of GroupNorm(32, C) per (level, episode, channel) from the fp64 sums the conv epilogue accumulated:
+//   y = x * scale + shift,  scale = gamma * rstd,  shift = beta - mean * scale   (biased variance, as torch)
+struct CoefArgs {
   int nl, B, C;
-  float eps, slope;
+  float eps;
   const double* stats;  // [nl, B, 32, 2]
   const float* gn_w;
   const float* gn_b;
-  float* y[OSD_MAX_LEVELS];
+  float2* coef;         // [nl, B, C]
   int hw[OSD_MAX_LEVELS];
 };
 
-__global__ void __launch_bounds__(256) fusion_gn_lrelu_kernel(GnArgs A) {
-  const int l = blockIdx.z, plane = blockIdx.y;  // plane = b * C + c
-  const int b = plane / A.C, c = plane - b * A.C;
-  const int hw = A.hw[l];
+__global__ void __launch_bounds__(512) fusion_gn_coef_kernel(CoefArgs A) {
+  const int l = blockIdx.x / A.B, b = blockIdx.x % A.B;
   const int gs = A.C / 32;
-  const double* st = A.stats + ((size_t)l * A.B + b) * 64 + 2 * (c / gs);
-  const double inv_cnt = 1.0 / ((double)gs * (double)hw);
-  const double mean = st[0] * inv_cnt;
-  const double var = fmax(st[1] * inv_cnt - mean * mean, 0.0);
-  const float rstd = (float)(1.0 / sqrt(var + (double)A.eps));
-  const float sc = A.gn_w[c] * rstd;
-  const float sh = A.gn_b[c] - (float)mean * sc;
-  float* y = A.y[l] + (size_t)plane * hw;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
-    float v = fmaf(y[i], sc, sh);
-    y[i] = v > 0.f ? v : v * A.slope;
+  const double inv_cnt = 1.0 / ((double)gs * (double)A.hw[l]);
+  for (int c = threadIdx.x; c < A.C; c += blockDim.x) {
+    const double* st = A.stats + ((size_t)l * A.B + b) * 64 + 2 * (c / gs);
+    const double mean = st[0] * inv_cnt;
+    const double var = fmax(st[1] * inv_cnt - mean * mean, 0.0);
+    const float rstd = (float)(1.0 / sqrt(var + (double)A.eps));
+    const float sc = A.gn_w[c] * rstd;
+    A.coef[((size_t)l * A.B + b) * A.C + c] = make_float2(sc, A.gn_b[c] - (float)mean * sc);
+  }
+}
+
+// out = LeakyReLU(y * scale[plane] + shift[plane]) in place: persistent grid, 128-bit loads/stores, 4 in flight
+struct GnLevel {
+  float* y;
+  const float2* coef;   // [B*C]
+  uint32_t hw;
+  uint32_t elems;       // B * C * hw
+  uint32_t chunk_begin;
+  FastDiv div_hw;
+};
+struct GnArgs {
+  int nl;
+  float slope;
+  uint32_t total_chunks;
+  GnLevel lv[OSD_MAX_LEVELS];
+};
+constexpr int kGnThreads = 256, kGnVec = 4, kGnChunk = kGnThreads * kGnVec;
+
+__global__ void __launch_bounds__(kGnThreads, 5) fusion_gn_lrelu_kernel(GnArgs A) {
+  for (uint32_t chunk = blockIdx.x; chunk < A.total_chunks; chunk += gridDim.x) {
+    int li = 0;
+#pragma unroll
+    for (int k = 1; k < OSD_MAX_LEVELS; ++k)
+      if (k < A.nl && chunk >= A.lv[k].chunk_begin) li = k;
+    const GnLevel& L = A.lv[li];
+    const uint32_t nvec = (L.elems + 3) / 4;
+    const uint32_t v0 = (chunk - L.chunk_begin) * kGnChunk;
+    float4 in[kGnVec];
+    uint32_t pl[kGnVec];
+    bool whole[kGnVec];
+#pragma unroll
+    for (int j = 0; j < kGnVec; ++j) {
+      const uint32_t v = v0 + j * kGnThreads + threadIdx.x;
+      whole[j] = false;
+      if (v < nvec) {
+        const uint32_t g = v * 4;
+        pl[j] = fdiv(g, L.div_hw);
+        const uint32_t r = g - pl[j] * L.hw;
+        whole[j] = (r + 4 <= L.hw) && (g + 4 <= L.elems) && ((L.hw & 3) == 0 || ((reinterpret_cast<uintptr_t>(L.y + g) & 15) == 0));
+        if (whole[j]) in[j] = *reinterpret_cast<const float4*>(L.y + g);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kGnVec; ++j) {
+      const uint32_t v = v0 + j * kGnThreads + threadIdx.x;
+      if (v >= nvec) continue;
+      const uint32_t g = v * 4;
+      if (whole[j]) {
+        const float2 cf = __ldg(L.coef + pl[j]);
+        float4 o;
+        o.x = fmaf(in[j].x, cf.x, cf.y); o.x = o.x > 0.f ? o.x : o.x * A.slope;
+        o.y = fmaf(in[j].y, cf.x, cf.y); o.y = o.y > 0.f ? o.y : o.y * A.slope;
+        o.z = fmaf(in[j].z, cf.x, cf.y); o.z = o.z > 0.f ? o.z : o.z * A.slope;
+        o.w = fmaf(in[j].w, cf.x, cf.y); o.w = o.w > 0.f ? o.w : o.w * A.slope;
+        *reinterpret_cast<float4*>(L.y + g) = o;
+      } else {
+        for (int k = 0; k < 4 && g + k < L.elems; ++k) {
+          const uint32_t p = fdiv(g + k, L.div_hw);
+          const float2 cf = __ldg(L.coef + p);
+          float o = fmaf(L.y[g + k], cf.x, cf.y);
+          L.y[g + k] = o > 0.f ? o : o * A.slope;
+        }
+      }
+    }
   }
 }
 
@@ -537,12 +622,13 @@ int plan_conv(int Cin, int Cout, ConvPlan* p) {
   const int num_mt = (Cout + kUmmaM - 1) / kUmmaM;
   const size_t b_bytes = 2 * (size_t)Cin * 128;
   const size_t a_stage = (size_t)num_mt * 16384;
-  const size_t budget = 220 * 1024;
-  int stages = (int)((budget - b_bytes - 1024 - 256) / a_stage);
+  const size_t fixed = 1024 + 256 + (size_t)kEpiWarps * kStageBytesPerWarp;   // alignment slack, barriers, epilogue stages
+  const size_t budget = 227 * 1024;
+  int stages = (int)((budget - b_bytes - fixed) / a_stage);
   if (stages > kMaxStages) stages = kMaxStages;
   OSD_REQUIRE(stages >= 2, "fusion: %d -> %d channels does not fit in shared memory", Cin, Cout);
   p->stages = stages;
-  p->smem = 1024 + b_bytes + stages * a_stage + 256;
+  p->smem = fixed + b_bytes + stages * a_stage;
   return OSD_OK;
 }
 
@@ -555,8 +641,8 @@ int launch_conv(const CUtensorMap& map, ConvArgs& A, cudaStream_t stream) {
   A.num_kc = A.Cin / kBlockK;
   static thread_local size_t configured = 0;
   if (p.smem > configured) {
-    OSD_CUDA(cudaFuncSetAttribute(conv1x1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    configured = 225 * 1024;
+    OSD_CUDA(cudaFuncSetAttribute(conv1x1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 227 * 1024;
   }
   if (A.total_tiles <= 0) return OSD_OK;
   const int grid = A.total_tiles < kNumSMs ? A.total_tiles : kNumSMs;
@@ -572,12 +658,16 @@ int launch_conv(const CUtensorMap& map, ConvArgs& A, cudaStream_t stream) {
 // C ABI
 // ------------------------------------------------------------------------------------------------
 static size_t fusion_carve(const osd_fusion_desc* d, osd::Carver& c, float** y1, double** stats1, double** stats2,
-                           float** bias_eff) {
+                           float** bias_eff, float2** coef1 = nullptr, float2** coef2 = nullptr) {
   size_t elems = 0;
   for (int l = 0; l < d->num_levels; ++l) elems += (size_t)d->batch * 2 * d->channels * d->hw[l];
   *stats1 = c.take<double>((size_t)d->num_levels * d->batch * 64);
   *stats2 = c.take<double>((size_t)d->num_levels * d->batch * 64);
   *bias_eff = c.take<float>((size_t)d->num_levels * d->batch * 2 * d->channels);
+  float2* k1 = c.take<float2>((size_t)d->num_levels * d->batch * 2 * d->channels);
+  float2* k2 = c.take<float2>((size_t)d->num_levels * d->batch * d->channels);
+  if (coef1) *coef1 = k1;
+  if (coef2) *coef2 = k2;
   *y1 = d->stage == OSD_FUSION_CONV1 ? nullptr : c.take<float>(elems);
   return c.total();
 }
@@ -618,7 +708,8 @@ extern "C" int osd_fusion_forward(const osd_fusion_desc* d, void* workspace, siz
   Carver c(workspace);
   float *y1, *bias_eff;
   double *stats1, *stats2;
-  const size_t need = fusion_carve(d, c, &y1, &stats1, &stats2, &bias_eff);
+  float2 *coef1, *coef2;
+  const size_t need = fusion_carve(d, c, &y1, &stats1, &stats2, &bias_eff, &coef1, &coef2);
   if (need > workspace_bytes) {
     set_error("osd_fusion_forward: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
     return OSD_ERR_WORKSPACE;
@@ -638,7 +729,7 @@ extern "C" int osd_fusion_forward(const osd_fusion_desc* d, void* workspace, siz
     BA.supp[l] = static_cast<const float*>(d->supp[l]);
   }
   BA.w1s_t = d->w1s_t; BA.b1 = d->b1; BA.bias_eff = bias_eff;
-  fusion_bias_kernel<<<nl * B, 512, C * sizeof(float), stream>>>(BA);
+  fusion_bias_kernel<<<dim3((unsigned)(nl * B), (unsigned)((C2 + 63) / 64)), 256, (C + 256) * sizeof(float), stream>>>(BA);
   OSD_LAUNCH_CHECK("fusion_bias_kernel");
 
   // ---- conv1: x [B,C,HW] -> y1 [B,2C,HW] (+ folded bias, GroupNorm-1 statistics)
@@ -665,14 +756,21 @@ extern "C" int osd_fusion_forward(const osd_fusion_desc* d, void* workspace, siz
   rc = launch_conv(map1, A1, stream);
   if (rc != OSD_OK || !full) return rc;
 
-  // ---- conv2: LeakyReLU(GN1(y1)) [B,2C,HW] -> y2 [B,C,HW] (+ b2, GroupNorm-2 statistics)
+  // ---- GroupNorm-1 coefficients, then conv2: LeakyReLU(GN1(y1)) [B,2C,HW] -> y2 [B,C,HW] (+ b2, GN-2 statistics)
+  CoefArgs K1{};
+  K1.nl = nl; K1.B = B; K1.C = C2; K1.eps = d->gn_eps; K1.stats = stats1; K1.gn_w = d->gn1_w; K1.gn_b = d->gn1_b;
+  K1.coef = coef1;
+  for (int l = 0; l < nl; ++l) K1.hw[l] = d->hw[l];
+  fusion_gn_coef_kernel<<<nl * B, 512, 0, stream>>>(K1);
+  OSD_LAUNCH_CHECK("fusion_gn_coef_kernel");
+
   CUtensorMap map2;
   rc = make_weight_map(d->w2_bf16, C, C2, &map2);
   if (rc != OSD_OK) return rc;
   ConvArgs A2{};
   A2.nl = nl; A2.B = B; A2.Cin = C2; A2.Cout = C; A2.xform = 1; A2.eps = d->gn_eps; A2.slope = d->lrelu_slope;
   A2.bias = d->b2; A2.bias_level_stride = 0; A2.bias_img_stride = 0;
-  A2.stats_in = stats1; A2.gn_in_w = d->gn1_w; A2.gn_in_b = d->gn1_b;
+  A2.coef_in = coef1;
   A2.stats_out = stats2;
   for (int l = 0; l < nl; ++l) {
     ConvLevel& L = A2.lv[l];
@@ -686,18 +784,31 @@ extern "C" int osd_fusion_forward(const osd_fusion_desc* d, void* workspace, siz
   rc = launch_conv(map2, A2, stream);
   if (rc != OSD_OK) return rc;
 
-  // ---- GroupNorm-2 + LeakyReLU in place
+  // ---- GroupNorm-2 + LeakyReLU in place (streaming pass)
+  CoefArgs K2{};
+  K2.nl = nl; K2.B = B; K2.C = C; K2.eps = d->gn_eps; K2.stats = stats2; K2.gn_w = d->gn2_w; K2.gn_b = d->gn2_b;
+  K2.coef = coef2;
+  for (int l = 0; l < nl; ++l) K2.hw[l] = d->hw[l];
+  fusion_gn_coef_kernel<<<nl * B, 512, 0, stream>>>(K2);
+  OSD_LAUNCH_CHECK("fusion_gn_coef_kernel");
   GnArgs G{};
-  G.nl = nl; G.B = B; G.C = C; G.eps = d->gn_eps; G.slope = d->lrelu_slope;
-  G.stats = stats2; G.gn_w = d->gn2_w; G.gn_b = d->gn2_b;
-  int max_hw = 1;
+  G.nl = nl; G.slope = d->lrelu_slope;
+  uint64_t chunks = 0;
   for (int l = 0; l < nl; ++l) {
-    G.y[l] = static_cast<float*>(d->out[l]);
-    G.hw[l] = d->hw[l];
-    if (d->hw[l] > max_hw) max_hw = d->hw[l];
+    GnLevel& L = G.lv[l];
+    L.y = static_cast<float*>(d->out[l]);
+    L.coef = coef2 + (size_t)l * B * C;
+    L.hw = (uint32_t)d->hw[l];
+    L.elems = (uint32_t)((size_t)B * C * d->hw[l]);
+    L.chunk_begin = (uint32_t)chunks;
+    L.div_hw = make_fastdiv(L.hw);
+    chunks += ((uint64_t)L.elems + 4ull * kGnChunk - 1) / (4ull * kGnChunk);
   }
-  dim3 grid((unsigned)((max_hw + 2047) / 2048), (unsigned)(B * C), (unsigned)nl);
-  fusion_gn_lrelu_kernel<<<grid, 256, 0, stream>>>(G);
-  OSD_LAUNCH_CHECK("fusion_gn_lrelu_kernel");
+  G.total_chunks = (uint32_t)chunks;
+  const int ctas = (int)std::min<uint64_t>(chunks, (uint64_t)kNumSMs * 16);
+  if (ctas > 0) {
+    fusion_gn_lrelu_kernel<<<ctas, kGnThreads, 0, stream>>>(G);
+    OSD_LAUNCH_CHECK("fusion_gn_lrelu_kernel");
+  }
   return OSD_OK;
 }

@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 
 #include "osd_common.cuh"
+#include "osd_device_utils.cuh"
 
 namespace osd {
 namespace {
@@ -16,20 +17,6 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kVecPerThread = 4;                     // independent 128-bit loads in flight per thread
 constexpr int kChunkVec = kThreads * kVecPerThread;  // 1024 x 16 B = 16 KB of output per chunk
-
-struct FastDiv {  // exact n / d for 32-bit n, d (Lemire): q = (M * n) >> 64
-  uint64_t M;
-  uint32_t d;
-};
-__host__ FastDiv make_fastdiv(uint32_t d) {
-  FastDiv f;
-  f.d = d;
-  f.M = d > 1 ? (0xFFFFFFFFFFFFFFFFull / d + 1ull) : 0ull;
-  return f;
-}
-__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
-  return f.d > 1 ? (uint32_t)__umul64hi(f.M, (uint64_t)n) : n;
-}
 
 struct Level {
   const void* feat;

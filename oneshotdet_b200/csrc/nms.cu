@@ -30,7 +30,8 @@ constexpr int kMergeStage = 6 * kChunk;   // keys staged per window by the merge
 constexpr int kMaskRows = 128;       // rows per mask tile (one thread per row)
 constexpr int kMaskCols = 128;       // columns per mask tile (2 words of 64)
 constexpr int kSweepThreads = 512;
-constexpr int kSweepPre = 8;         // mask words per thread the sweep keeps in flight for the next column
+constexpr int kSweepPre = 8;         // rows per thread whose column words the sweep prefetches (small passes)
+constexpr int kSweepDepth = 4;       // columns in flight in the sweep's cp.async ring
 
 typedef unsigned long long u64;
 
@@ -435,6 +436,14 @@ struct SweepArgs {
   int passthrough;
 };
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ u64 warp_or_u64(u64 v) {
   const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
   const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
@@ -471,50 +480,57 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W
   const u64* __restrict__ dc = W.diagcol + (size_t)e * W.NP;
   const int blim = min(A.blk_end, nblk);
   const int nb = blim - A.blk_begin;  // blocks swept by this pass (may be <= 0)
-  for (int w = tid; w < W.NW; w += kSweepThreads) kw[w] = (w < A.blk_begin) ? kb[w] : 0ull;
-  int count = W.kcount[e];
-  // rows of a pass that ends within 4096 boxes fit in registers, kSweepPre per thread: prefetch one column ahead
+  // A pass that ends within 4096 boxes ("small": the early-exit passes) keeps kSweepDepth columns in flight: every
+  // thread cp.asyncs the words of its own rows (tid + v*512) into a private slice of a shared-memory ring and reads
+  // them back itself, so no barrier is needed for the ring, and the L2 latency is off the serial chain.  The
+  // transposed diagonal tiles of the whole pass are preloaded as well.
   const bool small = 64 * blim <= kSweepThreads * kSweepPre;
-  u64 cur[kSweepPre], nxt[kSweepPre];
-#pragma unroll
-  for (int v = 0; v < kSweepPre; ++v) cur[v] = nxt[v] = 0ull;
+  u64* ring = kw + W.NW;                                           // [kSweepDepth][kSweepThreads * kSweepPre]
+  u64* dcs = ring + kSweepDepth * kSweepThreads * kSweepPre;       // [kSweepThreads * kSweepPre]
+  constexpr int kRingCol = kSweepThreads * kSweepPre;
+  auto prefetch_col = [&](int col, int slot) {
+    const u64* src = maskT + (size_t)col * W.NP;
+    u64* dst = ring + slot * kRingCol;
+    for (int row = tid; row < 64 * col; row += kSweepThreads) cp_async8(dst + row, src + row);
+  };
   if (small && nb > 0) {
 #pragma unroll
-    for (int v = 0; v < kSweepPre; ++v) {
-      const int row = tid + v * kSweepThreads;
-      if (row < 64 * A.blk_begin) cur[v] = maskT[(size_t)A.blk_begin * W.NP + row];
+    for (int d = 0; d < kSweepDepth - 1; ++d) {
+      if (d < nb) prefetch_col(A.blk_begin + d, d);
+      cp_async_commit();
     }
+    for (int i = tid; i < 64 * nb; i += kSweepThreads) dcs[i] = dc[64 * A.blk_begin + i];
   }
+  for (int w = tid; w < W.NW; w += kSweepThreads) kw[w] = (w < A.blk_begin) ? kb[w] : 0ull;
+  int count = W.kcount[e];
   __syncthreads();
   int it = 0;
   for (; it < nb; ++it) {
     const int blk = A.blk_begin + it;
     u64 c_lo = 0ull, c_hi = 0ull;
-    if (warp == 0) {
-      c_lo = dc[64 * blk + lane];
-      c_hi = dc[64 * blk + 32 + lane];
-    }
-    if (small && it + 1 < nb) {
-#pragma unroll
-      for (int v = 0; v < kSweepPre; ++v) {
-        const int row = tid + v * kSweepThreads;
-        nxt[v] = (row < 64 * (blk + 1)) ? maskT[(size_t)(blk + 1) * W.NP + row] : 0ull;
-      }
-    }
-    // suppression word of this block: OR over the kept earlier boxes
     u64 acc = 0ull;
     if (small) {
-#pragma unroll
-      for (int v = 0; v < kSweepPre; ++v) {
-        const int row = tid + v * kSweepThreads;
-        if (row < 64 * blk && ((kw[row >> 6] >> (row & 63)) & 1ull)) acc |= cur[v];
+      if (it + kSweepDepth - 1 < nb) prefetch_col(blk + kSweepDepth - 1, (it + kSweepDepth - 1) % kSweepDepth);
+      cp_async_commit();
+      cp_async_wait<kSweepDepth - 1>();  // this thread's words of column `blk` have landed
+      const u64* colw = ring + (it % kSweepDepth) * kRingCol;
+      for (int row = tid; row < 64 * blk; row += kSweepThreads)
+        if ((kw[row >> 6] >> (row & 63)) & 1ull) acc |= colw[row];
+      if (warp == 0) {
+        c_lo = dcs[64 * it + lane];
+        c_hi = dcs[64 * it + 32 + lane];
       }
     } else {
+      if (warp == 0) {
+        c_lo = dc[64 * blk + lane];
+        c_hi = dc[64 * blk + 32 + lane];
+      }
       const u64* col = maskT + (size_t)blk * W.NP;
 #pragma unroll 4
       for (int row = tid; row < 64 * blk; row += kSweepThreads)
         if ((kw[row >> 6] >> (row & 63)) & 1ull) acc |= col[row];
     }
+    // suppression word of this block: OR over the kept earlier boxes
     acc = warp_or_u64(acc);
     if (lane == 0) partial[warp] = acc;
     __syncthreads();
@@ -542,13 +558,12 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W
     }
     __syncthreads();
     count += s_nk;
-#pragma unroll
-    for (int v = 0; v < kSweepPre; ++v) cur[v] = nxt[v];
     if (count >= A.stop) {
       ++it;
       break;
     }
   }
+  cp_async_wait<0>();
   const int blk_next = A.blk_begin + (nb > 0 ? it : 0);
   const bool finished = (count >= A.stop) || (blk_next >= nblk);
   if (finished) {
@@ -707,7 +722,7 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
   // ---- mask + sweep, in passes over growing prefixes of the visiting order.  Without early exit there is one
   //      pass; with it, the first pass covers just enough boxes to keep post_top_n + 1 if little is suppressed,
   //      the second a 30 % larger prefix, the last everything.  Finished episodes skip later passes on the device.
-  const size_t sweep_smem = (size_t)W.NW * sizeof(u64);
+  const size_t sweep_smem = ((size_t)W.NW + (size_t)(kSweepDepth + 1) * kSweepThreads * kSweepPre) * sizeof(u64);
   {
     static thread_local size_t configured = 48 * 1024;
     if (sweep_smem > configured) {

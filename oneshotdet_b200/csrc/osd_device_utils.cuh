@@ -41,4 +41,20 @@ __device__ __forceinline__ int block_sum(int v, int* warp_tot) {
   return total;
 }
 
+
+// exact n / d for 32-bit n, d (Lemire): q = (M * n) >> 64
+struct FastDiv {
+  uint64_t M;
+  uint32_t d;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  f.M = d > 1 ? (0xFFFFFFFFFFFFFFFFull / d + 1ull) : 0ull;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  return f.d > 1 ? (uint32_t)__umul64hi(f.M, (uint64_t)n) : n;
+}
+
 }  // namespace osd

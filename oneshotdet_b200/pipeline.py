@@ -55,12 +55,36 @@ class EpisodePipeline:
                                      p.pre_nms_top_n, p.nms_thresh, p.fpn_post_nms_top_n, p.min_size, strict_iou,
                                      early_exit, private_workspace=True)
         self._host_out = None
+        self._streams = None
 
     # ---- device-resident step -------------------------------------------------------------------
     def run(self) -> ops.FcosResult:
-        """One pass of the hot path over the resident batch: 1 matching launch + the post-processing launches."""
+        """One pass of the hot path over the resident batch: 1 matching launch + the post-processing launches,
+        back to back on the current stream."""
         self.match()
         return self.post()
+
+    def run_overlapped(self) -> ops.FcosResult:
+        """The same work software-pipelined over two streams: the HBM-bound matching stream and the latency-bound
+        post-processing chain run concurrently (the post-processing stream has the higher priority so its small
+        CTAs slot in as matching CTAs retire).  In a deployment the overlapping pair is matching of batch i+1 and
+        post-processing of batch i (post-processing consumes the FCOS head's output of its own batch); here both
+        stages read resident inputs, so the pairing inside one call is equivalent.  The current stream waits for
+        both before the call returns control to later work."""
+        if self._streams is None:
+            lo, hi = torch.cuda.Stream.priority_range()
+            self._streams = (torch.cuda.Stream(self.device, priority=lo), torch.cuda.Stream(self.device, priority=hi))
+        s_match, s_post = self._streams
+        cur = torch.cuda.current_stream(self.device)
+        s_match.wait_stream(cur)
+        s_post.wait_stream(cur)
+        with torch.cuda.stream(s_match):
+            self.match()
+        with torch.cuda.stream(s_post):
+            res = self.post()
+        cur.wait_stream(s_match)
+        cur.wait_stream(s_post)
+        return res
 
     def input_tensors(self):
         return self.features + self.supp + self.cls + self.reg + self.ctr
