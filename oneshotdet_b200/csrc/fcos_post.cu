@@ -6,15 +6,21 @@
 #include <climits>
 
 #include "osd_common.cuh"
+#include <cooperative_groups.h>
+
 #include "osd_device_utils.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace osd {
 
 namespace {
 
-constexpr int kSelThreads = 1024;
-constexpr int kRadixBins = 2048;  // 11 + 11 + 10 bit digits
-constexpr int kSmemKeyCap = 48 * 1024;  // locations whose keys fit in shared memory (192 KB)
+constexpr int kCl = 8;              // CTAs per cluster = per (episode, level)
+constexpr int kSelThreads = 256;
+constexpr int kRadixBins = 2048;    // 11 + 11 + 10 bit digits
+constexpr int kMaxRounds = 3;       // 63 * 256 locations per round and CTA
+constexpr int kMaxSlice = kMaxRounds * 63 * kSelThreads;   // 48 384 locations per CTA (193 KB of keys)
 
 struct SelectArgs {
   int nl, B;
@@ -23,7 +29,7 @@ struct SelectArgs {
   const float* reg[OSD_MAX_LEVELS];
   const float* ctr[OSD_MAX_LEVELS];
   int slot[OSD_MAX_LEVELS];
-  int gkey_off[OSD_MAX_LEVELS];
+  FastDiv div_w[OSD_MAX_LEVELS];   // location index -> (row, col)
   const int32_t* image_hw;  // [B,2] (h, w)
   float pre_thr;
   int top_n;
@@ -33,8 +39,6 @@ struct SelectArgs {
   float* cand_scores;     // [B, cap]
   int32_t* cand_loc;      // [B, cap]
   int32_t* level_count;   // [B, nl]
-  uint32_t* gkeys;        // [B, gkey_stride] spill for levels with more than kSmemKeyCap locations
-  int gkey_stride;
 };
 
 __device__ __forceinline__ float sigmoidf_precise(float x) {
@@ -48,9 +52,9 @@ struct Decoded {
 };
 
 // inference.py:104-109 decode, bounding_box.py:214-224 clip, boxlist_ops.py:202-216 size filter
-__device__ __forceinline__ Decoded decode_clip(float dl, float dt, float dr, float db, int i, int Wl, int stride,
-                                               float xmax, float ymax, float min_size) {
-  const int row = i / Wl, col = i - row * Wl;
+__device__ __forceinline__ Decoded decode_clip(float dl, float dt, float dr, float db, int i, const FastDiv& div_w, int Wl,
+                                               int stride, float xmax, float ymax, float min_size) {
+  const int row = (int)fdiv((uint32_t)i, div_w), col = i - row * Wl;
   const float px = (float)(col * stride + stride / 2);  // fcos.py:220-234
   const float py = (float)(row * stride + stride / 2);
   Decoded d;
@@ -64,47 +68,62 @@ __device__ __forceinline__ Decoded decode_clip(float dl, float dt, float dr, flo
   return d;
 }
 
-__global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(SelectArgs A) {
+// One thread-block CLUSTER of kCl CTAs per (episode, level): CTA r scores and keeps the keys of its slice of the
+// level in its own shared memory; the radix-select histograms are combined through distributed shared memory
+// (every CTA sums the kCl histograms and runs the same bin search), and the ordered compaction uses the slice
+// totals exchanged the same way.  The P3 level (16 800 locations) is thus worked on by 8 SMs instead of one.
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads) fcos_select_kernel(SelectArgs A) {
+  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ uint32_t sm_dyn[];
   __shared__ int warp_tot[33];
+  __shared__ int xch[4];   // read by the other CTAs of the cluster: [0] candidates, [1] equal keys, [2] survivors
   __shared__ int s_bin, s_kk, s_eq;
-  int* hist = reinterpret_cast<int*>(sm_dyn);  // [kRadixBins]
-  uint32_t* smem_keys = sm_dyn + kRadixBins;
+  int* hist = reinterpret_cast<int*>(sm_dyn);               // [kRadixBins] this CTA's histogram
+  int* red = reinterpret_cast<int*>(sm_dyn) + kRadixBins;   // [kRadixBins] cluster-wide histogram
+  uint32_t* keys = sm_dyn + 2 * kRadixBins;                 // [slice]
 
-  const int l = blockIdx.x, e = blockIdx.y, tid = threadIdx.x;
+  const int r = (int)cluster.block_rank();
+  const int l = blockIdx.y, e = blockIdx.z, tid = threadIdx.x;
   const int Wl = A.W[l], HW = A.H[l] * Wl, stride = A.stride[l];
+  const int slice = (HW + kCl - 1) / kCl;
+  const int lo = min(HW, r * slice), hi = min(HW, lo + slice);
+  const int nloc = hi - lo;
   const float* __restrict__ cls = A.cls[l] + (size_t)e * HW;
   const float* __restrict__ ctr = A.ctr[l] + (size_t)e * HW;
   const float* __restrict__ reg = A.reg[l] + (size_t)e * 4 * HW;
-  uint32_t* keys = (HW <= kSmemKeyCap) ? smem_keys : (A.gkeys + (size_t)e * A.gkey_stride + A.gkey_off[l]);
 
   // ---- 1. scores -> order-preserving keys (0 = not a candidate); 4 independent loads in flight per array
   int my_cnt = 0;
-  for (int i0 = tid; i0 < HW; i0 += 4 * kSelThreads) {
+  for (int i0 = tid; i0 < nloc; i0 += 4 * kSelThreads) {
     float xc[4], xt[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * kSelThreads;
-      xc[u] = (i < HW) ? cls[i] : 0.f;
-      xt[u] = (i < HW) ? ctr[i] : 0.f;
+      xc[u] = (i < nloc) ? cls[lo + i] : 0.f;
+      xt[u] = (i < nloc) ? ctr[lo + i] : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * kSelThreads;
-      if (i < HW) {
+      if (i < nloc) {
         const float p = sigmoidf_precise(xc[u]);
         const float c = sigmoidf_precise(xt[u]);
-        const float s = __fmul_rn(p, c);                    // inference.py:79
+        const float sc = __fmul_rn(p, c);                   // inference.py:79
         const bool cand = p > A.pre_thr;                    // inference.py:74 (tested before the multiply)
-        keys[i] = cand ? (__float_as_uint(s) + 1u) : 0u;    // s >= 0, so its bit pattern is monotone
+        keys[i] = cand ? (__float_as_uint(sc) + 1u) : 0u;   // sc >= 0, so its bit pattern is monotone
         my_cnt += cand ? 1 : 0;
       }
     }
   }
-  const int cnt = block_sum(my_cnt, warp_tot);          // (contains the barrier that publishes keys)
+  const int cnt_r = block_sum(my_cnt, warp_tot);        // (contains the barrier that publishes keys)
+  if (tid == 0) xch[0] = cnt_r;
+  cluster.sync();
+  int cnt = 0;
+#pragma unroll
+  for (int rr = 0; rr < kCl; ++rr) cnt += cluster.map_shared_rank(xch, rr)[0];
   const int k = min(cnt, A.top_n);                      // inference.py:75-76
 
-  // ---- 2. k-th largest key by 3-digit radix select (only when the level overflows top_n)
+  // ---- 2. k-th largest key of the whole level by 3-digit radix select (only when the level overflows top_n)
   const bool take_all = (cnt <= k);
   uint32_t T = 1u;   // threshold key
   int need_eq = 0;   // how many keys equal to T are taken (lowest locations first)
@@ -120,117 +139,159 @@ __global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(SelectArgs A) 
       const uint32_t dm = (1u << widths[pass]) - 1u;
       for (int b = tid; b < kRadixBins; b += kSelThreads) hist[b] = 0;
       __syncthreads();
-      for (int i = tid; i < HW; i += kSelThreads) {
+      for (int i = tid; i < nloc; i += kSelThreads) {
         const uint32_t key = keys[i];
         if (key != 0u && (key & pmask) == prefix) atomicAdd(&hist[(key >> sh) & dm], 1);
       }
+      cluster.sync();  // every CTA's histogram is complete
+      for (int b = tid; b < kRadixBins; b += kSelThreads) {
+        int v = 0;
+#pragma unroll
+        for (int rr = 0; rr < kCl; ++rr) v += cluster.map_shared_rank(hist, rr)[b];
+        red[b] = v;
+      }
       __syncthreads();
-      // suffix sums: thread tid owns bins (2r, 2r+1) with r = 1023 - tid
-      const int r = kSelThreads - 1 - tid;
-      const int v0 = hist[2 * r], v1 = hist[2 * r + 1];
+      // suffix sums: thread tid owns bins [8q, 8q+8) with q = 255 - tid
+      const int q = kSelThreads - 1 - tid;
+      int v[8], sum = 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        v[u] = red[8 * q + u];
+        sum += v[u];
+      }
       int total;
-      const int above1 = block_exclusive_scan(v0 + v1, warp_tot, total);  // keys in bins > 2r+1
-      const int above0 = above1 + v1;                                     // keys in bins > 2r
-      if (above1 < kk && kk <= above1 + v1) {
-        s_bin = 2 * r + 1;
-        s_kk = kk - above1;
-        s_eq = v1;
-      } else if (above0 < kk && kk <= above0 + v0) {
-        s_bin = 2 * r;
-        s_kk = kk - above0;
-        s_eq = v0;
+      int above = block_exclusive_scan(sum, warp_tot, total);  // keys in bins > 8q+7
+#pragma unroll
+      for (int u = 7; u >= 0; --u) {
+        if (above < kk && kk <= above + v[u]) {
+          s_bin = 8 * q + u;
+          s_kk = kk - above;
+          s_eq = v[u];
+        }
+        above += v[u];
       }
       __syncthreads();
       prefix |= ((uint32_t)s_bin) << sh;
       pmask |= dm << sh;
       kk = s_kk;
       eq_total = s_eq;   // after the last pass: number of keys equal to the threshold key
-      __syncthreads();
+      cluster.sync();    // nobody still reads this CTA's histogram (it is zeroed next) or s_bin
     }
     T = prefix;
     need_eq = kk;
   }
 
   // ---- 3. decode + clip + size filter + ordered compaction.  Each thread owns a contiguous run of `per`
-  //         locations (per is odd: conflict-free shared-memory reads), so location order is thread order and one
-  //         block scan positions everything.
+  //         locations of the slice (per is odd: conflict-free shared-memory reads), so location order is
+  //         (CTA rank, thread) order.
   const int img_h = A.image_hw[2 * e], img_w = A.image_hw[2 * e + 1];
   const float xmax = (float)(img_w - 1), ymax = (float)(img_h - 1);
   const size_t obase = (size_t)e * A.cap + A.slot[l];
-  // per <= 63 so a run's flags fit one 64-bit mask; levels beyond 63 * 1024 locations take several rounds
-  const int per = min(((HW + kSelThreads - 1) / kSelThreads) | 1, 63);
-  const int round = per * kSelThreads;
   const bool ties = !take_all && need_eq < eq_total;  // ties at the top-k boundary: the lowest locations win
-  int level_total = 0, eq_seen = 0;
-  for (int seg0 = 0; seg0 < HW; seg0 += round) {
-    const int first = seg0 + tid * per;
-    const int run_end = min(min(HW, seg0 + round), first + per);  // this thread owns [first, run_end)
-    int eq_rank = 0;
-    if (ties) {
-      int my_eq = 0;
-      for (int i = first; i < run_end; ++i) my_eq += (keys[i] == T) ? 1 : 0;
+  int eq_before = 0;
+  if (ties) {
+    // equal keys in the slices of lower-ranked CTAs come first
+    int my_eq = 0;
+    for (int i = tid; i < nloc; i += kSelThreads) my_eq += (keys[i] == T) ? 1 : 0;
+    const int eq_r = block_sum(my_eq, warp_tot);
+    if (tid == 0) xch[1] = eq_r;
+    cluster.sync();
+    for (int rr = 0; rr < r; ++rr) eq_before += cluster.map_shared_rank(xch, rr)[1];
+  }
+  // per <= 63 so a run's flags fit one 64-bit mask; a slice of up to kMaxRounds * 63 * 256 locations takes
+  // kMaxRounds rounds (one for the BASELINE geometry)
+  const int per = min(((nloc + kSelThreads - 1) / kSelThreads) | 1, 63);
+  const int round = per * kSelThreads;
+  unsigned long long okm[kMaxRounds];
+  int pos0[kMaxRounds];
+  int running = 0, eq_seen = eq_before;
+  // A: which locations are selected and survive the size filter; positions inside this CTA's slice
+#pragma unroll
+  for (int rd = 0; rd < kMaxRounds; ++rd) {
+    okm[rd] = 0ull;
+    pos0[rd] = 0;
+    const int seg0 = rd * round;
+    if (seg0 < nloc) {  // uniform over the CTA
+      const int first = seg0 + tid * per;
+      const int run_end = min(min(nloc, seg0 + round), first + per);  // this thread owns [first, run_end) of the slice
+      int eq_rank = 0;
+      if (ties) {
+        int my_eq = 0;
+        for (int i = first; i < run_end; ++i) my_eq += (keys[i] == T) ? 1 : 0;
+        int tot;
+        eq_rank = eq_seen + block_exclusive_scan(my_eq, warp_tot, tot);
+        eq_seen += tot;
+      }
+      unsigned long long m = 0ull;
+      for (int qq = 0; first + qq < run_end; ++qq) {
+        const uint32_t key = keys[first + qq];
+        bool sel;
+        if (take_all) sel = key != 0u;
+        else if (key > T) sel = true;
+        else if (key == T) sel = !ties || (eq_rank++ < need_eq);
+        else sel = false;
+        if (sel) m |= 1ull << qq;
+      }
+      // survivors of the size filter (4 locations' loads in flight at a time)
+      unsigned long long ok = 0ull;
+      while (m) {
+        int qs[4];
+        float v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          qs[u] = m ? (__ffsll((long long)m) - 1) : -1;
+          if (m) m &= m - 1ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (qs[u] >= 0) {
+            const int i = lo + first + qs[u];
+            v[u][0] = reg[i];
+            v[u][1] = reg[HW + i];
+            v[u][2] = reg[2 * HW + i];
+            v[u][3] = reg[3 * HW + i];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (qs[u] >= 0) {
+            const Decoded d = decode_clip(v[u][0], v[u][1], v[u][2], v[u][3], lo + first + qs[u], A.div_w[l], Wl, stride,
+                                          xmax, ymax, A.min_size);
+            if (d.ok) ok |= 1ull << qs[u];
+          }
+        }
+      }
       int tot;
-      eq_rank = eq_seen + block_exclusive_scan(my_eq, warp_tot, tot);
-      eq_seen += tot;
+      pos0[rd] = running + block_exclusive_scan(__popcll(ok), warp_tot, tot);
+      running += tot;
+      okm[rd] = ok;
     }
-    unsigned long long selmask = 0ull;
-    for (int q = 0; first + q < run_end; ++q) {
-      const int i = first + q;
-      const uint32_t key = keys[i];
-      bool sel;
-      if (take_all) sel = key != 0u;
-      else if (key > T) sel = true;
-      else if (key == T) sel = !ties || (eq_rank++ < need_eq);
-      else sel = false;
-      if (sel) selmask |= 1ull << q;
-    }
-    // count pass: which selected locations survive the size filter (4 locations' loads in flight at a time)
-    unsigned long long okmask = 0ull, m = selmask;
+  }
+  // survivors in the slices of lower-ranked CTAs come first
+  if (tid == 0) xch[2] = running;
+  cluster.sync();
+  int base = 0;
+  for (int rr = 0; rr < r; ++rr) base += cluster.map_shared_rank(xch, rr)[2];
+  if (r == kCl - 1 && tid == 0) A.level_count[e * A.nl + l] = base + running;
+  // B: write (the loads now hit L1)
+#pragma unroll
+  for (int rd = 0; rd < kMaxRounds; ++rd) {
+    unsigned long long m = okm[rd];
+    const int first = rd * round + tid * per;
+    int pos = base + pos0[rd];
     while (m) {
-      int qs[4];
-      float v[4][4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        qs[u] = m ? (__ffsll((long long)m) - 1) : -1;
-        if (m) m &= m - 1ull;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (qs[u] >= 0) {
-          const int i = first + qs[u];
-          v[u][0] = reg[i];
-          v[u][1] = reg[HW + i];
-          v[u][2] = reg[2 * HW + i];
-          v[u][3] = reg[3 * HW + i];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (qs[u] >= 0) {
-          const Decoded d = decode_clip(v[u][0], v[u][1], v[u][2], v[u][3], first + qs[u], Wl, stride, xmax, ymax,
-                                        A.min_size);
-          if (d.ok) okmask |= 1ull << qs[u];
-        }
-      }
-    }
-    int tot;
-    int pos = level_total + block_exclusive_scan(__popcll(okmask), warp_tot, tot);
-    level_total += tot;
-    // write pass (the same loads now hit L1)
-    m = okmask;
-    while (m) {
-      const int q = __ffsll((long long)m) - 1;
+      const int qq = __ffsll((long long)m) - 1;
       m &= m - 1ull;
-      const int i = first + q;
-      const Decoded d = decode_clip(reg[i], reg[HW + i], reg[2 * HW + i], reg[3 * HW + i], i, Wl, stride, xmax, ymax,
-                                    A.min_size);
+      const int i = lo + first + qq;
+      const Decoded d = decode_clip(reg[i], reg[HW + i], reg[2 * HW + i], reg[3 * HW + i], i, A.div_w[l], Wl, stride, xmax,
+                                    ymax, A.min_size);
       A.cand_boxes[obase + pos] = d.box;
-      A.cand_scores[obase + pos] = __uint_as_float(keys[i] - 1u);
+      A.cand_scores[obase + pos] = __uint_as_float(keys[first + qq] - 1u);
       A.cand_loc[obase + pos] = i;
       ++pos;
     }
   }
-  if (tid == 0) A.level_count[e * A.nl + l] = level_total;
+  cluster.sync();  // no CTA exits while its shared memory may still be read by a neighbour
 }
 
 struct FcosBuffers {
@@ -239,9 +300,6 @@ struct FcosBuffers {
   int32_t* cand_loc;
   int32_t* level_count;
   int32_t* kept_total;
-  uint32_t* gkeys;
-  int gkey_stride;
-  int gkey_off[OSD_MAX_LEVELS];
   NmsWorkspace nms;
 };
 
@@ -255,7 +313,8 @@ int validate(const osd_fcos_config* cfg) {
   for (int l = 0; l < cfg->num_levels; ++l) {
     OSD_REQUIRE(cfg->height[l] >= 1 && cfg->width[l] >= 1 && cfg->stride[l] >= 1, "fcos: bad level %d geometry", l);
     const int64_t hw = (int64_t)cfg->height[l] * cfg->width[l];
-    OSD_REQUIRE(hw < (1 << 24), "fcos: level %d has too many locations", l);
+    OSD_REQUIRE(hw <= (int64_t)kCl * kMaxSlice, "fcos: level %d has %lld locations; at most %d are supported", l,
+                (long long)hw, kCl * kMaxSlice);
     OSD_REQUIRE(((int64_t)cfg->width[l] + 1) * cfg->stride[l] < (1 << 24) &&
                 ((int64_t)cfg->height[l] + 1) * cfg->stride[l] < (1 << 24), "fcos: level %d coordinates overflow fp32 integers", l);
     cap += hw < cfg->pre_nms_top_n ? hw : cfg->pre_nms_top_n;
@@ -266,17 +325,14 @@ int validate(const osd_fcos_config* cfg) {
 
 void carve(const osd_fcos_config* cfg, Carver& c, FcosBuffers* buf, osd_fcos_plan* plan) {
   const int B = cfg->batch > 0 ? cfg->batch : 1;
-  int cap = 0, gk = 0;
+  int cap = 0;
   int slot[OSD_MAX_LEVELS] = {0};
   FcosBuffers b{};
   for (int l = 0; l < cfg->num_levels; ++l) {
     const int hw = cfg->height[l] * cfg->width[l];
     slot[l] = cap;
     cap += hw < cfg->pre_nms_top_n ? hw : cfg->pre_nms_top_n;
-    b.gkey_off[l] = gk;
-    if (hw > kSmemKeyCap) gk += hw;
   }
-  b.gkey_stride = gk;
   const size_t o_boxes = c.offset_of_next();
   b.cand_boxes = c.take<float4>((size_t)B * cap);
   const size_t o_scores = c.offset_of_next();
@@ -287,7 +343,6 @@ void carve(const osd_fcos_config* cfg, Carver& c, FcosBuffers* buf, osd_fcos_pla
   b.level_count = c.take<int32_t>((size_t)B * cfg->num_levels);
   const size_t o_kt = c.offset_of_next();
   b.kept_total = c.take<int32_t>(B);
-  b.gkeys = gk ? c.take<uint32_t>((size_t)B * gk) : nullptr;
   nms_workspace_carve(c, B, cap, &b.nms);
   if (buf) *buf = b;
   if (plan) {
@@ -341,7 +396,7 @@ extern "C" int osd_fcos_postprocess(const osd_fcos_config* cfg, const float* con
   SelectArgs A{};
   A.nl = cfg->num_levels;
   A.B = cfg->batch;
-  int max_hw_smem = 0;
+  int max_slice = 0;
   for (int l = 0; l < cfg->num_levels; ++l) {
     OSD_REQUIRE(cls[l] && reg[l] && ctr[l], "osd_fcos_postprocess: null level %d input", l);
     A.H[l] = cfg->height[l];
@@ -351,9 +406,9 @@ extern "C" int osd_fcos_postprocess(const osd_fcos_config* cfg, const float* con
     A.reg[l] = reg[l];
     A.ctr[l] = ctr[l];
     A.slot[l] = plan.level_slot[l];
-    A.gkey_off[l] = buf.gkey_off[l];
-    const int hw = cfg->height[l] * cfg->width[l];
-    if (hw <= kSmemKeyCap && hw > max_hw_smem) max_hw_smem = hw;
+    A.div_w[l] = make_fastdiv((uint32_t)cfg->width[l]);
+    const int slice = (cfg->height[l] * cfg->width[l] + kCl - 1) / kCl;
+    if (slice > max_slice) max_slice = slice;
   }
   A.image_hw = image_hw;
   A.pre_thr = cfg->pre_nms_thresh;
@@ -364,19 +419,18 @@ extern "C" int osd_fcos_postprocess(const osd_fcos_config* cfg, const float* con
   A.cand_scores = buf.cand_scores;
   A.cand_loc = buf.cand_loc;
   A.level_count = buf.level_count;
-  A.gkeys = buf.gkeys;
-  A.gkey_stride = buf.gkey_stride;
 
-  const size_t smem = (size_t)kRadixBins * sizeof(int) + (size_t)max_hw_smem * sizeof(uint32_t);
+  const size_t smem = (size_t)2 * kRadixBins * sizeof(int) + (size_t)max_slice * sizeof(uint32_t);
   {
     static thread_local size_t configured = 48 * 1024;
     if (smem > configured) {
-      OSD_CUDA(cudaFuncSetAttribute(fcos_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(kRadixBins * sizeof(int) + kSmemKeyCap * sizeof(uint32_t))));
-      configured = kRadixBins * sizeof(int) + kSmemKeyCap * sizeof(uint32_t);
+      const size_t cap_bytes = (size_t)2 * kRadixBins * sizeof(int) + (size_t)kMaxSlice * sizeof(uint32_t);
+      OSD_CUDA(cudaFuncSetAttribute(fcos_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap_bytes));
+      configured = cap_bytes;
     }
   }
-  dim3 grid((unsigned)cfg->num_levels, (unsigned)cfg->batch);
+  // cluster of kCl CTAs along x per (level, episode); __cluster_dims__ on the kernel makes <<<>>> launch clusters
+  dim3 grid((unsigned)kCl, (unsigned)cfg->num_levels, (unsigned)cfg->batch);
   fcos_select_kernel<<<grid, kSelThreads, smem, stream>>>(A);
   OSD_LAUNCH_CHECK("fcos_select_kernel");
 

@@ -240,7 +240,7 @@ template <typename T, int MODE>
 int launch(const Args& A, int layout, cudaStream_t stream) {
   const FastDiv div_c = make_fastdiv((uint32_t)A.C);
   // persistent grid: a multiple of the SM count, capped by the work
-  int ctas = kNumSMs * 16;
+  int ctas = kNumSMs * 48;  // short-lived CTAs: slots free up quickly for a concurrently running post-processing stream
   if ((uint32_t)ctas > A.total_chunks) ctas = (int)A.total_chunks;
   if (ctas < 1) return OSD_OK;
   if (layout == OSD_LAYOUT_NCHW) {
