@@ -18,7 +18,7 @@ namespace {
 
 constexpr int kCl = 8;              // CTAs per cluster = per (episode, level)
 constexpr int kSelThreads = 256;
-constexpr int kRadixBins = 2048;    // 11 + 11 + 10 bit digits
+constexpr int kRadixBins = 256;     // radix-select digits: 8 + 8 + 8 + 7 bits (== kSelThreads: thread t owns bin t)
 constexpr int kMaxRounds = 3;       // 63 * 256 locations per round and CTA
 constexpr int kMaxSlice = kMaxRounds * 63 * kSelThreads;   // 48 384 locations per CTA (193 KB of keys)
 
@@ -129,53 +129,51 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads) fcos_
   int need_eq = 0;   // how many keys equal to T are taken (lowest locations first)
   int eq_total = 0;  // how many keys equal T
   if (!take_all) {
+    // keys are (bits of a float in [0, 1]) + 1 < 2^31: digits = exponent (8 bits) and the mantissa in 8/8/7 bits.
+    // Each pass: local 256-bin histogram (warp-aggregated shared-memory atomics), cluster barrier, then EVERY CTA
+    // sums the kCl histograms through distributed shared memory -- thread t owns bin t, 8 remote reads -- and runs the
+    // same suffix-scan bin search, so no result has to be broadcast.
     uint32_t prefix = 0u, pmask = 0u;
     int kk = k;
-    const int shifts[3] = {21, 10, 0};
-    const int widths[3] = {11, 11, 10};
+    const int shifts[4] = {23, 15, 7, 0};
+    const int widths[4] = {8, 8, 8, 7};
 #pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {
+    for (int pass = 0; pass < 4; ++pass) {
       const int sh = shifts[pass];
       const uint32_t dm = (1u << widths[pass]) - 1u;
-      for (int b = tid; b < kRadixBins; b += kSelThreads) hist[b] = 0;
+      hist[tid] = 0;   // kRadixBins == kSelThreads
       __syncthreads();
-      for (int i = tid; i < nloc; i += kSelThreads) {
-        const uint32_t key = keys[i];
-        if (key != 0u && (key & pmask) == prefix) atomicAdd(&hist[(key >> sh) & dm], 1);
+      for (int i0 = 0; i0 < nloc; i0 += kSelThreads) {
+        const int i = i0 + tid;
+        const uint32_t key = (i < nloc) ? keys[i] : 0u;
+        const bool on = key != 0u && (key & pmask) == prefix;
+        const uint32_t bin = on ? ((key >> sh) & dm) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        if (on && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
       }
       cluster.sync();  // every CTA's histogram is complete
-      for (int b = tid; b < kRadixBins; b += kSelThreads) {
-        int v = 0;
+      int v = 0;
 #pragma unroll
-        for (int rr = 0; rr < kCl; ++rr) v += cluster.map_shared_rank(hist, rr)[b];
-        red[b] = v;
-      }
+      for (int rr = 0; rr < kCl; ++rr) v += cluster.map_shared_rank(hist, rr)[tid];
+      // suffix sums: thread tid looks at bin q = 255 - tid, so the exclusive prefix over threads = keys in bins > q
+      // (the remote read above used bin tid; exchange through shared memory)
+      red[tid] = v;
       __syncthreads();
-      // suffix sums: thread tid owns bins [8q, 8q+8) with q = 255 - tid
       const int q = kSelThreads - 1 - tid;
-      int v[8], sum = 0;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        v[u] = red[8 * q + u];
-        sum += v[u];
-      }
+      const int vq = red[q];
       int total;
-      int above = block_exclusive_scan(sum, warp_tot, total);  // keys in bins > 8q+7
-#pragma unroll
-      for (int u = 7; u >= 0; --u) {
-        if (above < kk && kk <= above + v[u]) {
-          s_bin = 8 * q + u;
-          s_kk = kk - above;
-          s_eq = v[u];
-        }
-        above += v[u];
+      const int above = block_exclusive_scan(vq, warp_tot, total);
+      if (above < kk && kk <= above + vq) {
+        s_bin = q;
+        s_kk = kk - above;
+        s_eq = vq;
       }
       __syncthreads();
       prefix |= ((uint32_t)s_bin) << sh;
       pmask |= dm << sh;
       kk = s_kk;
       eq_total = s_eq;   // after the last pass: number of keys equal to the threshold key
-      cluster.sync();    // nobody still reads this CTA's histogram (it is zeroed next) or s_bin
+      cluster.sync();    // nobody still reads this CTA's histogram (it is zeroed next)
     }
     T = prefix;
     need_eq = kk;

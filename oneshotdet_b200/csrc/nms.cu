@@ -27,6 +27,8 @@ namespace {
 constexpr int kChunk = 2048;         // keys per sort chunk (one CTA each)
 constexpr int kChunkThreads = 512;
 constexpr int kMergeStage = 6 * kChunk;   // keys staged per window by the merge kernel (96 KB)
+constexpr int kMergeThreads = 1024;
+constexpr int kMergeKeys = kChunk / kMergeThreads;   // keys of the own chunk per thread
 constexpr int kMaskRows = 128;       // rows per mask tile (one thread per row)
 constexpr int kMaskCols = 128;       // columns per mask tile (2 words of 64)
 constexpr int kSweepThreads = 512;
@@ -180,9 +182,8 @@ __global__ void __launch_bounds__(kChunkThreads) nms_chunk_sort_kernel(CandLayou
         const bool up = (i & k) == 0;
         const bool lower = (i & j) == 0;
         const bool take_min = (lower == up);
-        const u64 mn = r[s] < other ? r[s] : other;
-        const u64 mx = r[s] < other ? other : r[s];
-        r[s] = take_min ? mn : mx;
+        // keys are unique: keep mine iff it is the one this position wants
+        r[s] = ((r[s] < other) == take_min) ? r[s] : other;
       }
     }
     // distances 2 and 1 stay inside the thread (static register indices)
@@ -217,7 +218,7 @@ __device__ __forceinline__ int count_less(const u64* __restrict__ run, int len2,
   return pos;
 }
 
-__global__ void __launch_bounds__(kChunkThreads) nms_merge_kernel(CandLayout L, NmsWorkspace W) {
+__global__ void __launch_bounds__(kMergeThreads) nms_merge_kernel(CandLayout L, NmsWorkspace W) {
   extern __shared__ u64 staged[];  // up to kMergeStage sorted keys of the other chunks
   __shared__ int lvl_prefix[OSD_MAX_LEVELS + 1];
   const int e = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
@@ -227,12 +228,12 @@ __global__ void __launch_bounds__(kChunkThreads) nms_merge_kernel(CandLayout L, 
   fill_level_prefix(L, e, lvl_prefix);
   const int len = min(kChunk, n - base);
   const u64* keys = W.sortkeys + (size_t)e * W.NP;
-  // own keys (4 per thread) and their running ranks
-  u64 mine[4];
-  int rank[4];
+  // own keys (kMergeKeys per thread) and their running ranks
+  u64 mine[kMergeKeys];
+  int rank[kMergeKeys];
 #pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int i = tid + s * kChunkThreads;
+  for (int s = 0; s < kMergeKeys; ++s) {
+    const int i = tid + s * kMergeThreads;
     mine[s] = (i < len) ? keys[base + i] : ~0ull;
     rank[s] = i;
   }
@@ -240,16 +241,16 @@ __global__ void __launch_bounds__(kChunkThreads) nms_merge_kernel(CandLayout L, 
   for (int w0 = 0; w0 < n; w0 += kMergeStage) {
     const int wn = min(kMergeStage, n - w0);
     __syncthreads();
-    for (int i = tid; i < wn; i += 4 * kChunkThreads) {  // 4 independent loads in flight
+    for (int i = tid; i < wn; i += 4 * kMergeThreads) {  // 4 independent loads in flight
       u64 t4[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int idx = i + u * kChunkThreads;
+        const int idx = i + u * kMergeThreads;
         t4[u] = idx < wn ? keys[w0 + idx] : 0ull;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int idx = i + u * kChunkThreads;
+        const int idx = i + u * kMergeThreads;
         if (idx < wn) staged[idx] = t4[u];
       }
     }
@@ -258,13 +259,13 @@ __global__ void __launch_bounds__(kChunkThreads) nms_merge_kernel(CandLayout L, 
       if (w0 + c2off == base) continue;  // own chunk
       const int len2 = min(kChunk, wn - c2off);
 #pragma unroll
-      for (int s = 0; s < 4; ++s) rank[s] += count_less(staged + c2off, len2, mine[s]);
+      for (int s = 0; s < kMergeKeys; ++s) rank[s] += count_less(staged + c2off, len2, mine[s]);
     }
   }
   bool regular = true;
 #pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int i = tid + s * kChunkThreads;
+  for (int s = 0; s < kMergeKeys; ++s) {
+    const int i = tid + s * kMergeThreads;
     if (i < len) write_sorted(L, W, e, rank[s], (int)(mine[s] & 0xffffffffu), lvl_prefix, regular);
   }
   if (!regular) atomicAnd(&W.flags[e], 0);
@@ -423,6 +424,85 @@ __global__ void __launch_bounds__(kMaskRows) nms_mask_kernel(NmsWorkspace W, Mas
 }
 
 // ------------------------------------------------------------------------------------------------
+// 4. emit (device function, called by the sweep CTA of an episode the moment the episode finishes): turns the
+//    kept bits (visiting order, in shared memory) into the caller's output layout.
+// ------------------------------------------------------------------------------------------------
+// exclusive prefix of popcounts over `nw` 64-bit words (smem in, smem out)
+__device__ void prefix_popc(const u64* words, int* prefix, int nw, int* warp_tot) {
+  int base = 0;
+  for (int w0 = 0; w0 < nw; w0 += blockDim.x) {
+    int w = w0 + threadIdx.x;
+    int v = (w < nw) ? __popcll(words[w]) : 0;
+    int total;
+    int ex = block_exclusive_scan(v, warp_tot, total);
+    if (w < nw) prefix[w] = base + ex;
+    base += total;
+  }
+  __syncthreads();
+}
+
+// vbits: kept bits in visiting order (smem, NW words, zero beyond the swept blocks); scratch: NW u64 + NW int
+__device__ void emit_episode(const CandLayout& L, const NmsWorkspace& W, const NmsOutputs& O, int post_top_n, int e,
+                             int total, const u64* vbits, u64* cbits, int* prefix, int* warp_tot) {
+  const int tid = threadIdx.x;
+  const int NW = W.NW;
+  const int n = W.n[e];
+  const size_t so = (size_t)e * W.NP;
+  for (int w = tid; w < NW; w += blockDim.x) cbits[w] = 0ull;
+  __syncthreads();
+  const bool cut = post_top_n > 0 && total > post_top_n;
+  const int64_t seg0 = L.seg ? L.seg[e] : 0;
+  if (cut) {
+    // best post_top_n by score = the first post_top_n kept boxes in visiting order
+    prefix_popc(vbits, prefix, NW, warp_tot);
+    for (int i = tid; i < n; i += blockDim.x) {
+      u64 wv = vbits[i >> 6];
+      if ((wv >> (i & 63)) & 1ull) {
+        int p = prefix[i >> 6] + __popcll(wv & ((1ull << (i & 63)) - 1ull));
+        if (p < post_top_n) {
+          if (O.keep_out) O.keep_out[seg0 + p] = seg0 + W.sidx[so + i];
+          if (O.out_boxes) {
+            size_t oo = (size_t)e * O.K + p;
+            reinterpret_cast<float4*>(O.out_boxes)[oo] = W.sbox[so + i];
+            O.out_scores[oo] = W.sscore[so + i];
+            O.out_index[oo] = W.sidx[so + i];
+          }
+        }
+      }
+    }
+  } else {
+    // every kept box, ascending candidate index (nms_cpu.cpp:64 nonzero(suppressed == 0))
+    for (int i = tid; i < n; i += blockDim.x) {
+      if ((vbits[i >> 6] >> (i & 63)) & 1ull) {
+        int c = W.sidx[so + i];
+        atomicOr(&cbits[c >> 6], 1ull << (c & 63));
+      }
+    }
+    __syncthreads();
+    prefix_popc(cbits, prefix, NW, warp_tot);
+    for (int i = tid; i < n; i += blockDim.x) {
+      if ((vbits[i >> 6] >> (i & 63)) & 1ull) {
+        int c = W.sidx[so + i];
+        int p = prefix[c >> 6] + __popcll(cbits[c >> 6] & ((1ull << (c & 63)) - 1ull));
+        if (O.keep_out) O.keep_out[seg0 + p] = seg0 + c;
+        if (O.out_boxes && p < O.K) {
+          size_t oo = (size_t)e * O.K + p;
+          reinterpret_cast<float4*>(O.out_boxes)[oo] = W.sbox[so + i];
+          O.out_scores[oo] = W.sscore[so + i];
+          O.out_index[oo] = c;
+        }
+      }
+    }
+  }
+  if (tid == 0) {
+    int cnt = cut ? post_top_n : total;
+    if (O.keep_counts) O.keep_counts[e] = cnt;
+    if (O.out_count) O.out_count[e] = O.out_boxes ? min(cnt, O.K) : cnt;
+    if (O.kept_total) O.kept_total[e] = total;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 3. sweep: one CTA per episode walks the 64-box blocks in visiting order.  The suppression word of block b is
 //    *pulled*: OR over all kept earlier boxes i of mask[b][i] -- a coalesced column read (the mask is word-major)
 //    and a tree reduction, no atomics.  The column of block b+1 is loaded before block b is resolved (it does not
@@ -434,6 +514,7 @@ struct SweepArgs {
   int blk_end;    // blocks [blk_begin, blk_end) are swept (clipped to the episode)
   int stop;       // finish the episode once this many boxes are kept
   int passthrough;
+  int post_top_n; // emit: keep the best post_top_n when more survive (<= 0: all)
 };
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
@@ -450,10 +531,11 @@ __device__ __forceinline__ u64 warp_or_u64(u64 v) {
   return ((u64)hi << 32) | lo;
 }
 
-__global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W, SweepArgs A) {
-  extern __shared__ u64 kw[];  // [NW] kept bits of the blocks swept so far
+__global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(CandLayout L, NmsWorkspace W, NmsOutputs O, SweepArgs A) {
+  extern __shared__ u64 kw[];  // [NW] kept bits of the blocks swept so far | scratch (ring / emit)
   __shared__ u64 partial[kSweepThreads / 32];
   __shared__ int s_nk;
+  __shared__ int warp_tot[33];
   const int e = blockIdx.x;
   if (W.done[e]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -461,6 +543,7 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W
   const int nblk = (n + 63) >> 6;
   u64* kb = W.keptbits + (size_t)e * W.NW;
   if (A.passthrough) {
+    // boxlist_nms with nms_thresh <= 0: nothing is suppressed
     for (int w = tid; w < W.NW; w += kSweepThreads) {
       u64 v = 0;
       if (w < nblk) {
@@ -468,7 +551,10 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W
         v = nv == 64 ? ~0ull : ((1ull << nv) - 1ull);
       }
       kb[w] = v;
+      kw[w] = v;
     }
+    __syncthreads();
+    emit_episode(L, W, O, A.post_top_n, e, n, kw, kw + W.NW, reinterpret_cast<int*>(kw + 2 * W.NW), warp_tot);
     if (tid == 0) {
       W.kcount[e] = n;
       W.done[e] = 1;
@@ -568,6 +654,8 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W
   const bool finished = (count >= A.stop) || (blk_next >= nblk);
   if (finished) {
     for (int w = blk_next + tid; w < W.NW; w += kSweepThreads) kb[w] = 0ull;
+    __syncthreads();  // kw[] complete; the ring is free to be reused as emit scratch
+    emit_episode(L, W, O, A.post_top_n, e, count, kw, kw + W.NW, reinterpret_cast<int*>(kw + 2 * W.NW), warp_tot);
   }
   if (tid == 0) {
     W.kcount[e] = count;
@@ -575,94 +663,6 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(NmsWorkspace W
       W.done[e] = 1;
       atomicAdd(&W.sched[0], 1);
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// 4. emit: one CTA per episode turns kept bits into the caller's output layout
-// ------------------------------------------------------------------------------------------------
-// exclusive prefix of popcounts over `nw` 64-bit words (smem in, smem out)
-__device__ void prefix_popc(const u64* words, int* prefix, int nw, int* warp_tot) {
-  int base = 0;
-  for (int w0 = 0; w0 < nw; w0 += blockDim.x) {
-    int w = w0 + threadIdx.x;
-    int v = (w < nw) ? __popcll(words[w]) : 0;
-    int total;
-    int ex = block_exclusive_scan(v, warp_tot, total);
-    if (w < nw) prefix[w] = base + ex;
-    base += total;
-  }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(1024) nms_emit_kernel(CandLayout L, NmsWorkspace W, NmsOutputs O,
-                                                        int post_top_n) {
-  extern __shared__ u64 sm_words[];  // [NW] kept bits (visiting order) | [NW] kept bits (candidate order)
-  __shared__ int warp_tot[33];
-  const int e = blockIdx.x;
-  const int tid = threadIdx.x;
-  const int NW = W.NW;
-  u64* vbits = sm_words;
-  u64* cbits = sm_words + NW;
-  int* prefix = reinterpret_cast<int*>(sm_words + 2 * NW);  // [NW]
-  const int n = W.n[e];
-  const int total = W.kcount[e];
-  const u64* kb = W.keptbits + (size_t)e * NW;
-  const size_t so = (size_t)e * W.NP;
-  for (int w = tid; w < NW; w += blockDim.x) {
-    vbits[w] = kb[w];
-    cbits[w] = 0ull;
-  }
-  __syncthreads();
-  const bool cut = post_top_n > 0 && total > post_top_n;
-  const int64_t seg0 = L.seg ? L.seg[e] : 0;
-  if (cut) {
-    // best post_top_n by score = the first post_top_n kept boxes in visiting order
-    prefix_popc(vbits, prefix, NW, warp_tot);
-    for (int i = tid; i < n; i += blockDim.x) {
-      u64 wv = vbits[i >> 6];
-      if ((wv >> (i & 63)) & 1ull) {
-        int p = prefix[i >> 6] + __popcll(wv & ((1ull << (i & 63)) - 1ull));
-        if (p < post_top_n) {
-          if (O.keep_out) O.keep_out[seg0 + p] = seg0 + W.sidx[so + i];
-          if (O.out_boxes) {
-            size_t oo = (size_t)e * O.K + p;
-            reinterpret_cast<float4*>(O.out_boxes)[oo] = W.sbox[so + i];
-            O.out_scores[oo] = W.sscore[so + i];
-            O.out_index[oo] = W.sidx[so + i];
-          }
-        }
-      }
-    }
-  } else {
-    // every kept box, ascending candidate index (nms_cpu.cpp:64 nonzero(suppressed == 0))
-    for (int i = tid; i < n; i += blockDim.x) {
-      if ((vbits[i >> 6] >> (i & 63)) & 1ull) {
-        int c = W.sidx[so + i];
-        atomicOr(&cbits[c >> 6], 1ull << (c & 63));
-      }
-    }
-    __syncthreads();
-    prefix_popc(cbits, prefix, NW, warp_tot);
-    for (int i = tid; i < n; i += blockDim.x) {
-      if ((vbits[i >> 6] >> (i & 63)) & 1ull) {
-        int c = W.sidx[so + i];
-        int p = prefix[c >> 6] + __popcll(cbits[c >> 6] & ((1ull << (c & 63)) - 1ull));
-        if (O.keep_out) O.keep_out[seg0 + p] = seg0 + c;
-        if (O.out_boxes && p < O.K) {
-          size_t oo = (size_t)e * O.K + p;
-          reinterpret_cast<float4*>(O.out_boxes)[oo] = W.sbox[so + i];
-          O.out_scores[oo] = W.sscore[so + i];
-          O.out_index[oo] = c;
-        }
-      }
-    }
-  }
-  if (tid == 0) {
-    int cnt = cut ? post_top_n : total;
-    if (O.keep_counts) O.keep_counts[e] = cnt;
-    if (O.out_count) O.out_count[e] = O.out_boxes ? min(cnt, O.K) : cnt;
-    if (O.kept_total) O.kept_total[e] = total;
   }
 }
 
@@ -715,14 +715,15 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
                                     (int)(kMergeStage * sizeof(u64))));
       merge_configured = true;
     }
-    nms_merge_kernel<<<g, kChunkThreads, merge_smem, stream>>>(L, W);
+    nms_merge_kernel<<<g, kMergeThreads, merge_smem, stream>>>(L, W);
     OSD_LAUNCH_CHECK("nms_merge_kernel");
   }
 
   // ---- mask + sweep, in passes over growing prefixes of the visiting order.  Without early exit there is one
   //      pass; with it, the first pass covers just enough boxes to keep post_top_n + 1 if little is suppressed,
   //      the second a 30 % larger prefix, the last everything.  Finished episodes skip later passes on the device.
-  const size_t sweep_smem = ((size_t)W.NW + (size_t)(kSweepDepth + 1) * kSweepThreads * kSweepPre) * sizeof(u64);
+  const size_t sweep_smem = std::max(((size_t)W.NW + (size_t)(kSweepDepth + 1) * kSweepThreads * kSweepPre) * sizeof(u64),
+                                     (size_t)W.NW * (2 * sizeof(u64) + sizeof(int)) + 64);
   {
     static thread_local size_t configured = 48 * 1024;
     if (sweep_smem > configured) {
@@ -734,11 +735,12 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
   }
   SweepArgs S{};
   S.passthrough = P.passthrough;
+  S.post_top_n = P.post_top_n;
   if (P.passthrough) {
     S.blk_begin = 0;
     S.blk_end = INT_MAX;
     S.stop = INT_MAX;
-    nms_sweep_kernel<<<E, kSweepThreads, sweep_smem, stream>>>(W, S);
+    nms_sweep_kernel<<<E, kSweepThreads, sweep_smem, stream>>>(L, W, O, S);
     OSD_LAUNCH_CHECK("nms_sweep_kernel");
   } else {
     MaskArgs M{};
@@ -753,10 +755,9 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
     int bounds[3];
     int npass = 0;
     if (early) {
+      // enough boxes to keep post_top_n + 1 when at most ~5 % of the best-scored boxes are suppressed
       const int b1 = (int)align_up((size_t)P.post_top_n + 1, 64) + 64;
-      const int b2 = (int)align_up((size_t)((int64_t)P.post_top_n + (3 * (int64_t)P.post_top_n) / 10 + 128), 64);
       if (b1 < NPu) bounds[npass++] = b1;
-      if (b2 < NPu && b2 > b1) bounds[npass++] = b2;
     }
     bounds[npass++] = NPu;
     int prev = 0;
@@ -777,25 +778,12 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
       OSD_LAUNCH_CHECK("nms_mask_kernel");
       S.blk_begin = prev / 64;
       S.blk_end = hi / 64;
-      nms_sweep_kernel<<<E, kSweepThreads, sweep_smem, stream>>>(W, S);
+      nms_sweep_kernel<<<E, kSweepThreads, sweep_smem, stream>>>(L, W, O, S);
       OSD_LAUNCH_CHECK("nms_sweep_kernel");
       prev = hi;
     }
   }
 
-  // ---- emit
-  const size_t emit_smem = (size_t)W.NW * (2 * sizeof(u64) + sizeof(int));
-  {
-    static thread_local size_t configured = 48 * 1024;
-    if (emit_smem > configured) {
-      OSD_REQUIRE(emit_smem <= 200 * 1024, "nms: %d candidates per episode exceed the emit capacity", max_len);
-      OSD_CUDA(cudaFuncSetAttribute(nms_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)emit_smem));
-      configured = emit_smem;
-    }
-  }
-  nms_emit_kernel<<<E, 1024, emit_smem, stream>>>(L, W, O, P.post_top_n);
-  OSD_LAUNCH_CHECK("nms_emit_kernel");
   return OSD_OK;
 }
 
