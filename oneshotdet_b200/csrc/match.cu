@@ -8,6 +8,8 @@
 // multiply a single rounded fp32 product: fp32 results are bit-identical to the reference expression.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "osd_common.cuh"
 #include "osd_device_utils.cuh"
 
@@ -240,7 +242,16 @@ template <typename T, int MODE>
 int launch(const Args& A, int layout, cudaStream_t stream) {
   const FastDiv div_c = make_fastdiv((uint32_t)A.C);
   // persistent grid: a multiple of the SM count, capped by the work
-  int ctas = kNumSMs * 48;  // short-lived CTAs: slots free up quickly for a concurrently running post-processing stream
+  // CTAs per SM of the persistent grid.  The stream is HBM-bound, a few hundred threads per SM with 4 x 128-bit loads
+  // in flight each saturate it; keeping the footprint small leaves registers and thread slots for the
+  // post-processing kernels that run concurrently on the second stream (OSD_MATCH_CTAS_PER_SM overrides for tuning).
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    const char* env = getenv("OSD_MATCH_CTAS_PER_SM");
+    per_sm = env ? atoi(env) : 4;
+    if (per_sm < 1) per_sm = 1;
+  }
+  int ctas = kNumSMs * per_sm;
   if ((uint32_t)ctas > A.total_chunks) ctas = (int)A.total_chunks;
   if (ctas < 1) return OSD_OK;
   if (layout == OSD_LAYOUT_NCHW) {

@@ -34,6 +34,8 @@ constexpr int kMaskCols = 128;       // columns per mask tile (2 words of 64)
 constexpr int kSweepThreads = 512;
 constexpr int kSweepPre = 8;         // rows per thread whose column words the sweep prefetches (small passes)
 constexpr int kSweepDepth = 4;       // columns in flight in the sweep's cp.async ring
+constexpr int kEdgeCap = 16384;      // suppression edges per episode handled by the sparse sweep (128 KB)
+constexpr int kEdgeRounds = 48;      // relaxation rounds before the sparse sweep gives up
 
 typedef unsigned long long u64;
 
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(kChunkThreads) nms_chunk_sort_kernel(CandLayou
     W.flags[e] = 1;
     W.done[e] = 0;
     W.kcount[e] = 0;
+    W.ecount[e] = 0;
     if (e == 0) {
       W.sched[0] = 0;  // episodes finished
       W.sched[1] = W.sched[2] = W.sched[3] = 0;  // mask tile counters of the passes
@@ -419,6 +422,21 @@ __global__ void __launch_bounds__(kMaskRows) nms_mask_kernel(NmsWorkspace W, Mas
         bits = above;
       }
       mcol[(size_t)(ct0 >> 6) * W.NP] = bits;
+      if (bits) {
+        // sparse view of the same information for the edge sweep: (suppressed box, suppressing box)
+        const int cntb = __popcll(bits);
+        const int base = atomicAdd(&W.ecount[e], cntb);
+        if (base + cntb <= W.ecap) {
+          u64* ed = W.edges + (size_t)e * W.ecap + base;
+          u64 m = bits;
+          int k = 0;
+          while (m) {
+            const int b = __ffsll((long long)m) - 1;
+            m &= m - 1ull;
+            ed[k++] = ((u64)(uint32_t)(ct0 + b) << 32) | (uint32_t)i;
+          }
+        }
+      }
     }
   }
 }
@@ -579,19 +597,77 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(CandLayout L, 
     u64* dst = ring + slot * kRingCol;
     for (int row = tid; row < 64 * col; row += kSweepThreads) cp_async8(dst + row, src + row);
   };
-  if (small && nb > 0) {
+  for (int w = tid; w < W.NW; w += kSweepThreads) kw[w] = (w < A.blk_begin) ? kb[w] : 0ull;
+  int count = W.kcount[e];
+  __syncthreads();
+  int it = 0;
+  // ---- sparse sweep.  When few pairs overlap enough to suppress (the usual case at nms_thresh 0.6-0.8) the mask
+  //      kernel's edge list (i, j) = "j suppresses i if j is kept" is tiny.  kept[] is the unique fixpoint of
+  //      kept[i] = !exists (i, j): kept[j]; starting from all-kept, parallel relaxation over the edges reaches it in
+  //      (longest suppression chain + 1) rounds -- no per-block serial walk at all.  Dense cases (edge list over
+  //      capacity or long chains) fall through to the block sweep below, which is exact for any input.
+  const int ne = W.ecount[e];
+  bool sparse_done = false;
+  if (nb > 0 && ne <= W.ecap) {
+    u64* sup = ring;             // [NW]
+    u64* eds = ring + W.NW;      // [ne] staged edges (ne <= kEdgeCap fits the ring)
+    const u64* ge = W.edges + (size_t)e * W.ecap;
+    for (int k = tid; k < ne; k += kSweepThreads) eds[k] = ge[k];
+    for (int w = A.blk_begin + tid; w < blim; w += kSweepThreads) {
+      const int nv = min(64, n - 64 * w);
+      kw[w] = nv == 64 ? ~0ull : ((1ull << nv) - 1ull);
+    }
+    __syncthreads();
+    const uint32_t lo_box = 64u * (uint32_t)A.blk_begin, hi_box = 64u * (uint32_t)blim;
+    int rounds = 0;
+    int changed = 1;
+    while (changed && rounds < kEdgeRounds) {
+      for (int w = A.blk_begin + tid; w < blim; w += kSweepThreads) sup[w] = 0ull;
+      __syncthreads();
+      for (int k = tid; k < ne; k += kSweepThreads) {
+        const u64 ed = eds[k];
+        const uint32_t bi = (uint32_t)(ed >> 32), bj = (uint32_t)ed;
+        if (bi >= lo_box && bi < hi_box && ((kw[bj >> 6] >> (bj & 63)) & 1ull)) atomicOr(&sup[bi >> 6], 1ull << (bi & 63));
+      }
+      __syncthreads();
+      int ch = 0;
+      for (int w = A.blk_begin + tid; w < blim; w += kSweepThreads) {
+        const int nv = min(64, n - 64 * w);
+        const u64 vm = nv == 64 ? ~0ull : ((1ull << nv) - 1ull);
+        const u64 nk = vm & ~sup[w];
+        if (nk != kw[w]) {
+          ch = 1;
+          kw[w] = nk;
+        }
+      }
+      changed = __syncthreads_or(ch);
+      ++rounds;
+    }
+    if (!changed) {
+      int c = 0;
+      for (int w = A.blk_begin + tid; w < blim; w += kSweepThreads) {
+        c += __popcll(kw[w]);
+        kb[w] = kw[w];
+      }
+      count += block_sum(c, warp_tot);
+      it = nb;
+      sparse_done = true;
+    } else {
+      // did not converge within the round budget: redo this pass with the block sweep
+      for (int w = A.blk_begin + tid; w < blim; w += kSweepThreads) kw[w] = 0ull;
+      __syncthreads();
+    }
+  }
+  if (!sparse_done && small && nb > 0) {
 #pragma unroll
     for (int d = 0; d < kSweepDepth - 1; ++d) {
       if (d < nb) prefetch_col(A.blk_begin + d, d);
       cp_async_commit();
     }
     for (int i = tid; i < 64 * nb; i += kSweepThreads) dcs[i] = dc[64 * A.blk_begin + i];
+    __syncthreads();
   }
-  for (int w = tid; w < W.NW; w += kSweepThreads) kw[w] = (w < A.blk_begin) ? kb[w] : 0ull;
-  int count = W.kcount[e];
-  __syncthreads();
-  int it = 0;
-  for (; it < nb; ++it) {
+  for (; it < nb && !sparse_done; ++it) {
     const int blk = A.blk_begin + it;
     u64 c_lo = 0ull, c_hi = 0ull;
     u64 acc = 0ull;
@@ -690,6 +766,9 @@ size_t nms_workspace_carve(Carver& c, int64_t E, int64_t max_len, NmsWorkspace* 
   w.diagcol = c.take<unsigned long long>(E * NP);
   w.keptbits = c.take<unsigned long long>(E * NW);
   w.sortkeys = c.take<unsigned long long>(E * NP);
+  w.edges = c.take<unsigned long long>(E * kEdgeCap);
+  w.ecount = c.take<int32_t>(E);
+  w.ecap = kEdgeCap;
   w.mask = c.take<unsigned long long>(E * NP * NW);
   if (ws) *ws = w;
   return c.total();

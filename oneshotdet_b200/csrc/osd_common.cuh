@@ -94,7 +94,10 @@ struct NmsWorkspace {
   unsigned long long* mask;     // [E, NW, NP] word-major: bit j of mask[e][w][i]: box 64w+j suppressed by box i (64w+j > i)
   unsigned long long* diagcol;  // [E, NP] for box i: which earlier boxes of its own 64-block suppress it
   unsigned long long* keptbits; // [E, NW]
-  unsigned long long* sortkeys; // [E, NP] scratch for the large-N rank sort
+  unsigned long long* sortkeys; // [E, NP] sorted 64-bit keys of the chunks
+  unsigned long long* edges;    // [E, kEdgeCap] suppression edges (i << 32 | j): box j (earlier) overlaps box i enough to suppress it
+  int32_t* ecount;              // [E] edges found so far (may exceed the capacity: then the bitmask sweep is used)
+  int32_t ecap;
 };
 
 size_t nms_workspace_carve(Carver& c, int64_t E, int64_t max_len, NmsWorkspace* ws);
