@@ -242,9 +242,18 @@ def run_b200_arm(args):
     ep_off = rank * BATCH
 
     overlap = not args.serial
+    launch = "eager"
+    step_fn = pipe.run_overlapped if overlap else pipe.run
+    if not args.no_graph:
+        try:
+            step_fn = pipe.capture(overlapped=overlap)
+            launch = "cuda-graph"
+        except Exception as exc:  # noqa: BLE001  (launch mechanism only; the kernels are the same either way)
+            print(f"[bench] CUDA-graph capture failed ({exc}); launching eagerly", file=sys.stderr)
+            torch.cuda.synchronize()
 
     def step():
-        res = pipe.run_overlapped() if overlap else pipe.run()
+        res = step_fn()
         if world > 1:
             d, c = pipe.pack_detections(res, ep_off)
             gather_detections(d, c)
@@ -253,6 +262,12 @@ def run_b200_arm(args):
     for _ in range(warmup):
         res = step()
     torch.cuda.synchronize()
+    # kernels of this library per step, counted on one eager step (a CUDA-graph replay re-launches the same kernels
+    # without passing through the library's launch counter)
+    ops.reset_launch_count()
+    pipe.run()
+    torch.cuda.synchronize()
+    launches_per_step = ops.launch_count()
     # isolated stage times (serial, one stream): the roofline of the matching kernel and the post-processing chain
     iso = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     iso_match, iso_post = [], []
@@ -286,7 +301,7 @@ def run_b200_arm(args):
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
-    launches = ops.launch_count()
+    launches = launches_per_step * steps
     total_ms = ev[0][0].elapsed_time(ev[-1][1])
     match_ms, post_ms = iso_match, iso_post
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -311,6 +326,7 @@ def run_b200_arm(args):
     stages = {"match_ms_isolated": match_avg_ms, "post_ms_isolated": statistics.mean(post_ms),
               "serial_ms_per_step": match_avg_ms + statistics.mean(post_ms),
               "overlap": "match || post-processing on two streams (software pipelining)" if overlap else "none (one stream)",
+              "launch": launch,
               "post_algorithmic_read_bytes": post_read,
               "host_ms_per_step": 1e3 * (t_host1 - t_host0) / steps}
 
@@ -407,6 +423,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fusion", action="store_true")
     ap.add_argument("--serial", action="store_true", help="one stream: matching then post-processing, no overlap")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
