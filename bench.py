@@ -219,7 +219,7 @@ def run_b200_arm(args):
     import torch.distributed as dist
 
     from oneshotdet_b200 import ops
-    from oneshotdet_b200.distributed import gather_detections
+    from oneshotdet_b200.distributed import DetectionGatherer
     from oneshotdet_b200.pipeline import EpisodePipeline, PostParams
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -252,15 +252,18 @@ def run_b200_arm(args):
             print(f"[bench] CUDA-graph capture failed ({exc}); launching eagerly", file=sys.stderr)
             torch.cuda.synchronize()
 
+    gatherer = DetectionGatherer(BATCH, pipe.post.plan.out_capacity, dev, ep_off) if world > 1 else None
+
     def step():
         res = step_fn()
-        if world > 1:
-            d, c = pipe.pack_detections(res, ep_off)
-            gather_detections(d, c)
+        if gatherer is not None:   # snapshot + asynchronous NCCL all-gather, overlapped with the next step
+            gatherer.submit(res.boxes, res.scores, res.count)
         return res
 
     for _ in range(warmup):
         res = step()
+    if gatherer is not None:
+        gatherer.finish()
     torch.cuda.synchronize()
     # kernels of this library per step, counted on one eager step (a CUDA-graph replay re-launches the same kernels
     # without passing through the library's launch counter)
@@ -296,6 +299,9 @@ def run_b200_arm(args):
         ev[i][0].record()
         step()
         ev[i][1].record()
+    if gatherer is not None:
+        gatherer.finish()     # the last gathers are inside the timed region
+        ev[-1][1].record()
     torch.cuda.synchronize()
     t_host1 = time.perf_counter()
     if world > 1:

@@ -41,3 +41,49 @@ def unpack_detections(dets: torch.Tensor, counts: torch.Tensor, num_episodes: in
         out[gid] = (dets[e, :n, :4].clone(), dets[e, :n, 4].clone())
     ids = sorted(out) if num_episodes is None else range(num_episodes)
     return [out[i] for i in ids if i in out]
+
+
+class DetectionGatherer:
+    """Double-buffered, asynchronous gather of the per-step detections: the step's results are snapshotted into a
+    packed payload [E_local, K + 1, 6] (rows 0..K-1: x1, y1, x2, y2, score, global episode id; row K: the count in
+    column 0) and ONE all_gather_into_tensor is issued with async_op=True, so NCCL moves batch i over NVLink while
+    the kernels of batch i+1 already run.  ``submit`` waits for the gather issued two steps earlier before reusing its
+    buffers; ``finish`` drains everything."""
+
+    def __init__(self, e_local: int, k: int, device, episode_offset: int = 0, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.e, self.k = e_local, k
+        self.payload, self.out, self.work = [], [], [None, None]
+        for _ in range(2):
+            p = torch.zeros((e_local, k + 1, 6), dtype=torch.float32, device=device)
+            p[:, :k, 5] = torch.arange(episode_offset, episode_offset + e_local, device=device, dtype=torch.float32).view(-1, 1)
+            self.payload.append(p)
+            self.out.append(torch.empty((self.world * e_local, k + 1, 6), dtype=torch.float32, device=device))
+        self.i = 0
+
+    def submit(self, boxes, scores, count):
+        slot = self.i & 1
+        self.i += 1
+        if self.work[slot] is not None:
+            self.work[slot].wait()
+        p = self.payload[slot]
+        p[:, :self.k, :4].copy_(boxes)
+        p[:, :self.k, 4].copy_(scores)
+        p[:, self.k, 0].copy_(count)
+        if self.world > 1:
+            self.work[slot] = dist.all_gather_into_tensor(self.out[slot], p, group=self.group, async_op=True)
+        else:
+            self.out[slot].copy_(p)
+        return slot
+
+    def finish(self):
+        for w in self.work:
+            if w is not None:
+                w.wait()
+        self.work = [None, None]
+
+    def result(self, slot):
+        """(dets [E_total, K, 6], counts int32 [E_total]) of a finished slot."""
+        o = self.out[slot]
+        return o[:, :self.k], o[:, self.k, 0].to(torch.int32)

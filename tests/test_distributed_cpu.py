@@ -78,3 +78,51 @@ def test_single_process_is_identity():
     c = torch.zeros(3, dtype=torch.int32)
     gd, gc = gather_detections(d, c)
     assert gd is d and gc is c
+
+
+def _gatherer_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oneshotdet_b200.distributed import DetectionGatherer
+
+        e, k = 3, 4
+        g = DetectionGatherer(e, k, torch.device("cpu"), episode_offset=rank * e)
+        ok = True
+        slots = []
+        for step in range(5):   # more steps than buffers: exercises the reuse wait
+            gen = torch.Generator().manual_seed(100 * step + rank)
+            boxes = torch.rand(e, k, 4, generator=gen)
+            scores = torch.rand(e, k, generator=gen)
+            count = torch.randint(0, k + 1, (e,), generator=gen, dtype=torch.int32)
+            slots.append((g.submit(boxes, scores, count), step))
+        g.finish()
+        slot, step = slots[-1]
+        dets, counts = g.result(slot)
+        for r in range(world):
+            gen = torch.Generator().manual_seed(100 * step + r)
+            boxes = torch.rand(e, k, 4, generator=gen)
+            scores = torch.rand(e, k, generator=gen)
+            count = torch.randint(0, k + 1, (e,), generator=gen, dtype=torch.int32)
+            blk = dets[r * e:(r + 1) * e]
+            ok = ok and torch.equal(blk[..., :4], boxes) and torch.equal(blk[..., 4], scores)
+            ok = ok and torch.equal(counts[r * e:(r + 1) * e], count)
+            ok = ok and blk[:, 0, 5].tolist() == [float(r * e + i) for i in range(e)]
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_async_detection_gatherer_world_size_2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gatherer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(0, True), (1, True)]
