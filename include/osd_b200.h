@@ -204,6 +204,35 @@ typedef struct {
 int osd_fusion_workspace_bytes(const osd_fusion_desc* desc, size_t* bytes);
 int osd_fusion_forward(const osd_fusion_desc* desc, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Support-embedding producer (the step right before the matching path).
+ *
+ * Replaces  SuppAlignLayer (maskrcnn_benchmark/modeling/detector/generalized_rcnn.py:20-52, call :305): ROIAlign with a
+ *           (1,1) output, one whole-image ROI per support, per FPN level (kernel csrc/cuda/ROIAlign_cuda.cu:65-122,
+ *           CPU twin csrc/cpu/ROIAlign_cpu.cpp:113-214) -- mode OSD_POOL_ROIALIGN; and nn.AdaptiveAvgPool2d((1,1))
+ *           (generalized_rcnn.py:94, :303) -- mode OSD_POOL_AVG.
+ * feat[l] is [N, C, H_l, W_l] fp32 NCHW (N = B*S supports), out[l] is [N, C]; rois is [N, 4] (x1, y1, x2, y2) in
+ * support-image coordinates, scaled by spatial_scale[l] per level.  OSD_POOL_ROIALIGN is bit-identical to the
+ * reference CPU operator.
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum { OSD_POOL_ROIALIGN = 0, OSD_POOL_AVG = 1 } osd_pool_mode;
+
+typedef struct {
+  int32_t num_levels;
+  int32_t num_supports;   /* N = B*S */
+  int32_t channels;
+  int32_t mode;           /* osd_pool_mode */
+  int32_t sampling_ratio; /* ROIAlign sampling ratio (<= 0: adaptive, ceil(roi extent)) */
+  int32_t height[OSD_MAX_LEVELS];
+  int32_t width[OSD_MAX_LEVELS];
+  float spatial_scale[OSD_MAX_LEVELS];
+  const void* feat[OSD_MAX_LEVELS];
+  void* out[OSD_MAX_LEVELS];
+  const float* rois;      /* device fp32 [N, 4]; unused for OSD_POOL_AVG */
+} osd_support_pool_desc;
+
+int osd_support_pool(const osd_support_pool_desc* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,15 @@ class FusionDesc(ctypes.Structure):
                 ("b2", ctypes.c_void_p), ("gn2_w", ctypes.c_void_p), ("gn2_b", ctypes.c_void_p)]
 
 
+class SupportPoolDesc(ctypes.Structure):
+    _fields_ = [("num_levels", ctypes.c_int32), ("num_supports", ctypes.c_int32), ("channels", ctypes.c_int32),
+                ("mode", ctypes.c_int32), ("sampling_ratio", ctypes.c_int32),
+                ("height", ctypes.c_int32 * OSD_MAX_LEVELS), ("width", ctypes.c_int32 * OSD_MAX_LEVELS),
+                ("spatial_scale", ctypes.c_float * OSD_MAX_LEVELS),
+                ("feat", ctypes.c_void_p * OSD_MAX_LEVELS), ("out", ctypes.c_void_p * OSD_MAX_LEVELS),
+                ("rois", ctypes.c_void_p)]
+
+
 # every symbol include/osd_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "osd_version": (ctypes.c_int, []),
@@ -71,6 +80,7 @@ SYMBOLS = {
     "osd_match_forward": (ctypes.c_int, [ctypes.POINTER(MatchDesc), c_void_p]),
     "osd_fusion_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(FusionDesc), ctypes.POINTER(ctypes.c_size_t)]),
     "osd_fusion_forward": (ctypes.c_int, [ctypes.POINTER(FusionDesc), c_void_p, ctypes.c_size_t, c_void_p]),
+    "osd_support_pool": (ctypes.c_int, [ctypes.POINTER(SupportPoolDesc), c_void_p]),
 }
 
 _lib = None
