@@ -22,6 +22,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstring>
+
 #include "osd_common.cuh"
 #include "osd_device_utils.cuh"
 
@@ -79,6 +81,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -160,6 +170,7 @@ struct ConvArgs {
   int num_kc;           // Cin / 64
   int stages;           // weight stages in shared memory
   int total_tiles;
+  int tma_out_mask;     // bit l: level l's output has a tensor map (epilogue stores through TMA)
   int xform;            // 0: identity; 1: GroupNorm(32, Cin) + LeakyReLU on the input (stats_in)
   float eps, slope;
   const float* bias;    // [nl, B, Cout] (bias_level_stride / bias_img_stride may be 0)
@@ -171,6 +182,12 @@ struct ConvArgs {
 
 struct TileInfo {
   int level, img, px0, nvalid;
+};
+
+// output tensor maps, one per level ([B*Cout rows, HW columns] fp32, box 32 x 32, 128-byte swizzle); only used for
+// levels with HW % 4 == 0 (TMA needs a 16-byte row pitch)
+struct OutMaps {
+  CUtensorMap m[OSD_MAX_LEVELS];
 };
 
 __device__ __forceinline__ TileInfo decode_tile(const ConvArgs& A, int tile) {
@@ -197,7 +214,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // the GEMM kernel
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1)
-conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) {
+conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ OutMaps out_maps, const ConvArgs A) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [B buffers: 2 x (Cin x 128 B)] [A stages: stages x (num_mt x 16 KB)] [barriers]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -291,19 +308,20 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
-      mbar_wait(b_empty + 8u * buf, ph ^ 1u);
       const TileInfo t = decode_tile(A, tile);
       const ConvLevel& L = A.lv[t.level];
       const float* src = L.in + (size_t)t.img * A.Cin * L.hw + t.px0 + j * 8;
       const bool vec_ok = ((L.hw & 3) == 0) && (t.px0 + j * 8 + 8 <= L.hw);
       const int nleft = L.hw - (t.px0 + j * 8);  // valid pixels from this chunk's start (may be <= 0)
       const float2* coef = A.xform ? A.coef_in + ((size_t)t.level * A.B + t.img) * A.Cin : nullptr;
-      for (int k0 = pw * 4 + rsub; k0 < A.Cin; k0 += 32 * 4) {
-        // 4 rows (8 x 128-bit loads) in flight per thread, 32 KB per SM
-        float v[4][8];
+      // 256 input channels at a time: every thread first issues ALL its loads of the block (8 rows x 2 x 128 bit
+      // = 64 KB in flight per SM, enough to cover HBM latency at the SM's share of the bandwidth) and only then
+      // waits for the activation buffer to be free -- the loads of tile i+1 fly while tile i is multiplied.
+      for (int kh = 0; kh < A.Cin; kh += 256) {
+        float v[8][8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int k = k0 + u * 32;
+        for (int u = 0; u < 8; ++u) {
+          const int k = kh + pw * 4 + rsub + u * 32;
           const float* p = src + (size_t)k * L.hw;
           if (k < A.Cin) {
             if (vec_ok) {
@@ -317,9 +335,10 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) 
             }
           }
         }
+        if (kh == 0) mbar_wait(b_empty + 8u * buf, ph ^ 1u);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int k = k0 + u * 32;
+        for (int u = 0; u < 8; ++u) {
+          const int k = kh + pw * 4 + rsub + u * 32;
           if (k < A.Cin) {
             if (A.xform) {
               // GroupNorm + LeakyReLU of the producer conv's output: y = x * scale + shift
@@ -389,26 +408,35 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) 
           const uint32_t a = stage + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4);
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(y[0]), "f"(y[1]), "f"(y[2]), "f"(y[3]) : "memory");
         }
-        __syncwarp();
-        // read back transposed: 8 lanes cover the 128 bytes of one row, 4 rows per instruction
+        if ((A.tma_out_mask >> t.level) & 1) {
+          // the stage is exactly a SWIZZLE_128B box of 32 rows x 32 fp32: hand it to the TMA unit, which clips pixels
+          // past the end of the level; global stores leave the LSU / L1 path entirely
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && oc0 < A.Cout) {
+            tma_store_2d(&out_maps.m[t.level], stage, t.px0 + pxh, t.img * A.Cout + oc0);
+            tma_store_commit();
+            tma_store_wait_read();   // the stage may be rewritten once the bulk copy has read it
+          }
+          __syncwarp();
+        } else {
+          __syncwarp();
+          // levels whose rows are not 16-byte aligned (H*W % 4 != 0): read back transposed and store with the LSU
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = 4 * i + (lane >> 3), c = lane & 7;
-          const int orow = oc0 + row;
-          const float4 v = *reinterpret_cast<const float4*>(stage_gen + row * 32 + ((c ^ (row & 7)) << 2));
-          if (orow < A.Cout) {
-            float* dst = L.out + ((size_t)t.img * A.Cout + orow) * L.hw + t.px0 + pxh + 4 * c;
-            if (vec_ok) {
-              if (4 * c < nval) *reinterpret_cast<float4*>(dst) = v;   // hw % 4 == 0: a chunk is all-valid or all-padding
-            } else {
+          for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + (lane >> 3), c = lane & 7;
+            const int orow = oc0 + row;
+            const float4 v = *reinterpret_cast<const float4*>(stage_gen + row * 32 + ((c ^ (row & 7)) << 2));
+            if (orow < A.Cout) {
+              float* dst = L.out + ((size_t)t.img * A.Cout + orow) * L.hw + t.px0 + pxh + 4 * c;
               const float vs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e)
                 if (4 * c + e < nval) dst[e] = vs[e];
             }
           }
+          __syncwarp();  // the stage is rewritten by the next accumulator tile
         }
-        __syncwarp();  // the stage is rewritten by the next accumulator tile
         if (A.stats_out) {
           // GroupNorm statistics of this conv's output: reduce over the gs_out consecutive channels (lanes) of a group
           for (int o = 1; o < gs_out; o <<= 1) {
@@ -426,6 +454,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvArgs A) 
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty + 8u * buf);
     }
+    if (lane == 0) tma_store_wait_all();   // every bulk store of this warp has been written
   }
 
   tc_fence_before();
@@ -632,6 +661,24 @@ int plan_conv(int Cin, int Cout, ConvPlan* p) {
   return OSD_OK;
 }
 
+// fp32 output [rows, cols] row-major -> 2-D tensor map, box = 32 (pixels) x 32 (rows), 128-byte swizzle
+int make_output_map(float* base, int64_t rows, int64_t cols, CUtensorMap* map) {
+  EncodeTiledFn fn;
+  int rc = get_encode_fn(&fn);
+  if (rc != OSD_OK) return rc;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output) failed with CUresult %d", (int)r);
+    return OSD_ERR_CUDA;
+  }
+  return OSD_OK;
+}
+
 int launch_conv(const CUtensorMap& map, ConvArgs& A, cudaStream_t stream) {
   ConvPlan p;
   int rc = plan_conv(A.Cin, A.Cout, &p);
@@ -646,7 +693,17 @@ int launch_conv(const CUtensorMap& map, ConvArgs& A, cudaStream_t stream) {
   }
   if (A.total_tiles <= 0) return OSD_OK;
   const int grid = A.total_tiles < kNumSMs ? A.total_tiles : kNumSMs;
-  conv1x1_tc_kernel<<<grid, kThreads, p.smem, stream>>>(map, A);
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
+  A.tma_out_mask = 0;
+  for (int l = 0; l < A.nl; ++l) {
+    if ((A.lv[l].hw & 3) == 0 && (reinterpret_cast<uintptr_t>(A.lv[l].out) & 15) == 0) {
+      rc = make_output_map(A.lv[l].out, (int64_t)A.B * A.Cout, A.lv[l].hw, &om.m[l]);
+      if (rc != OSD_OK) return rc;
+      A.tma_out_mask |= 1 << l;
+    }
+  }
+  conv1x1_tc_kernel<<<grid, kThreads, p.smem, stream>>>(map, om, A);
   OSD_LAUNCH_CHECK("conv1x1_tc_kernel");
   return OSD_OK;
 }
