@@ -76,5 +76,39 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+EXT = os.path.join(PKG, "_C_torch.so")
+
+
+def build_torch_extension(force: bool = False, verbose: bool = False) -> str:
+    """Thin pybind11/torch extension `oneshotdet_b200._C_torch` over the C ABI (csrc/torch_ext.cpp): g++ directly, linked
+    against libosd_b200.so (rpath $ORIGIN/lib) and torch's libraries."""
+    import sysconfig
+
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    src = os.path.join(CSRC, "torch_ext.cpp")
+    lib = build(force=False, verbose=verbose)
+    if not force and not _stale(EXT, [src, lib, os.path.join(ROOT, "include", "osd_b200.h")]):
+        return EXT
+    inc = []
+    for p in ce.include_paths() + [sysconfig.get_paths()["include"], "/usr/local/cuda/include"]:
+        inc += ["-isystem", p]
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-DTORCH_EXTENSION_NAME=_C_torch",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI),
+           "-I", os.path.join(ROOT, "include")] + inc + [src, "-o", EXT,
+           "-L", os.path.join(PKG, "lib"), "-losd_b200", "-Wl,-rpath,$ORIGIN/lib",
+           "-L", tlib, "-Wl,-rpath," + tlib, "-lc10", "-lc10_cuda", "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-ltorch_python"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return EXT
+
+
 if __name__ == "__main__":
     print(build(force="-f" in sys.argv, verbose="-v" in sys.argv))
+    if "--ext" in sys.argv:
+        print(build_torch_extension(force="-f" in sys.argv, verbose="-v" in sys.argv))

@@ -83,3 +83,18 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
+
+
+def test_torch_extension_loads_and_refuses_cpu_tensors():
+    """The thin torch C++ extension over the C ABI (csrc/torch_ext.cpp) builds on the CPU box, imports without a GPU
+    and has no CPU path."""
+    import torch
+
+    from oneshotdet_b200 import build as osd_build
+
+    osd_build.build_torch_extension()
+    from oneshotdet_b200 import _C_torch
+
+    assert _C_torch.version() == _lib.load().osd_version()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        _C_torch.nms(torch.zeros(4, 4), torch.zeros(4), 0.5)

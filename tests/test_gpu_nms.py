@@ -173,3 +173,25 @@ def test_properties_at_full_size():
         area = (kb[:, 2] - kb[:, 0] + 1) * (kb[:, 3] - kb[:, 1] + 1)
         iou = inter / (area + (b[2] - b[0] + 1) * (b[3] - b[1] + 1) - inter)
         assert bool(((iou >= 0.8) & better).any())
+
+
+def test_torch_extension_binding_matches_oracle(golden_dir):
+    """`_C.nms` through the thin torch C++ extension (csrc/torch_ext.cpp): same kernels, same keeps."""
+    from oneshotdet_b200 import _C
+
+    ext = pytest.importorskip("oneshotdet_b200._C_torch")
+    assert _C.BINDING == "torch-extension" and _C.nms is ext.nms
+    with open(os.path.join(golden_dir, "nms_kat.json")) as f:
+        for c in json.load(f)["cases"]:
+            keep = _C.nms(torch.tensor(c["boxes"], dtype=torch.float32, device=DEV),
+                          torch.tensor(c["scores"], dtype=torch.float32, device=DEV), c["thresh"])
+            assert keep.dtype == torch.int64 and keep.is_cuda
+            np.testing.assert_array_equal(keep.cpu().numpy(), np.asarray(c["keep_sorted"]))
+    for n, thr, seed in [(1, 0.5, 0), (777, 0.6, 1), (6000, 0.8, 2)]:
+        boxes, scores = clustered_boxes(np.random.RandomState(seed), n, clusters=max(2, n // 60))
+        keep = _C.nms(torch.from_numpy(boxes).to(DEV), torch.from_numpy(scores).to(DEV), thr)
+        np.testing.assert_array_equal(keep.cpu().numpy(), orc.nms(boxes, scores, thr))
+    empty = _C.nms(torch.zeros((0, 4), device=DEV), torch.zeros((0,), device=DEV), 0.5)
+    assert empty.dtype == torch.int64 and empty.numel() == 0 and empty.device.type == "cpu"
+    with pytest.raises(RuntimeError):
+        _C.nms(torch.zeros((3, 4)), torch.zeros((3,)), 0.5)          # no CPU path
