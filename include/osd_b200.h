@@ -95,6 +95,12 @@ int osd_batched_nms(const float* boxes,          /* device [N,4] xyxy */
  * none) and, if more than post_nms_top_n > 0 boxes survive, the post_nms_top_n best by score in
  * descending order, else all survivors in ascending candidate order.
  * ---------------------------------------------------------------------------------------------- */
+/* What the regression input is.  OSD_REG_DISTANCES: ltrb distances as FCOSHead.forward returns them (already
+ * exp'd, fcos.py:95-97).  OSD_REG_RAW_EXP_SCALE: the raw output of the bbox_pred conv; the head's tail
+ * torch.exp(self.scales[l](x)) = exp(x * scale_l) (fcos.py:95-97, layers/scale.py:10-11) is then evaluated here, for
+ * the <= pre_nms_top_n selected locations of a level only -- the two elementwise passes over [B,4,H,W] disappear. */
+typedef enum { OSD_REG_DISTANCES = 0, OSD_REG_RAW_EXP_SCALE = 1 } osd_reg_transform;
+
 typedef struct {
   int32_t num_levels;
   int32_t batch;                   /* B episodes */
@@ -109,6 +115,8 @@ typedef struct {
   int32_t strict;                  /* 0: IoU >= thr suppresses (nms_cpu), 1: IoU > thr (nms.cu) */
   int32_t early_exit;              /* 1: stop an episode's NMS once post_nms_top_n + 1 boxes are kept
                                       (result identical; only meaningful when post_nms_top_n > 0) */
+  int32_t reg_transform;           /* osd_reg_transform: what reg[l] holds */
+  float reg_scale[OSD_MAX_LEVELS]; /* OSD_REG_RAW_EXP_SCALE: the per-level Scale parameter (layers/scale.py:5-11) */
 } osd_fcos_config;
 
 typedef struct {

@@ -24,7 +24,8 @@ class FcosConfig(ctypes.Structure):
                 ("stride", ctypes.c_int32 * OSD_MAX_LEVELS),
                 ("pre_nms_thresh", ctypes.c_float), ("pre_nms_top_n", ctypes.c_int32),
                 ("nms_thresh", ctypes.c_float), ("post_nms_top_n", ctypes.c_int32),
-                ("min_size", ctypes.c_float), ("strict", ctypes.c_int32), ("early_exit", ctypes.c_int32)]
+                ("min_size", ctypes.c_float), ("strict", ctypes.c_int32), ("early_exit", ctypes.c_int32),
+                ("reg_transform", ctypes.c_int32), ("reg_scale", ctypes.c_float * OSD_MAX_LEVELS)]
 
 
 class FcosPlan(ctypes.Structure):

@@ -39,11 +39,18 @@ struct SelectArgs {
   float* cand_scores;     // [B, cap]
   int32_t* cand_loc;      // [B, cap]
   int32_t* level_count;   // [B, nl]
+  int reg_exp;            // OSD_REG_RAW_EXP_SCALE: reg holds the raw bbox_pred output
+  float reg_scale[OSD_MAX_LEVELS];
 };
 
 __device__ __forceinline__ float sigmoidf_precise(float x) {
   // inference.py:58 / :72  torch.sigmoid in fp32: 1 / (1 + exp(-x))
   return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+}
+
+// fcos.py:95-97 with layers/scale.py:10-11: torch.exp(x * scale) -- the product is rounded to fp32 before the exp
+__device__ __forceinline__ float reg_distance(float v, bool raw, float scale) {
+  return raw ? expf(__fmul_rn(v, scale)) : v;
 }
 
 struct Decoded {
@@ -53,7 +60,12 @@ struct Decoded {
 
 // inference.py:104-109 decode, bounding_box.py:214-224 clip, boxlist_ops.py:202-216 size filter
 __device__ __forceinline__ Decoded decode_clip(float dl, float dt, float dr, float db, int i, const FastDiv& div_w, int Wl,
-                                               int stride, float xmax, float ymax, float min_size) {
+                                               int stride, float xmax, float ymax, float min_size, bool raw,
+                                               float scale) {
+  dl = reg_distance(dl, raw, scale);
+  dt = reg_distance(dt, raw, scale);
+  dr = reg_distance(dr, raw, scale);
+  db = reg_distance(db, raw, scale);
   const int row = (int)fdiv((uint32_t)i, div_w), col = i - row * Wl;
   const float px = (float)(col * stride + stride / 2);  // fcos.py:220-234
   const float py = (float)(row * stride + stride / 2);
@@ -85,6 +97,8 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads) fcos_
   const int r = (int)cluster.block_rank();
   const int l = blockIdx.y, e = blockIdx.z, tid = threadIdx.x;
   const int Wl = A.W[l], HW = A.H[l] * Wl, stride = A.stride[l];
+  const bool raw = A.reg_exp != 0;
+  const float rscale = A.reg_scale[l];
   const int slice = (HW + kCl - 1) / kCl;
   const int lo = min(HW, r * slice), hi = min(HW, lo + slice);
   const int nloc = hi - lo;
@@ -254,7 +268,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads) fcos_
         for (int u = 0; u < 4; ++u) {
           if (qs[u] >= 0) {
             const Decoded d = decode_clip(v[u][0], v[u][1], v[u][2], v[u][3], lo + first + qs[u], A.div_w[l], Wl, stride,
-                                          xmax, ymax, A.min_size);
+                                          xmax, ymax, A.min_size, raw, rscale);
             if (d.ok) ok |= 1ull << qs[u];
           }
         }
@@ -282,7 +296,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads) fcos_
       m &= m - 1ull;
       const int i = lo + first + qq;
       const Decoded d = decode_clip(reg[i], reg[HW + i], reg[2 * HW + i], reg[3 * HW + i], i, A.div_w[l], Wl, stride, xmax,
-                                    ymax, A.min_size);
+                                    ymax, A.min_size, raw, rscale);
       A.cand_boxes[obase + pos] = d.box;
       A.cand_scores[obase + pos] = __uint_as_float(keys[first + qq] - 1u);
       A.cand_loc[obase + pos] = i;
@@ -307,6 +321,8 @@ int validate(const osd_fcos_config* cfg) {
               cfg->num_levels);
   OSD_REQUIRE(cfg->batch >= 0 && cfg->batch <= 65535, "fcos: batch %d out of range", cfg->batch);
   OSD_REQUIRE(cfg->pre_nms_top_n >= 1, "fcos: pre_nms_top_n must be >= 1");
+  OSD_REQUIRE(cfg->reg_transform == OSD_REG_DISTANCES || cfg->reg_transform == OSD_REG_RAW_EXP_SCALE,
+              "fcos: unknown reg_transform %d", cfg->reg_transform);
   int64_t cap = 0;
   for (int l = 0; l < cfg->num_levels; ++l) {
     OSD_REQUIRE(cfg->height[l] >= 1 && cfg->width[l] >= 1 && cfg->stride[l] >= 1, "fcos: bad level %d geometry", l);
@@ -412,6 +428,8 @@ extern "C" int osd_fcos_postprocess(const osd_fcos_config* cfg, const float* con
   A.pre_thr = cfg->pre_nms_thresh;
   A.top_n = cfg->pre_nms_top_n;
   A.min_size = cfg->min_size;
+  A.reg_exp = cfg->reg_transform == OSD_REG_RAW_EXP_SCALE;
+  for (int l = 0; l < cfg->num_levels; ++l) A.reg_scale[l] = cfg->reg_scale[l];
   A.cap = plan.cand_capacity;
   A.cand_boxes = buf.cand_boxes;
   A.cand_scores = buf.cand_scores;

@@ -69,14 +69,18 @@ class FCOSPostProcessor(torch.nn.Module):
         return [c if c.size(1) == 1 else c[:, 0:1].contiguous() for c in box_cls]
 
     # -- the accelerated path ----------------------------------------------------------------------
-    def forward_fixed(self, box_cls, box_regression, centerness, image_sizes) -> ops.FcosResult:
-        """Padded device-resident result (boxes [B,K,4], scores [B,K], index [B,K], count [B]); no host sync."""
+    def forward_fixed(self, box_cls, box_regression, centerness, image_sizes, reg_scales=None) -> ops.FcosResult:
+        """Padded device-resident result (boxes [B,K,4], scores [B,K], index [B,K], count [B]); no host sync.
+
+        ``reg_scales`` (one float per level, the head's ``scales[l].scale``): ``box_regression`` then holds the RAW
+        ``bbox_pred`` conv outputs and the head's tail ``torch.exp(self.scales[l](x))`` (fcos.py:95-97) is folded
+        into the decode of the selected locations."""
         if len(box_cls) > len(self.fpn_strides):
             raise ValueError("more feature levels than fpn_strides")
         return ops.fcos_postprocess(self._pos_logits(box_cls), box_regression, centerness,
                                     self.fpn_strides[:len(box_cls)], image_sizes, self.pre_nms_thresh,
                                     self.pre_nms_top_n, self.nms_thresh, self.fpn_post_nms_top_n, self.min_size,
-                                    strict=self.strict_iou, early_exit=self.early_exit)
+                                    strict=self.strict_iou, early_exit=self.early_exit, reg_scales=reg_scales)
 
     def forward(self, locations, box_cls, box_regression, centerness, image_sizes, targets=None):
         """inference.py:251-281 at eval.  ``locations`` is accepted for interface compatibility (and verified);

@@ -141,7 +141,7 @@ class FcosResult:
 
 
 def fcos_config(level_shapes, strides, batch, pre_nms_thresh, pre_nms_top_n, nms_thresh, post_nms_top_n, min_size,
-                strict=False, early_exit=True) -> FcosConfig:
+                strict=False, early_exit=True, reg_scales=None) -> FcosConfig:
     if len(level_shapes) > OSD_MAX_LEVELS:
         raise OsdError(f"at most {OSD_MAX_LEVELS} FPN levels are supported")
     cfg = FcosConfig()
@@ -156,6 +156,12 @@ def fcos_config(level_shapes, strides, batch, pre_nms_thresh, pre_nms_top_n, nms
     cfg.min_size = float(min_size)
     cfg.strict = int(bool(strict))
     cfg.early_exit = int(bool(early_exit))
+    if reg_scales is not None:  # reg[l] is the raw bbox_pred conv output: exp(x * scale_l) is evaluated in the kernel
+        if len(reg_scales) != len(level_shapes):
+            raise OsdError(f"fcos_postprocess: {len(level_shapes)} levels but {len(reg_scales)} regression scales")
+        cfg.reg_transform = 1
+        for l, v in enumerate(reg_scales):
+            cfg.reg_scale[l] = float(v)
     return cfg
 
 
@@ -164,7 +170,7 @@ class PreparedFcos:
     C-ABI invocation on the current stream (serving loops, CUDA-graph capture)."""
 
     def __init__(self, cls, reg, ctr, strides, image_sizes, pre_nms_thresh, pre_nms_top_n, nms_thresh, post_nms_top_n,
-                 min_size=0.0, strict=False, early_exit=True, workspace=None, private_workspace=False):
+                 min_size=0.0, strict=False, early_exit=True, workspace=None, private_workspace=False, reg_scales=None):
         self.lib = _lib.load()
         dev = cls[0].device
         _lib.require_device(dev)
@@ -183,7 +189,7 @@ class PreparedFcos:
         self.ctr = [t.contiguous() for t in ctr]
         self.device = dev
         self.cfg = fcos_config(shapes, strides, b, pre_nms_thresh, pre_nms_top_n, nms_thresh, post_nms_top_n, min_size,
-                               strict, early_exit)
+                               strict, early_exit, reg_scales)
         self.plan = FcosPlan()
         _lib.check(self.lib.osd_fcos_postprocess_plan(ctypes.byref(self.cfg), ctypes.byref(self.plan)),
                    "osd_fcos_postprocess_plan")
@@ -229,13 +235,16 @@ class PreparedFcos:
 
 
 def fcos_postprocess(cls, reg, ctr, strides, image_sizes, pre_nms_thresh, pre_nms_top_n, nms_thresh, post_nms_top_n,
-                     min_size=0.0, strict=False, early_exit=True, workspace: torch.Tensor | None = None) -> FcosResult:
+                     min_size=0.0, strict=False, early_exit=True, workspace: torch.Tensor | None = None,
+                     reg_scales=None) -> FcosResult:
     """Fused score / top-k / decode / clip / NMS / post-top-n for all levels and episodes.
 
     cls[l] [B,1,H,W] logits, reg[l] [B,4,H,W] ltrb distances, ctr[l] [B,1,H,W] logits (fp32 CUDA, NCHW);
-    image_sizes: list of (h, w) per episode, or an int32 CUDA tensor [B,2].  No host synchronisation."""
+    image_sizes: list of (h, w) per episode, or an int32 CUDA tensor [B,2].  No host synchronisation.
+    reg_scales (one float per level): reg[l] is the RAW output of the head's bbox_pred conv and the head's tail
+    ``torch.exp(scales[l](x))`` (fcos.py:95-97) is folded into the decode of the selected locations."""
     return PreparedFcos(cls, reg, ctr, strides, image_sizes, pre_nms_thresh, pre_nms_top_n, nms_thresh, post_nms_top_n,
-                        min_size, strict, early_exit, workspace)()
+                        min_size, strict, early_exit, workspace, reg_scales=reg_scales)()
 
 
 # --------------------------------------------------------------------------------------------------

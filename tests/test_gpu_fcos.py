@@ -202,3 +202,38 @@ def test_multi_class_logits_use_channel_zero():
     n = int(a.count[0])
     assert torch.equal(a.count, b.count) and torch.equal(a.boxes[:, :n], b.boxes[:, :n])
     assert torch.equal(a.scores[:, :n], b.scores[:, :n])
+
+
+def test_raw_regression_with_folded_exp_scale():
+    """SURVEY 8(f) row 3: box_regression given as the RAW bbox_pred conv output plus the per-level Scale parameters;
+    the head's tail exp(x * scale_l) (fcos.py:95-97) is evaluated inside the decode.  Tolerance: the device expf and
+    ATen's CPU exp differ by <= 2 ulp of the distance (<= 2.4e-4 px at distances < 2048 px) and the box coordinate
+    adds one rounding -> |delta| <= 1e-3 px, written below; selection, scores and the NMS boundary stay exact."""
+    b, h, w = 3, 200, 264
+    cls, reg, ctr = orc.synth_head_outputs(b, h, w, seed=31)
+    scales = [1.0, 0.83, 1.21, 0.97, 1.4]
+    raw = [torch.log(r) / s for r, s in zip(reg, scales)]
+    sizes = [(200, 260), (190, 264), (200, 264)]
+    p = orc.PostParams(0.0, 800, 0.7, 150, 0.0)
+    post = make_post(p)
+    res = post.forward_fixed(to_dev(cls), to_dev(raw), to_dev(ctr), sizes, reg_scales=scales)
+    torch.cuda.synchronize()
+    reg_ref = [orc.fcos_head_tail(x, s) for x, s in zip(raw, scales)]     # the reference's elementwise passes
+    oc = orc.fcos_candidates(cls, reg_ref, ctr, orc.FPN_STRIDES, sizes, p)
+    counts = res.count.cpu().numpy()
+    cands = gpu_candidates(res)                                            # (the workspace is shared between calls)
+    for e, ((gb, gs, glv, gloc), (ob, os_, olv, oloc)) in enumerate(zip(cands, oc)):
+        np.testing.assert_array_equal(glv, olv)
+        np.testing.assert_array_equal(gloc, oloc)
+        np.testing.assert_allclose(gs, os_, rtol=SCORE_RTOL, atol=0)
+        np.testing.assert_allclose(gb, ob, rtol=0, atol=1e-3)
+        eb, es, ek = orc.select_over_all_levels(gb, gs, p)                 # NMS boundary on the GPU's candidates
+        n = counts[e]
+        assert n == ek.shape[0]
+        np.testing.assert_array_equal(res.index[e, :n].cpu().numpy(), ek)
+        np.testing.assert_array_equal(res.boxes[e, :n].cpu().numpy(), eb)
+    # and with scale 1 on already-exp'd input the two entry forms agree to the same tolerance
+    res2 = post.forward_fixed(to_dev(cls), to_dev(reg_ref), to_dev(ctr), sizes)
+    torch.cuda.synchronize()
+    for (gb, *_), (hb, *_) in zip(cands, gpu_candidates(res2)):
+        np.testing.assert_allclose(gb, hb, rtol=0, atol=1e-3)
