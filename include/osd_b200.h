@@ -241,6 +241,63 @@ typedef struct {
 
 int osd_support_pool(const osd_support_pool_desc* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Second-stage (ROI box head) post-processing -- SURVEY section 8(f) row 2, the step after the hot path.
+ *
+ * Replaces  PostProcessor.forward / prepare_boxlist / filter_results
+ *           (maskrcnn_benchmark/modeling/roi_heads/box_head/inference.py:46-167), BoxCoder.decode
+ *           (modeling/box_coder.py:52-95), BoxList.clip_to_image (structures/bounding_box.py:214-224) and the
+ *           boxlist_nms call of :150-152, for the one-foreground-class episode problem (num_classes = 2, :89).
+ *
+ * class_logits [B*R, num_logits], box_regression [B*R, reg_columns] (class 1 uses columns
+ * [reg_offset, reg_offset+4): 4 for the 8-column head output of :60 with or without CLS_AGNOSTIC_BBOX_REG),
+ * proposals [B, R, 4] xyxy (R rows per image; roi_count[b] <= R valid rows when roi_count != NULL), image_hw [B,2].
+ * score = softmax(logits)[1] (ce/cxe, :66-67) or sigmoid(logits[0]) (focal, :62-65); a proposal survives iff
+ * score > score_thresh (:142); its box is BoxCoder.decode with `weights` and the dw/dh clamp, clipped to the image;
+ * per image NMS(nms_thresh) in proposal order (:144-152), then, if more than detections_per_img > 0 survive, the best
+ * detections_per_img by score in descending order (:162-166), else all survivors in ascending proposal order.
+ * Outputs as osd_fcos_postprocess: out_index holds the compact candidate index (its proposal row is
+ * cand_src[out_index], see the plan offsets).  No host synchronisation.
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum { OSD_SCORE_SOFTMAX = 0, OSD_SCORE_SIGMOID = 1 } osd_score_mode;
+
+typedef struct {
+  int32_t batch;               /* B images */
+  int32_t rois_per_image;      /* R */
+  int32_t num_logits;          /* columns of class_logits */
+  int32_t reg_columns;         /* columns of box_regression */
+  int32_t reg_offset;          /* first regression column of class 1 */
+  int32_t score_mode;          /* osd_score_mode */
+  float weights[4];            /* BoxCoder weights (wx, wy, ww, wh); MODEL.ROI_HEADS.BBOX_REG_WEIGHTS */
+  float bbox_xform_clip;       /* box_coder.py:21: log(1000/16) */
+  float score_thresh;          /* MODEL.ROI_HEADS.SCORE_THRESH */
+  float nms_thresh;            /* MODEL.ROI_HEADS.NMS; <= 0: no suppression */
+  int32_t detections_per_img;  /* MODEL.ROI_HEADS.DETECTIONS_PER_IMG; <= 0: unlimited */
+  int32_t strict;              /* as osd_fcos_config */
+  int32_t early_exit;
+} osd_box_post_config;
+
+typedef struct {
+  size_t workspace_bytes;
+  int32_t cand_capacity;   /* R */
+  int32_t out_capacity;    /* K: rows per image in the outputs */
+  size_t off_cand_boxes;   /* float [B, R, 4] decoded + clipped boxes of the surviving proposals, compacted */
+  size_t off_cand_scores;  /* float [B, R] */
+  size_t off_cand_src;     /* int32 [B, R] proposal row of each candidate */
+  size_t off_cand_count;   /* int32 [B] */
+  size_t off_kept_count;   /* int32 [B] kept by NMS before the cut */
+} osd_box_post_plan;
+
+int osd_box_postprocess_plan(const osd_box_post_config* cfg, osd_box_post_plan* plan);
+
+int osd_box_postprocess(const osd_box_post_config* cfg,
+                        const float* class_logits, const float* box_regression, const float* proposals,
+                        const int32_t* roi_count,  /* device int32 [B] or NULL */
+                        const int32_t* image_hw,   /* device int32 [B,2]: (h, w) */
+                        void* workspace, size_t workspace_bytes,
+                        float* out_boxes, float* out_scores, int32_t* out_index, int32_t* out_count,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

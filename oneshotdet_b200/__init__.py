@@ -8,8 +8,9 @@ from . import _C  # noqa: F401
 from .layers import nms  # noqa: F401
 from .modeling.matching import MatchingModule  # noqa: F401
 from .modeling.rpn.fcos.inference import FCOSPostProcessor, make_fcos_postprocessor  # noqa: F401
+from .modeling.roi_heads.box_head.inference import BoxCoder, PostProcessor, make_roi_box_post_processor  # noqa: F401
 from .modeling.support_pooling import SuppAlignLayer, SuppAvgPool, support_pool  # noqa: F401
-from .ops import batched_nms, fcos_postprocess, match_forward  # noqa: F401
+from .ops import batched_nms, box_postprocess, fcos_postprocess, match_forward  # noqa: F401
 from .structures.bounding_box import BoxList  # noqa: F401
 from .structures.boxlist_ops import boxlist_nms, cat_boxlist, remove_small_boxes  # noqa: F401
 

@@ -36,6 +36,21 @@ class FcosPlan(ctypes.Structure):
                 ("off_kept_count", ctypes.c_size_t)]
 
 
+class BoxPostConfig(ctypes.Structure):
+    _fields_ = [("batch", ctypes.c_int32), ("rois_per_image", ctypes.c_int32), ("num_logits", ctypes.c_int32),
+                ("reg_columns", ctypes.c_int32), ("reg_offset", ctypes.c_int32), ("score_mode", ctypes.c_int32),
+                ("weights", ctypes.c_float * 4), ("bbox_xform_clip", ctypes.c_float), ("score_thresh", ctypes.c_float),
+                ("nms_thresh", ctypes.c_float), ("detections_per_img", ctypes.c_int32), ("strict", ctypes.c_int32),
+                ("early_exit", ctypes.c_int32)]
+
+
+class BoxPostPlan(ctypes.Structure):
+    _fields_ = [("workspace_bytes", ctypes.c_size_t), ("cand_capacity", ctypes.c_int32),
+                ("out_capacity", ctypes.c_int32), ("off_cand_boxes", ctypes.c_size_t),
+                ("off_cand_scores", ctypes.c_size_t), ("off_cand_src", ctypes.c_size_t),
+                ("off_cand_count", ctypes.c_size_t), ("off_kept_count", ctypes.c_size_t)]
+
+
 class MatchDesc(ctypes.Structure):
     _fields_ = [("num_levels", ctypes.c_int32), ("batch", ctypes.c_int32), ("shots", ctypes.c_int32),
                 ("channels", ctypes.c_int32), ("mode", ctypes.c_int32), ("layout", ctypes.c_int32),
@@ -82,6 +97,9 @@ SYMBOLS = {
     "osd_fusion_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(FusionDesc), ctypes.POINTER(ctypes.c_size_t)]),
     "osd_fusion_forward": (ctypes.c_int, [ctypes.POINTER(FusionDesc), c_void_p, ctypes.c_size_t, c_void_p]),
     "osd_support_pool": (ctypes.c_int, [ctypes.POINTER(SupportPoolDesc), c_void_p]),
+    "osd_box_postprocess_plan": (ctypes.c_int, [ctypes.POINTER(BoxPostConfig), ctypes.POINTER(BoxPostPlan)]),
+    "osd_box_postprocess": (ctypes.c_int, [ctypes.POINTER(BoxPostConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, ctypes.c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -320,3 +320,101 @@ def match_forward(features, supp_pooled, batch_size: int, mode: str = "product",
     (episode-major, shot-minor).  Returns a list of [B,C,H,W] (product) or [B,2C,H,W] (concat) tensors in the
     input's memory format.  All levels go out in one kernel launch."""
     return PreparedMatch(list(features), list(supp_pooled), batch_size, mode, out)()
+
+
+# --------------------------------------------------------------------------------------------------
+# second-stage box post-processing  (reference: modeling/roi_heads/box_head/inference.py:46-167,
+# modeling/box_coder.py:52-95) -- SURVEY section 8(f) row 2
+# --------------------------------------------------------------------------------------------------
+SCORE_MODES = {"softmax": 0, "sigmoid": 1}
+BBOX_XFORM_CLIP = 4.135166556742356  # math.log(1000. / 16), box_coder.py:21
+
+
+@dataclass
+class BoxPostResult:
+    boxes: torch.Tensor        # [B, K, 4]
+    scores: torch.Tensor       # [B, K]
+    index: torch.Tensor        # [B, K] int32 compact candidate index
+    count: torch.Tensor        # [B] int32
+    plan: "_lib.BoxPostPlan"
+    workspace: torch.Tensor
+
+    def _view(self, off, dtype, shape):
+        n = 1
+        for s in shape:
+            n *= s
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        return self.workspace[off:off + nbytes].view(dtype).view(*shape)
+
+    def candidates(self):
+        """(cand_boxes [B,R,4], cand_scores [B,R], cand_src [B,R] proposal rows, cand_count [B])."""
+        b, r = self.boxes.size(0), self.plan.cand_capacity
+        return (self._view(self.plan.off_cand_boxes, torch.float32, (b, r, 4)),
+                self._view(self.plan.off_cand_scores, torch.float32, (b, r)),
+                self._view(self.plan.off_cand_src, torch.int32, (b, r)),
+                self._view(self.plan.off_cand_count, torch.int32, (b,)))
+
+
+def box_postprocess(class_logits, box_regression, proposals, image_sizes, score_thresh=0.0, nms_thresh=0.5,
+                    detections_per_img=2000, weights=(10.0, 10.0, 5.0, 5.0), score_mode="softmax", reg_offset=4,
+                    roi_count=None, bbox_xform_clip=BBOX_XFORM_CLIP, strict=False, early_exit=True,
+                    private_workspace=False) -> BoxPostResult:
+    """Second-stage post-processing for all images of the batch, no host synchronisation.
+
+    class_logits [B*R, L], box_regression [B*R, >= reg_offset+4] (fp32 CUDA), proposals [B, R, 4] xyxy,
+    image_sizes list of (h, w) or int32 CUDA [B,2]; roi_count optional int32 CUDA [B] (valid rows per image)."""
+    dev = class_logits.device
+    _lib.require_device(dev)
+    lib = _lib.load()
+    if score_mode not in SCORE_MODES:
+        raise OsdError(f"box_postprocess: unknown score_mode '{score_mode}' (expected one of {sorted(SCORE_MODES)})")
+    if proposals.dim() != 3 or proposals.size(2) != 4:
+        raise OsdError(f"box_postprocess: proposals must be [B,R,4], got {tuple(proposals.shape)}")
+    b, r = proposals.size(0), proposals.size(1)
+    for name, t in (("class_logits", class_logits), ("box_regression", box_regression), ("proposals", proposals)):
+        if t.dtype != torch.float32 or t.device != dev:
+            raise OsdError(f"box_postprocess: {name} must be float32 on {dev}")
+    if class_logits.dim() != 2 or class_logits.size(0) != b * r or box_regression.dim() != 2 or box_regression.size(0) != b * r:
+        raise OsdError(f"box_postprocess: expected {b * r} rows of logits / regression, got "
+                       f"{tuple(class_logits.shape)} / {tuple(box_regression.shape)}")
+    cfg = _lib.BoxPostConfig()
+    cfg.batch, cfg.rois_per_image = b, max(r, 1)
+    cfg.num_logits, cfg.reg_columns, cfg.reg_offset = class_logits.size(1), box_regression.size(1), int(reg_offset)
+    cfg.score_mode = SCORE_MODES[score_mode]
+    for k in range(4):
+        cfg.weights[k] = float(weights[k])
+    cfg.bbox_xform_clip = float(bbox_xform_clip)
+    cfg.score_thresh, cfg.nms_thresh = float(score_thresh), float(nms_thresh)
+    cfg.detections_per_img = int(detections_per_img)
+    cfg.strict, cfg.early_exit = int(bool(strict)), int(bool(early_exit))
+    plan = _lib.BoxPostPlan()
+    _lib.check(lib.osd_box_postprocess_plan(ctypes.byref(cfg), ctypes.byref(plan)), "osd_box_postprocess_plan")
+    if isinstance(image_sizes, torch.Tensor):
+        hw = image_sizes.to(device=dev, dtype=torch.int32).contiguous()
+    else:
+        key = (dev.index, tuple((int(h), int(w)) for h, w in image_sizes))
+        hw = _cached_small_tensor(_hw_cache, key, [[int(h), int(w)] for h, w in image_sizes], torch.int32, dev)
+    if hw.numel() != 2 * b:
+        raise OsdError(f"box_postprocess: {b} images but {hw.numel() // 2} image sizes")
+    if roi_count is not None:
+        if roi_count.dtype != torch.int32 or roi_count.device != dev or roi_count.numel() != b:
+            raise OsdError("box_postprocess: roi_count must be an int32 vector [B] on the inputs' device")
+        roi_count = roi_count.contiguous()
+    k = plan.out_capacity
+    out_boxes = torch.empty((b, k, 4), dtype=torch.float32, device=dev)
+    out_scores = torch.empty((b, k), dtype=torch.float32, device=dev)
+    out_index = torch.empty((b, k), dtype=torch.int32, device=dev)
+    out_count = torch.zeros((b,), dtype=torch.int32, device=dev)
+    ws = (torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev) if private_workspace
+          else _workspace.get(dev, plan.workspace_bytes))
+    res = BoxPostResult(out_boxes, out_scores, out_index, out_count, plan, ws)
+    if b == 0 or r == 0:
+        return res
+    cl, br, pr = class_logits.contiguous(), box_regression.contiguous(), proposals.contiguous()
+    with torch.cuda.device(dev):
+        rc = lib.osd_box_postprocess(ctypes.byref(cfg), cl.data_ptr(), br.data_ptr(), pr.data_ptr(),
+                                     roi_count.data_ptr() if roi_count is not None else None, hw.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), out_boxes.data_ptr(), out_scores.data_ptr(),
+                                     out_index.data_ptr(), out_count.data_ptr(), _lib.current_stream_ptr(dev))
+    _lib.check(rc, "osd_box_postprocess")
+    return res

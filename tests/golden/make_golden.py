@@ -13,6 +13,8 @@ What is executed (paths relative to /root/reference):
   * modeling/roi_heads/box_head/box_head.py:43-54,147-149   concat + compress_dim_conv (the stock nn.Sequential
                                                         the reference builds there)          -> match_*.npz
 
+  * modeling/roi_heads/box_head/inference.py:46-167     PostProcessor.forward (with modeling/box_coder.py)  -> box_post_*.npz
+
 Inputs are seeded numpy; they are stored next to the outputs so tests never need the reference.
 """
 from __future__ import annotations
@@ -167,9 +169,50 @@ def match_case(name, batch, shots, channels, height, width, seed):
     print(f"match_{name}.npz written")
 
 
+def box_post_case(name, batch, rois, image_sizes, params, seed, cls_loss="ce_loss", num_logits=2, agnostic=False):
+    """The reference's second-stage PostProcessor.forward (modeling/roi_heads/box_head/inference.py:46-104), executed."""
+    from maskrcnn_benchmark.modeling.box_coder import BoxCoder  # noqa: PLC0415
+    from maskrcnn_benchmark.modeling.roi_heads.box_head.inference import PostProcessor  # noqa: PLC0415
+    from maskrcnn_benchmark.structures.bounding_box import BoxList  # noqa: PLC0415
+
+    cfg = types.SimpleNamespace(FEW_SHOT=types.SimpleNamespace(SECOND_STAGE_CLS_LOSS=cls_loss))
+    post = PostProcessor(cfg, params.score_thresh, params.nms_thresh, params.detections_per_img,
+                         BoxCoder(weights=params.weights), agnostic).eval()
+    logits, reg, props = orc.synth_box_head_outputs(batch, rois, image_sizes, seed, num_logits=num_logits)
+    boxes = [BoxList(props[i].clone(), (int(image_sizes[i][1]), int(image_sizes[i][0])), mode="xyxy") for i in range(batch)]
+    target_ids = [7 + i for i in range(batch)]
+    with torch.no_grad():
+        out = post((logits.clone(), reg.clone()), boxes, target_ids=target_ids)
+    data = {"batch": batch, "rois": rois, "seed": seed, "image_sizes": np.asarray(image_sizes, dtype=np.int64),
+            "params": np.asarray([params.score_thresh, params.nms_thresh, params.detections_per_img], dtype=np.float64),
+            "weights": np.asarray(params.weights, dtype=np.float64), "cls_loss": np.asarray(cls_loss),
+            "agnostic": np.asarray(int(agnostic)), "target_ids": np.asarray(target_ids, dtype=np.int64),
+            "logits": logits.numpy(), "reg": reg.numpy(), "props": props.numpy()}
+    for i, bl in enumerate(out):
+        assert bl.mode == "xyxy"
+        data[f"out_boxes{i}"] = bl.bbox.numpy().astype(np.float32)
+        data[f"out_scores{i}"] = bl.get_field("scores").numpy().astype(np.float32)
+        data[f"out_labels{i}"] = bl.get_field("labels").numpy().astype(np.int64)
+        data[f"out_size{i}"] = np.asarray(bl.size, dtype=np.int64)
+        data[f"out_fields{i}"] = np.asarray(sorted(bl.fields()))
+    np.savez_compressed(os.path.join(HERE, f"box_post_{name}.npz"), **data)
+    print(f"box_post_{name}.npz:", [len(b) for b in out], "detections")
+
+
+def box_post_cases():
+    BP = orc.BoxPostParams
+    box_post_case("default", 2, 400, [(480, 640), (500, 375)], BP(0.0, 0.5, 2000), seed=41)
+    box_post_case("cut_thresh", 3, 300, [(300, 400)] * 3, BP(0.05, 0.7, 40), seed=42)
+    box_post_case("focal_agnostic", 2, 200, [(256, 256), (200, 300)], BP(0.3, 0.5, 2000, (10., 10., 5., 5.), "sigmoid"),
+                  seed=43, cls_loss="focal_loss", num_logits=1, agnostic=True)
+
+
 def main():
     torch.set_num_threads(1)
     ref_c = import_reference()
+    if "--only-box-post" in sys.argv:
+        box_post_cases()
+        return
     record_nms_kat(ref_c)
     P = orc.PostParams
     # small padded inputs (multiples of 128 so every level is non-empty and regular)
@@ -179,6 +222,7 @@ def main():
     fcos_case("nonms_small", 1, 128, 128, [(128, 128)], P(0.05, 50, 0.0, 30, 0.0), seed=14)
     match_case("s1_c64", 2, 1, 64, 96, 160, seed=21)
     match_case("s3_c64", 2, 3, 64, 64, 96, seed=22)
+    box_post_cases()
 
 
 if __name__ == "__main__":
