@@ -298,6 +298,41 @@ int osd_box_postprocess(const osd_box_post_config* cfg,
                         float* out_boxes, float* out_scores, int32_t* out_index, int32_t* out_count,
                         void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-level ROI pooler of the second stage -- SURVEY section 8(f) row 2, pooling half.
+ *
+ * Replaces  Pooler.forward (maskrcnn_benchmark/modeling/poolers.py:93-125) with LevelMapper (:10-41) and the
+ *           per-level ROIAlign modules (layers/roi_align.py; kernel csrc/cuda/ROIAlign_cuda.cu:65-122, CPU twin
+ *           csrc/cpu/ROIAlign_cpu.cpp:14-214).
+ * feat[l] [B, C, H_l, W_l] fp32 NCHW; rois [B, R, 4] xyxy in image coordinates (ROI (b, r) reads image b -- the
+ * (img_id, box) rows of convert_to_roi_format, poolers.py:77-91); out [B*R, C, P, P] fp32, the reference's layout
+ * (viewed [B, R, C, P, P] at poolers.py:123).  ROI -> level: floor(canonical_level + log2(sqrt(area)/canonical_scale
+ * + eps)) clamped to [k_min, k_max], minus k_min; a single level skips the mapper (:104-105).  Rows r >= roi_count[b]
+ * (when roi_count != NULL) are written as zeros, levels_out = -1.  Bit-identical to the reference CPU operator.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t num_levels;
+  int32_t batch;            /* B */
+  int32_t rois_per_image;   /* R */
+  int32_t channels;         /* C */
+  int32_t pooled_size;      /* P: MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION */
+  int32_t sampling_ratio;   /* MODEL.ROI_BOX_HEAD.POOLER_SAMPLING_RATIO (<= 0: adaptive) */
+  int32_t height[OSD_MAX_LEVELS];
+  int32_t width[OSD_MAX_LEVELS];
+  float spatial_scale[OSD_MAX_LEVELS];   /* MODEL.ROI_BOX_HEAD.POOLER_SCALES */
+  int32_t k_min, k_max;     /* -log2(scales[0]), -log2(scales[-1])  (poolers.py:72-74) */
+  float canonical_scale;    /* 224 */
+  int32_t canonical_level;  /* 4 */
+  float eps;                /* 1e-6 */
+  const void* feat[OSD_MAX_LEVELS];
+  const float* rois;        /* device [B, R, 4], 16-byte aligned */
+  const int32_t* roi_count; /* device int32 [B] or NULL */
+  float* out;               /* device [B*R, C, P, P] */
+  int32_t* levels_out;      /* device int32 [B*R] or NULL: the level each ROI was pooled from */
+} osd_roi_pool_desc;
+
+int osd_roi_pool(const osd_roi_pool_desc* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

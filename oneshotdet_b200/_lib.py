@@ -79,6 +79,17 @@ class SupportPoolDesc(ctypes.Structure):
                 ("rois", ctypes.c_void_p)]
 
 
+class RoiPoolDesc(ctypes.Structure):
+    _fields_ = [("num_levels", ctypes.c_int32), ("batch", ctypes.c_int32), ("rois_per_image", ctypes.c_int32),
+                ("channels", ctypes.c_int32), ("pooled_size", ctypes.c_int32), ("sampling_ratio", ctypes.c_int32),
+                ("height", ctypes.c_int32 * OSD_MAX_LEVELS), ("width", ctypes.c_int32 * OSD_MAX_LEVELS),
+                ("spatial_scale", ctypes.c_float * OSD_MAX_LEVELS),
+                ("k_min", ctypes.c_int32), ("k_max", ctypes.c_int32), ("canonical_scale", ctypes.c_float),
+                ("canonical_level", ctypes.c_int32), ("eps", ctypes.c_float),
+                ("feat", ctypes.c_void_p * OSD_MAX_LEVELS), ("rois", ctypes.c_void_p), ("roi_count", ctypes.c_void_p),
+                ("out", ctypes.c_void_p), ("levels_out", ctypes.c_void_p)]
+
+
 # every symbol include/osd_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "osd_version": (ctypes.c_int, []),
@@ -97,6 +108,7 @@ SYMBOLS = {
     "osd_fusion_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(FusionDesc), ctypes.POINTER(ctypes.c_size_t)]),
     "osd_fusion_forward": (ctypes.c_int, [ctypes.POINTER(FusionDesc), c_void_p, ctypes.c_size_t, c_void_p]),
     "osd_support_pool": (ctypes.c_int, [ctypes.POINTER(SupportPoolDesc), c_void_p]),
+    "osd_roi_pool": (ctypes.c_int, [ctypes.POINTER(RoiPoolDesc), c_void_p]),
     "osd_box_postprocess_plan": (ctypes.c_int, [ctypes.POINTER(BoxPostConfig), ctypes.POINTER(BoxPostPlan)]),
     "osd_box_postprocess": (ctypes.c_int, [ctypes.POINTER(BoxPostConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, ctypes.c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -15,6 +15,8 @@ What is executed (paths relative to /root/reference):
 
   * modeling/roi_heads/box_head/inference.py:46-167     PostProcessor.forward (with modeling/box_coder.py)  -> box_post_*.npz
 
+  * modeling/poolers.py:93-125 with layers/roi_align.py  Pooler.forward + LevelMapper                         -> pooler_*.npz
+
 Inputs are seeded numpy; they are stored next to the outputs so tests never need the reference.
 """
 from __future__ import annotations
@@ -207,11 +209,42 @@ def box_post_cases():
                   seed=43, cls_loss="focal_loss", num_logits=1, agnostic=True)
 
 
+def pooler_case(name, batch, rois, channels, height, width, image_sizes, seed, resolution=7, sampling=2, lo=12.0):
+    """The reference's Pooler.forward (modeling/poolers.py:93-125: LevelMapper + per-level ROIAlign modules), executed."""
+    from maskrcnn_benchmark.modeling.poolers import Pooler  # noqa: PLC0415
+    from maskrcnn_benchmark.structures.bounding_box import BoxList  # noqa: PLC0415
+
+    scales = tuple(1.0 / s for s in orc.FPN_STRIDES)
+    pooler = Pooler(output_size=(resolution, resolution), scales=scales, sampling_ratio=sampling)
+    feats, _ = orc.synth_features(batch, 1, channels, height, width, seed)
+    boxes_t = orc.synth_rois(batch, rois, image_sizes, seed + 1, lo)
+    boxes = [BoxList(boxes_t[i].clone(), (int(image_sizes[i][1]), int(image_sizes[i][0])), mode="xyxy") for i in range(batch)]
+    with torch.no_grad():
+        out = pooler(tuple(feats), boxes)
+        levels = pooler.map_levels(boxes)
+    assert tuple(out.shape) == (batch, rois, channels, resolution, resolution)
+    data = {"batch": batch, "rois": rois, "channels": channels, "height": height, "width": width, "seed": seed,
+            "resolution": resolution, "sampling": sampling, "lo": lo, "image_sizes": np.asarray(image_sizes, dtype=np.int64),
+            "scales": np.asarray(scales, dtype=np.float64), "boxes": boxes_t.numpy(),
+            "pooled": out.numpy().astype(np.float32), "levels": levels.numpy().astype(np.int64)}
+    np.savez_compressed(os.path.join(HERE, f"pooler_{name}.npz"), **data)
+    print(f"pooler_{name}.npz: levels", np.bincount(levels.numpy().astype(np.int64), minlength=5).tolist())
+
+
+def pooler_cases():
+    pooler_case("r7_s2", 2, 48, 8, 512, 640, [(500, 640), (512, 600)], seed=71)
+    pooler_case("all_levels", 1, 64, 2, 2048, 2304, [(2048, 2300)], seed=75, lo=150.0)
+    pooler_case("r3_adaptive", 1, 32, 4, 384, 384, [(384, 384)], seed=73, resolution=3, sampling=0)
+
+
 def main():
     torch.set_num_threads(1)
     ref_c = import_reference()
     if "--only-box-post" in sys.argv:
         box_post_cases()
+        return
+    if "--only-pooler" in sys.argv:
+        pooler_cases()
         return
     record_nms_kat(ref_c)
     P = orc.PostParams
@@ -223,6 +256,7 @@ def main():
     match_case("s1_c64", 2, 1, 64, 96, 160, seed=21)
     match_case("s3_c64", 2, 3, 64, 64, 96, seed=22)
     box_post_cases()
+    pooler_cases()
 
 
 if __name__ == "__main__":
