@@ -329,8 +329,12 @@ typedef struct {
   const int32_t* roi_count; /* device int32 [B] or NULL */
   float* out;               /* device [B*R, C, P, P] */
   int32_t* levels_out;      /* device int32 [B*R] or NULL: the level each ROI was pooled from */
+  void* workspace;          /* device scratch of osd_roi_pool_workspace_bytes() bytes (256-byte aligned) for the
+                               channels-last copy of the maps; NULL: pool straight from NCHW (slower, same result) */
+  size_t workspace_bytes;
 } osd_roi_pool_desc;
 
+int osd_roi_pool_workspace_bytes(const osd_roi_pool_desc* desc, size_t* bytes);
 int osd_roi_pool(const osd_roi_pool_desc* desc, void* stream);
 
 #ifdef __cplusplus

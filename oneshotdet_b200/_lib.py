@@ -87,7 +87,8 @@ class RoiPoolDesc(ctypes.Structure):
                 ("k_min", ctypes.c_int32), ("k_max", ctypes.c_int32), ("canonical_scale", ctypes.c_float),
                 ("canonical_level", ctypes.c_int32), ("eps", ctypes.c_float),
                 ("feat", ctypes.c_void_p * OSD_MAX_LEVELS), ("rois", ctypes.c_void_p), ("roi_count", ctypes.c_void_p),
-                ("out", ctypes.c_void_p), ("levels_out", ctypes.c_void_p)]
+                ("out", ctypes.c_void_p), ("levels_out", ctypes.c_void_p), ("workspace", ctypes.c_void_p),
+                ("workspace_bytes", ctypes.c_size_t)]
 
 
 # every symbol include/osd_b200.h declares: name -> (restype, argtypes)
@@ -109,6 +110,7 @@ SYMBOLS = {
     "osd_fusion_forward": (ctypes.c_int, [ctypes.POINTER(FusionDesc), c_void_p, ctypes.c_size_t, c_void_p]),
     "osd_support_pool": (ctypes.c_int, [ctypes.POINTER(SupportPoolDesc), c_void_p]),
     "osd_roi_pool": (ctypes.c_int, [ctypes.POINTER(RoiPoolDesc), c_void_p]),
+    "osd_roi_pool_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(RoiPoolDesc), ctypes.POINTER(ctypes.c_size_t)]),
     "osd_box_postprocess_plan": (ctypes.c_int, [ctypes.POINTER(BoxPostConfig), ctypes.POINTER(BoxPostPlan)]),
     "osd_box_postprocess": (ctypes.c_int, [ctypes.POINTER(BoxPostConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, ctypes.c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -118,8 +118,139 @@ __global__ void __launch_bounds__(kPoolThreads) roi_pool_kernel(RoiPoolArgs A) {
   }
 }
 
+// ---- channels-last path -----------------------------------------------------------------------------------------
+// NCHW taps of one ROI touch 256 channel planes with ~100-byte row segments each: every warp load splinters into 10+
+// sectors.  With the maps transposed once per batch to [B, H*W, C] (a 2 x 367 MB streaming pass at config size) a tap is
+// one contiguous C-vector: 64 threads x LDG.128 = 1 KB, fully coalesced, and the hi/lo taps of neighbouring samples hit
+// in L1.  Results are staged in shared memory in the reference's [C][P][P] order and written as one linear run.
+constexpr int kTr = 32;
+
+struct TransposeArgs {
+  int nl, B, C;
+  const float* in[OSD_MAX_LEVELS];
+  float* out[OSD_MAX_LEVELS];
+  int HW[OSD_MAX_LEVELS];
+  int tile0[OSD_MAX_LEVELS + 1];   // first blockIdx.x of each level (tiles of 32 pixels)
+};
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(TransposeArgs A) {
+  __shared__ float tile[kTr][kTr + 1];
+  int l = 0;
+  while (l + 1 < A.nl && (int)blockIdx.x >= A.tile0[l + 1]) ++l;
+  const int p0 = ((int)blockIdx.x - A.tile0[l]) * kTr, c0 = blockIdx.y * kTr, b = blockIdx.z;
+  const int HW = A.HW[l];
+  const float* in = A.in[l] + (size_t)b * A.C * HW;
+  float* out = A.out[l] + (size_t)b * HW * A.C;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int k = 0; k < kTr; k += 8) {
+    const int c = c0 + ty + k, p = p0 + tx;
+    if (c < A.C && p < HW) tile[ty + k][tx] = in[(size_t)c * HW + p];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kTr; k += 8) {
+    const int p = p0 + ty + k, c = c0 + tx;
+    if (c < A.C && p < HW) out[(size_t)p * A.C + c] = tile[tx][ty + k];
+  }
+}
+
+__global__ void __launch_bounds__(kPoolThreads) roi_pool_nhwc_kernel(RoiPoolArgs A) {
+  extern __shared__ float stage[];   // [C * P * P] in output order
+  __shared__ AxisTap ytab[kTab], xtab[kTab];
+  const int roi = blockIdx.x;
+  const int b = roi / A.R, r = roi - b * A.R;
+  const int tid = threadIdx.x;
+  const int PP = A.P * A.P, per_roi = A.C * PP;
+  float* out = A.out + (size_t)roi * per_roi;
+  const int n_valid = A.roi_count ? min(max(A.roi_count[b], 0), A.R) : A.R;
+  if (r >= n_valid) {
+    for (int e = tid; e < per_roi; e += kPoolThreads) out[e] = 0.f;
+    if (tid == 0 && A.levels_out) A.levels_out[roi] = -1;
+    return;
+  }
+  const float4 box = A.rois[roi];
+  const float area = __fmul_rn(__fadd_rn(__fsub_rn(box.z, box.x), 1.0f), __fadd_rn(__fsub_rn(box.w, box.y), 1.0f));
+  const float s = __fsqrt_rn(area);
+  float lv = floorf(__fadd_rn(A.lvl0, log2f(__fadd_rn(__fdiv_rn(s, A.s0), A.eps))));
+  lv = fminf(fmaxf(lv, A.k_min), A.k_max);
+  const int l = A.nl == 1 ? 0 : (int)(lv - A.k_min);
+  if (tid == 0 && A.levels_out) A.levels_out[roi] = l;
+  const int H = A.H[l], W = A.W[l];
+  const float sc = A.scale[l];
+  const float roi_start_w = __fmul_rn(box.x, sc), roi_start_h = __fmul_rn(box.y, sc);
+  const float roi_end_w = __fmul_rn(box.z, sc), roi_end_h = __fmul_rn(box.w, sc);
+  const float roi_width = fmaxf(__fsub_rn(roi_end_w, roi_start_w), 1.0f);
+  const float roi_height = fmaxf(__fsub_rn(roi_end_h, roi_start_h), 1.0f);
+  const float bin_h = __fdiv_rn(roi_height, (float)A.P), bin_w = __fdiv_rn(roi_width, (float)A.P);
+  const int gh = A.sampling > 0 ? A.sampling : (int)ceilf(__fdiv_rn(roi_height, (float)A.P));
+  const int gw = A.sampling > 0 ? A.sampling : (int)ceilf(__fdiv_rn(roi_width, (float)A.P));
+  const float count = (float)(gh * gw);
+  const bool tabbed = A.P * gh <= kTab && A.P * gw <= kTab;
+  if (tabbed) {
+    for (int t = tid; t < A.P * gh; t += kPoolThreads) ytab[t] = axis_tap(roi_start_h, bin_h, t / gh, t % gh, gh, H);
+    for (int t = tid; t < A.P * gw; t += kPoolThreads) xtab[t] = axis_tap(roi_start_w, bin_w, t / gw, t % gw, gw, W);
+  }
+  __syncthreads();
+  // feat[l] here is the transposed copy [B, H*W, C]
+  const float4* fmap = reinterpret_cast<const float4*>(A.feat[l] + (size_t)b * H * W * A.C);
+  const int C4 = A.C >> 2;
+  // work items: (bin, channel quad); consecutive threads take consecutive quads of one bin
+  for (int item = tid; item < PP * C4; item += kPoolThreads) {
+    const int bin = item / C4, q = item - bin * C4;
+    const int ph = bin / A.P, pw = bin - ph * A.P;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int iy = 0; iy < gh; ++iy) {
+      const AxisTap ty = tabbed ? ytab[ph * gh + iy] : axis_tap(roi_start_h, bin_h, ph, iy, gh, H);
+      for (int ix = 0; ix < gw; ++ix) {
+        const AxisTap tx = tabbed ? xtab[pw * gw + ix] : axis_tap(roi_start_w, bin_w, pw, ix, gw, W);
+        if (!(ty.valid && tx.valid)) continue;
+        const float w1 = __fmul_rn(ty.h, tx.h), w2 = __fmul_rn(ty.h, tx.l), w3 = __fmul_rn(ty.l, tx.h), w4 = __fmul_rn(ty.l, tx.l);
+        const float4 v1 = __ldg(fmap + (size_t)(ty.lo * W + tx.lo) * C4 + q);
+        const float4 v2 = __ldg(fmap + (size_t)(ty.lo * W + tx.hi) * C4 + q);
+        const float4 v3 = __ldg(fmap + (size_t)(ty.hi * W + tx.lo) * C4 + q);
+        const float4 v4 = __ldg(fmap + (size_t)(ty.hi * W + tx.hi) * C4 + q);
+#define OSD_TAP(f) acc.f = __fadd_rn(acc.f, __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.f), __fmul_rn(w2, v2.f)), \
+                                                                 __fmul_rn(w3, v3.f)), __fmul_rn(w4, v4.f)))
+        OSD_TAP(x); OSD_TAP(y); OSD_TAP(z); OSD_TAP(w);
+#undef OSD_TAP
+      }
+    }
+    const int c = q << 2;
+    stage[(c + 0) * PP + bin] = __fdiv_rn(acc.x, count);
+    stage[(c + 1) * PP + bin] = __fdiv_rn(acc.y, count);
+    stage[(c + 2) * PP + bin] = __fdiv_rn(acc.z, count);
+    stage[(c + 3) * PP + bin] = __fdiv_rn(acc.w, count);
+  }
+  __syncthreads();
+  if ((per_roi & 3) == 0) {   // out + roi * per_roi is then 16-byte aligned (cudaMalloc / torch allocations are)
+    float4* o4 = reinterpret_cast<float4*>(out);
+    const float4* s4 = reinterpret_cast<const float4*>(stage);
+    for (int e = tid; e < (per_roi >> 2); e += kPoolThreads) __stcs(o4 + e, s4[e]);
+  } else {
+    for (int e = tid; e < per_roi; e += kPoolThreads) __stcs(out + e, stage[e]);
+  }
+}
+
+size_t transposed_bytes(const osd_roi_pool_desc* d, size_t* off) {
+  size_t total = 0;
+  for (int l = 0; l < d->num_levels; ++l) {
+    if (off) off[l] = total;
+    total += align_up((size_t)d->batch * d->channels * d->height[l] * d->width[l] * sizeof(float), 256);
+  }
+  return total;
+}
+
 }  // namespace
 }  // namespace osd
+
+extern "C" int osd_roi_pool_workspace_bytes(const osd_roi_pool_desc* d, size_t* bytes) {
+  using namespace osd;
+  OSD_REQUIRE(d != nullptr && bytes != nullptr, "osd_roi_pool_workspace_bytes: null argument");
+  OSD_REQUIRE(d->num_levels >= 1 && d->num_levels <= OSD_MAX_LEVELS, "osd_roi_pool: num_levels %d out of range", d->num_levels);
+  *bytes = transposed_bytes(d, nullptr);
+  return OSD_OK;
+}
 
 extern "C" int osd_roi_pool(const osd_roi_pool_desc* d, void* stream_) {
   using namespace osd;
@@ -150,7 +281,46 @@ extern "C" int osd_roi_pool(const osd_roi_pool_desc* d, void* stream_) {
   A.s0 = d->canonical_scale; A.lvl0 = (float)d->canonical_level; A.eps = d->eps;
   A.out = d->out;
   A.levels_out = d->levels_out;
-  roi_pool_kernel<<<(unsigned)n, kPoolThreads, 0, static_cast<cudaStream_t>(stream_)>>>(A);
-  OSD_LAUNCH_CHECK("roi_pool_kernel");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t stage_bytes = (size_t)d->channels * d->pooled_size * d->pooled_size * sizeof(float);
+  const bool channels_last = d->workspace != nullptr && (d->channels & 3) == 0 && stage_bytes <= 200 * 1024 &&
+                             (reinterpret_cast<uintptr_t>(d->out) & 15) == 0;
+  if (!channels_last) {  // direct NCHW taps (any C, no workspace)
+    roi_pool_kernel<<<(unsigned)n, kPoolThreads, 0, stream>>>(A);
+    OSD_LAUNCH_CHECK("roi_pool_kernel");
+    return OSD_OK;
+  }
+  size_t off[OSD_MAX_LEVELS];
+  const size_t need = transposed_bytes(d, off);
+  if (need > d->workspace_bytes) {
+    set_error("osd_roi_pool: workspace of %zu bytes needed, %zu given", need, d->workspace_bytes);
+    return OSD_ERR_WORKSPACE;
+  }
+  OSD_REQUIRE((reinterpret_cast<uintptr_t>(d->workspace) & 255) == 0, "osd_roi_pool: workspace must be 256-byte aligned");
+  TransposeArgs T{};
+  T.nl = d->num_levels; T.B = d->batch; T.C = d->channels;
+  int tiles = 0;
+  for (int l = 0; l < d->num_levels; ++l) {
+    T.in[l] = A.feat[l];
+    T.out[l] = reinterpret_cast<float*>(static_cast<char*>(d->workspace) + off[l]);
+    T.HW[l] = d->height[l] * d->width[l];
+    T.tile0[l] = tiles;
+    tiles += (int)ceil_div(T.HW[l], kTr);
+    A.feat[l] = T.out[l];
+  }
+  T.tile0[d->num_levels] = tiles;
+  OSD_REQUIRE(d->batch <= 65535 && ceil_div(d->channels, kTr) <= 65535, "osd_roi_pool: batch / channels out of range");
+  dim3 tgrid((unsigned)tiles, (unsigned)ceil_div(d->channels, kTr), (unsigned)d->batch);
+  nchw_to_nhwc_kernel<<<tgrid, 256, 0, stream>>>(T);
+  OSD_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+  {
+    static thread_local size_t configured = 48 * 1024;
+    if (stage_bytes > configured) {
+      OSD_CUDA(cudaFuncSetAttribute(roi_pool_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = 200 * 1024;
+    }
+  }
+  roi_pool_nhwc_kernel<<<(unsigned)n, kPoolThreads, stage_bytes, stream>>>(A);
+  OSD_LAUNCH_CHECK("roi_pool_nhwc_kernel");
   return OSD_OK;
 }

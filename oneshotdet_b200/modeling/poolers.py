@@ -14,11 +14,17 @@ from oneshotdet_b200 import _lib
 from oneshotdet_b200._lib import OsdError, RoiPoolDesc, OSD_MAX_LEVELS
 
 
+_workspace = _lib.Workspace()
+
+
 @torch.no_grad()
 def roi_pool(features, rois, scales, output_size: int = 7, sampling_ratio: int = 2, roi_count=None,
-             canonical_scale: float = 224.0, canonical_level: int = 4, eps: float = 1e-6, return_levels: bool = False):
+             canonical_scale: float = 224.0, canonical_level: int = 4, eps: float = 1e-6, return_levels: bool = False,
+             channels_last: bool = True):
     """features[l] [B,C,H_l,W_l] fp32 CUDA (NCHW); rois [B,R,4] xyxy (image coordinates; ROI (b, r) reads image b);
-    scales[l] per level.  Returns [B*R, C, P, P] (and the int32 level of every ROI when ``return_levels``)."""
+    scales[l] per level.  Returns [B*R, C, P, P] (and the int32 level of every ROI when ``return_levels``).
+    ``channels_last`` (default, needs C % 4 == 0): the library first transposes the maps to [B, H*W, C] in a scratch
+    buffer so that every bilinear tap is one contiguous channel vector; False pools straight from NCHW.  Same bits."""
     lib = _lib.load()
     nl = len(features)
     if nl == 0 or nl > OSD_MAX_LEVELS or len(scales) != nl:
@@ -55,6 +61,11 @@ def roi_pool(features, rois, scales, output_size: int = 7, sampling_ratio: int =
         d.roi_count = roi_count.data_ptr()
     d.rois, d.out = rois.data_ptr(), out.data_ptr()
     d.levels_out = levels.data_ptr() if levels is not None else None
+    if channels_last and c % 4 == 0 and b * r > 0:  # pool from a channels-last copy of the maps made by the library
+        need = ctypes.c_size_t(0)
+        _lib.check(lib.osd_roi_pool_workspace_bytes(ctypes.byref(d), ctypes.byref(need)), "osd_roi_pool_workspace_bytes")
+        ws = _workspace.get(dev, need.value)
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
     if b * r > 0:
         with torch.cuda.device(dev):
             rc = lib.osd_roi_pool(ctypes.byref(d), _lib.current_stream_ptr(dev))

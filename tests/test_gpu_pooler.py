@@ -77,7 +77,13 @@ def test_full_size_properties_and_time():
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(); out = osd.roi_pool(dfe, drois, SCALES, 7, 2); ev1.record(); torch.cuda.synchronize()
-    print(f"\nroi_pool 16x2000x256x7x7: {ev0.elapsed_time(ev1):.3f} ms, {out.numel() * 4 / 1e9 / (ev0.elapsed_time(ev1) / 1e3):.0f} GB/s written")
+    print(f"\nroi_pool 16x2000x256x7x7 (channels-last copy + pool): {ev0.elapsed_time(ev1):.3f} ms, "
+          f"{out.numel() * 4 / 1e9 / (ev0.elapsed_time(ev1) / 1e3):.0f} GB/s written")
+    direct = osd.roi_pool(dfe, drois, SCALES, 7, 2, channels_last=False)
+    ev0.record(); direct = osd.roi_pool(dfe, drois, SCALES, 7, 2, channels_last=False); ev1.record(); torch.cuda.synchronize()
+    print(f"roi_pool direct NCHW taps: {ev0.elapsed_time(ev1):.3f} ms")
+    assert torch.equal(out, direct)                                    # the two kernels produce the same bits
+    del direct
     pick = [(0, 0), (3, 77), (15, 1999), (8, 1000)]
     for (i, j) in pick:                                                # each picked ROI against its own image
         want, _ = orc.pooler_forward([f[i:i + 1] for f in feats], rois[i:i + 1, j:j + 1], SCALES, 7, 2)
