@@ -316,13 +316,13 @@ def run_b200_arm(args):
     total_ms_max = float(t.item())
     value = BATCH * n_gpus * steps / (total_ms_max * 1e-3)
 
-    # ---- roofline of the dominant streaming kernel (match_nchw_kernel: one launch per step)
+    # ---- roofline of the dominant streaming kernel (match_product_bulk_kernel: one launch per step)
     locs = sum(h * w for h, w in pipe.shapes)
     match_bytes = 2 * 4 * CHANNELS * locs * BATCH                     # fp32 in + out, SURVEY section 8(d)
     match_avg_ms = statistics.mean(match_ms)
     peak, peak_src = measured_peak_hbm()
     achieved = match_bytes / (match_avg_ms * 1e-3) / 1e9
-    roofline = {"kernel": "match_nchw_kernel<float, product>", "bound": "hbm", "achieved": achieved, "peak": peak,
+    roofline = {"kernel": "match_product_bulk_kernel<float>", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
                 "algorithmic_bytes_per_launch": match_bytes, "avg_launch_ms": match_avg_ms, "peak_source": peak_src,
                 "timing": "CUDA events around the kernel on its launching stream, kernel running alone (serial loop "

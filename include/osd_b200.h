@@ -40,6 +40,12 @@ int osd_check_device(void);
 /* Number of kernels this library has launched on this thread since the last reset (bench accounting). */
 int64_t osd_launch_count(void);
 void osd_reset_launch_count(void);
+/* Profiling aid (replaces the reference's host-side Timer, utils/timer.py, for this path): when enabled (or with
+ * OSD_TIMELINE=1 in the environment) every kernel launch of the library is followed by a CUDA event on its stream;
+ * osd_timeline_read synchronises the device and writes "name milliseconds-since-first-mark" lines, returns the
+ * number of marks and clears them.  Launches inside a stream capture are not marked. */
+void osd_timeline_enable(int on);
+int osd_timeline_read(char* buf, size_t capacity);
 
 /* ------------------------------------------------------------------------------------------------
  * Batched NMS.

@@ -8,7 +8,7 @@ import threading
 
 OSD_MAX_LEVELS = 8
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libosd_b200.so")
+LIB_PATH = os.environ.get("OSD_B200_LIB") or os.path.join(_HERE, "lib", "libosd_b200.so")  # env: an alternative build
 
 c_f32p = ctypes.c_void_p  # device pointers travel as integers
 c_void_p = ctypes.c_void_p
@@ -98,6 +98,8 @@ SYMBOLS = {
     "osd_check_device": (ctypes.c_int, []),
     "osd_launch_count": (ctypes.c_int64, []),
     "osd_reset_launch_count": (None, []),
+    "osd_timeline_enable": (None, [ctypes.c_int]),
+    "osd_timeline_read": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t]),
     "osd_batched_nms_plan": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(NmsPlan)]),
     "osd_batched_nms": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_float,
                                        ctypes.c_int, c_void_p, ctypes.c_size_t, c_void_p, c_void_p, c_void_p]),

@@ -1,5 +1,9 @@
 // Error plumbing, version and device checks of libosd_b200.so.
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "osd_common.cuh"
 
@@ -17,6 +21,36 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches += n; }
 
+// ---- kernel timeline (profiling aid): one CUDA event after every launch, on the launching stream ----------------
+namespace {
+struct Mark {
+  const char* name;
+  cudaEvent_t ev;
+};
+std::mutex g_tl_mutex;
+std::vector<Mark> g_marks;
+int g_timeline = -1;
+}  // namespace
+
+bool timeline_on() {
+  if (g_timeline < 0) {
+    const char* env = getenv("OSD_TIMELINE");
+    g_timeline = (env && atoi(env) > 0) ? 1 : 0;
+  }
+  return g_timeline > 0;
+}
+
+void timeline_mark(const char* name, cudaStream_t stream) {
+  if (!timeline_on()) return;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, stream);
+  std::lock_guard<std::mutex> lock(g_tl_mutex);
+  g_marks.push_back({name, ev});
+}
+
 }  // namespace osd
 
 extern "C" int osd_version(void) { return 100; }
@@ -26,6 +60,28 @@ extern "C" const char* osd_last_error(void) { return osd::g_err; }
 extern "C" int64_t osd_launch_count(void) { return osd::g_launches; }
 
 extern "C" void osd_reset_launch_count(void) { osd::g_launches = 0; }
+
+extern "C" void osd_timeline_enable(int on) { osd::g_timeline = on ? 1 : 0; }
+
+extern "C" int osd_timeline_read(char* buf, size_t cap) {
+  using namespace osd;
+  OSD_REQUIRE(buf != nullptr && cap > 0, "osd_timeline_read: null buffer");
+  OSD_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(g_tl_mutex);
+  std::string out;
+  char line[160];
+  for (size_t i = 0; i < g_marks.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_marks[0].ev, g_marks[i].ev);
+    snprintf(line, sizeof(line), "%s %.6f\n", g_marks[i].name, ms);
+    out += line;
+  }
+  for (auto& m : g_marks) cudaEventDestroy(m.ev);
+  const int n = (int)g_marks.size();
+  g_marks.clear();
+  snprintf(buf, cap, "%s", out.c_str());
+  return n;
+}
 
 extern "C" int osd_check_device(void) {
   int dev = 0;

@@ -13,11 +13,28 @@
 namespace cg = cooperative_groups;
 
 namespace osd {
+#ifdef OSD_DEBUG_TS
+__device__ unsigned long long g_sel_ts[8];
+#define OSD_STAMP(k)                                                                       \
+  do {                                                                                     \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == (gridDim.z - 1) && threadIdx.x == 0) { \
+      unsigned long long _t;                                                               \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                               \
+      g_sel_ts[k] = _t;                                                                    \
+    }                                                                                      \
+  } while (0)
+#else
+#define OSD_STAMP(k) do {} while (0)
+#endif
 
 namespace {
 
 constexpr int kCl = 8;              // CTAs per cluster = per (episode, level)
 constexpr int kSelThreads = 256;
+constexpr int kSelLoads = 9;          // loads in flight per thread and array while scoring (9 x 256 >= a 2100-location slice)
+#ifndef OSD_SEL_MINB
+#define OSD_SEL_MINB 5               // <= 48 registers: 5 CTAs per SM next to the matching kernel's CTA
+#endif
 constexpr int kRadixBins = 256;     // radix-select digits: 8 + 8 + 8 + 7 bits (== kSelThreads: thread t owns bin t)
 constexpr int kMaxRounds = 3;       // 63 * 256 locations per round and CTA
 constexpr int kMaxSlice = kMaxRounds * 63 * kSelThreads;   // 48 384 locations per CTA (193 KB of keys)
@@ -84,7 +101,8 @@ __device__ __forceinline__ Decoded decode_clip(float dl, float dt, float dr, flo
 // level in its own shared memory; the radix-select histograms are combined through distributed shared memory
 // (every CTA sums the kCl histograms and runs the same bin search), and the ordered compaction uses the slice
 // totals exchanged the same way.  The P3 level (16 800 locations) is thus worked on by 8 SMs instead of one.
-__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads) fcos_select_kernel(SelectArgs A) {
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads, OSD_SEL_MINB) fcos_select_kernel(SelectArgs A) {
+  OSD_STAMP(0);
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ uint32_t sm_dyn[];
   __shared__ int warp_tot[33];
@@ -106,18 +124,20 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads) fcos_
   const float* __restrict__ ctr = A.ctr[l] + (size_t)e * HW;
   const float* __restrict__ reg = A.reg[l] + (size_t)e * 4 * HW;
 
-  // ---- 1. scores -> order-preserving keys (0 = not a candidate); 4 independent loads in flight per array
+  // ---- 1. scores -> order-preserving keys (0 = not a candidate).  kSelLoads independent loads per array are in flight
+  //         per thread: a P3 slice of the 800x1344 geometry (2100 locations) is fetched in ONE round trip, which is what
+  //         matters when the HBM queues are full of the matching stream's traffic
   int my_cnt = 0;
-  for (int i0 = tid; i0 < nloc; i0 += 4 * kSelThreads) {
-    float xc[4], xt[4];
+  for (int i0 = tid; i0 < nloc; i0 += kSelLoads * kSelThreads) {
+    float xc[kSelLoads], xt[kSelLoads];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kSelLoads; ++u) {
       const int i = i0 + u * kSelThreads;
-      xc[u] = (i < nloc) ? cls[lo + i] : 0.f;
-      xt[u] = (i < nloc) ? ctr[lo + i] : 0.f;
+      xc[u] = (i < nloc) ? __ldg(cls + lo + i) : 0.f;
+      xt[u] = (i < nloc) ? __ldg(ctr + lo + i) : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kSelLoads; ++u) {
       const int i = i0 + u * kSelThreads;
       if (i < nloc) {
         const float p = sigmoidf_precise(xc[u]);
@@ -137,6 +157,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads) fcos_
   for (int rr = 0; rr < kCl; ++rr) cnt += cluster.map_shared_rank(xch, rr)[0];
   const int k = min(cnt, A.top_n);                      // inference.py:75-76
 
+  OSD_STAMP(1);
   // ---- 2. k-th largest key of the whole level by 3-digit radix select (only when the level overflows top_n)
   const bool take_all = (cnt <= k);
   uint32_t T = 1u;   // threshold key
@@ -193,6 +214,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads) fcos_
     need_eq = kk;
   }
 
+  OSD_STAMP(2);
   // ---- 3. decode + clip + size filter + ordered compaction.  Each thread owns a contiguous run of `per`
   //         locations of the slice (per is odd: conflict-free shared-memory reads), so location order is
   //         (CTA rank, thread) order.
@@ -279,6 +301,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads) fcos_
       okm[rd] = ok;
     }
   }
+  OSD_STAMP(3);
   // survivors in the slices of lower-ranked CTAs come first
   if (tid == 0) xch[2] = running;
   cluster.sync();
@@ -304,6 +327,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads) fcos_
     }
   }
   cluster.sync();  // no CTA exits while its shared memory may still be read by a neighbour
+  OSD_STAMP(4);
 }
 
 struct FcosBuffers {
@@ -375,6 +399,12 @@ void carve(const osd_fcos_config* cfg, Carver& c, FcosBuffers* buf, osd_fcos_pla
 }  // namespace
 }  // namespace osd
 
+#ifdef OSD_DEBUG_TS
+extern "C" int osd_debug_select_stamps(unsigned long long* out8) {
+  return (int)cudaMemcpyFromSymbol(out8, osd::g_sel_ts, sizeof(unsigned long long) * 8);
+}
+#endif
+
 extern "C" int osd_fcos_postprocess_plan(const osd_fcos_config* cfg, osd_fcos_plan* plan) {
   OSD_REQUIRE(plan != nullptr, "osd_fcos_postprocess_plan: plan is null");
   int rc = osd::validate(cfg);
@@ -445,10 +475,19 @@ extern "C" int osd_fcos_postprocess(const osd_fcos_config* cfg, const float* con
       configured = cap_bytes;
     }
   }
+  {
+    static thread_local bool carveout_set = false;
+    if (!carveout_set) {
+      OSD_CUDA(prefer_max_shared_carveout(fcos_select_kernel));
+      carveout_set = true;
+    }
+  }
   // cluster of kCl CTAs along x per (level, episode); __cluster_dims__ on the kernel makes <<<>>> launch clusters
   dim3 grid((unsigned)kCl, (unsigned)cfg->num_levels, (unsigned)cfg->batch);
+  timeline_mark("post_begin", stream);
   fcos_select_kernel<<<grid, kSelThreads, smem, stream>>>(A);
   OSD_LAUNCH_CHECK("fcos_select_kernel");
+    timeline_mark("fcos_select_kernel", stream);
 
   CandLayout L{};
   L.boxes = buf.cand_boxes;

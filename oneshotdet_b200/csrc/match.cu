@@ -17,7 +17,13 @@ namespace osd {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kVecPerThread = 4;                     // independent 128-bit loads in flight per thread
+#ifndef OSD_MATCH_VEC
+#define OSD_MATCH_VEC 4
+#endif
+#ifndef OSD_MATCH_MINB
+#define OSD_MATCH_MINB 5
+#endif
+constexpr int kVecPerThread = OSD_MATCH_VEC;         // independent 128-bit loads in flight per thread
 constexpr int kChunkVec = kThreads * kVecPerThread;  // 1024 x 16 B = 16 KB of output per chunk
 
 struct Level {
@@ -34,6 +40,7 @@ struct Level {
 struct Args {
   int nl, B, S, C, Cout, mode;
   uint32_t total_chunks;
+  int l2_evict_first;    // bulk kernel: tag the streamed lines evict-first in L2
   FastDiv div_cout;      // q / Cout (NCHW concat: plane -> episode; NHWC: offset -> pixel)
   Level lv[OSD_MAX_LEVELS];
 };
@@ -95,7 +102,7 @@ __device__ __forceinline__ float nchw_value(const Args& A, const Level& L, uint3
 }
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads, 5) match_nchw_kernel(Args A, FastDiv div_c) {
+__global__ void __launch_bounds__(kThreads, OSD_MATCH_MINB) match_nchw_kernel(Args A, FastDiv div_c) {
   constexpr int N = Vec<T>::N;
   // no shared memory, no barriers: every warp streams independently; the pooled support scalar of a plane is a
   // 4-byte read that stays in L1 (B*C*S values per level)
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 5) match_nchw_kernel(Args A, FastDiv
 // so a vector never leaves its pixel nor its half.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads, 5) match_nhwc_kernel(Args A, FastDiv div_c) {
+__global__ void __launch_bounds__(kThreads, OSD_MATCH_MINB) match_nhwc_kernel(Args A, FastDiv div_c) {
   constexpr int N = Vec<T>::N;
   for (uint32_t chunk = blockIdx.x; chunk < A.total_chunks; chunk += gridDim.x) {
     int li = 0;
@@ -238,6 +245,222 @@ __global__ void __launch_bounds__(kThreads, 5) match_nhwc_kernel(Args A, FastDiv
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Bulk-copy (TMA) variant of the NCHW product: same arithmetic, different data movement.
+// The LSU kernel above needs ~48 K registers per SM to keep 64 KB of loads in flight (4 CTAs x 256 threads), which
+// starves the post-processing chain that runs concurrently on the second stream: its 512/1024-thread CTAs (merge,
+// sweep) cannot become resident until the matching CTAs retire (measured with tools/timeline.py: the chain made no
+// progress behind fcos_select until the match kernel ended).  Here one small CTA per SM streams through a shared
+// memory ring instead: a producer thread issues cp.async.bulk global->shared (16 KB chunks, mbarrier complete_tx),
+// two consumer groups scale their chunk in place and hand it to cp.async.bulk shared->global.  In-flight bytes live
+// in shared memory, so the kernel holds 288 threads x ~40 registers per SM and leaves the rest to the other stream.
+// ---------------------------------------------------------------------------------------------
+#ifndef OSD_BULK_MINB
+#define OSD_BULK_MINB 5      // caps the kernel at 40 registers/thread: the other stream's CTAs need the register file
+#endif
+#ifndef OSD_BULK_BACKOFF_NS
+#define OSD_BULK_BACKOFF_NS 200
+#endif
+#ifndef OSD_BULK_GROUPS
+#define OSD_BULK_GROUPS 2
+#endif
+#ifndef OSD_BULK_SLOTS
+#define OSD_BULK_SLOTS 6     // measured on one box, step / kernel alone: 5: 0.183 / 0.161 ms, 6: 0.181 / 0.145, 7: 0.192 / 0.135,
+#endif                       // 8: 0.204 / 0.136 -- deeper queues make the kernel itself faster and its neighbours slower
+constexpr int kBulkSlots = OSD_BULK_SLOTS;                                  // x 16 KB ring
+constexpr int kBulkGroups = OSD_BULK_GROUPS;
+constexpr int kBulkGroupThreads = 128;
+constexpr int kBulkThreads = 32 + kBulkGroups * kBulkGroupThreads;
+constexpr uint32_t kChunkBytes = kChunkVec * 16;
+constexpr uint32_t kBulkSpinLimit = 1u << 28;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+#ifndef OSD_BULK_NO_BACKOFF
+    __nanosleep(OSD_BULK_BACKOFF_NS);   // waiting warps must not eat the issue slots of the other stream's CTAs on this SM
+#endif
+    if (++spins > kBulkSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+// the same with an L2 eviction policy: the feature stream is touched once, the concurrently running post-processing
+// chain's working set (head outputs, candidates, sort keys, bitmask) should be what stays in L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_load_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_store_hint(void* dst, uint32_t src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               ::"l"(dst), "r"(src), "r"(bytes), "l"(pol) : "memory");
+}
+
+struct ChunkRef {
+  int level;
+  uint32_t v0;      // first vector of the chunk inside the level
+  uint32_t bytes;   // 16 KB, or the level's tail
+};
+
+template <typename T>
+__device__ __forceinline__ ChunkRef locate_chunk(const Args& A, uint32_t chunk) {
+  constexpr int N = Vec<T>::N;
+  int li = 0;
+#pragma unroll
+  for (int k = 1; k < OSD_MAX_LEVELS; ++k)
+    if (k < A.nl && chunk >= A.lv[k].chunk_begin) li = k;
+  ChunkRef c;
+  c.level = li;
+  c.v0 = (chunk - A.lv[li].chunk_begin) * kChunkVec;
+  const uint32_t nvec = A.lv[li].out_elems / N;   // the bulk path requires out_elems % N == 0
+  c.bytes = min((uint32_t)kChunkVec, nvec - c.v0) * 16u;
+  return c;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBulkThreads, OSD_BULK_MINB) match_product_bulk_kernel(Args A, FastDiv div_c) {
+  OSD_TS("match_block0_start");
+  constexpr int N = Vec<T>::N;
+  extern __shared__ __align__(128) uint8_t ring_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kBulkSlots], empty_bar[kBulkSlots];
+  const uint32_t ring = (smem_addr(ring_raw) + 127u) & ~127u;
+  uint8_t* ring_ptr = ring_raw + (ring - smem_addr(ring_raw));
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < kBulkSlots; ++s) {
+      mbar_init(smem_addr(&full_bar[s]), 1);
+      mbar_init(smem_addr(&empty_bar[s]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // this CTA's chunks: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const uint32_t n_my = A.total_chunks > blockIdx.x ? (A.total_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 0) {
+    if (tid == 0) {
+      for (uint32_t i = 0; i < n_my; ++i) {
+        const uint32_t s = i % kBulkSlots;
+        if (i >= (uint32_t)kBulkSlots) mbar_wait(smem_addr(&empty_bar[s]), ((i / kBulkSlots) - 1) & 1);
+        const ChunkRef c = locate_chunk<T>(A, blockIdx.x + i * gridDim.x);
+        const uint32_t bar = smem_addr(&full_bar[s]);
+        mbar_expect_tx(bar, c.bytes);
+        const uint8_t* src = static_cast<const uint8_t*>(A.lv[c.level].feat) + (size_t)c.v0 * 16;
+        if (A.l2_evict_first) bulk_load_hint(ring + s * kChunkBytes, src, c.bytes, bar, l2_evict_first_policy());
+        else bulk_load(ring + s * kChunkBytes, src, c.bytes, bar);
+      }
+    }
+    return;
+  }
+
+  const int g = (warp - 1) / (kBulkGroupThreads / 32);
+  const int t = tid - 32 - g * kBulkGroupThreads;
+  for (uint32_t i = g; i < n_my; i += kBulkGroups) {
+    const uint32_t s = i % kBulkSlots;
+    const ChunkRef c = locate_chunk<T>(A, blockIdx.x + i * gridDim.x);
+    const Level& L = A.lv[c.level];
+    const T* supp = static_cast<const T*>(L.supp);
+    mbar_wait(smem_addr(&full_bar[s]), (i / kBulkSlots) & 1);
+    uint4* slot = reinterpret_cast<uint4*>(ring_ptr + s * kChunkBytes);
+    const uint32_t nv = c.bytes >> 4;
+    const uint32_t e_first = c.v0 * N;
+#ifdef OSD_BULK_NO_FASTPATH
+    if (false) {
+#else
+    if (L.hw >= kChunkVec * N) {
+#endif
+      // large planes (P3, P4: 94 % of the bytes): the chunk touches at most two planes, so the two pooled scalars are
+      // fetched once per chunk and a vector only compares its element range with the plane boundary
+      const uint32_t p0 = fdiv(e_first, L.div_hw);
+      const uint32_t boundary = (p0 + 1) * L.hw;   // first element of the next plane (level-relative index)
+      const float s0 = pooled_at(supp, A.S, A.C, p0, div_c);
+      const float s1 = (boundary < e_first + nv * N) ? pooled_at(supp, A.S, A.C, p0 + 1, div_c) : s0;
+#pragma unroll 8
+      for (uint32_t j = t; j < nv; j += kBulkGroupThreads) {
+        uint4 v = slot[j];
+        const uint32_t e0 = e_first + j * N;
+        T* x = reinterpret_cast<T*>(&v);
+        if (e0 + N <= boundary || e0 >= boundary) {
+          const float sc = (e0 >= boundary) ? s1 : s0;
+#pragma unroll
+          for (int k = 0; k < N; ++k) from_f(x[k], __fmul_rn(to_f(x[k]), sc));
+        } else {
+#pragma unroll
+          for (int k = 0; k < N; ++k) from_f(x[k], __fmul_rn(to_f(x[k]), (e0 + k < boundary) ? s0 : s1));
+        }
+        slot[j] = v;
+      }
+    } else {
+#pragma unroll 4
+      for (uint32_t j = t; j < nv; j += kBulkGroupThreads) {
+        uint4 v = slot[j];
+        const uint32_t e0 = e_first + j * N;
+        const uint32_t p = fdiv(e0, L.div_hw), r = e0 - p * L.hw;
+        const float s0 = pooled_at(supp, A.S, A.C, p, div_c);
+        T* x = reinterpret_cast<T*>(&v);
+        if (r + N <= L.hw) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) from_f(x[k], __fmul_rn(to_f(x[k]), s0));
+        } else {  // the vector runs into the next plane (HW not a multiple of the vector width; HW >= N: one crossing)
+          const float s1 = pooled_at(supp, A.S, A.C, p + 1, div_c);
+#pragma unroll
+          for (int k = 0; k < N; ++k) from_f(x[k], __fmul_rn(to_f(x[k]), (r + k < L.hw) ? s0 : s1));
+        }
+        slot[j] = v;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the bulk store
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(kBulkGroupThreads) : "memory");
+    if (t == 0) {
+      uint8_t* dst = static_cast<uint8_t*>(L.out) + (size_t)c.v0 * 16;
+      if (A.l2_evict_first) bulk_store_hint(dst, ring + s * kChunkBytes, c.bytes, l2_evict_first_policy());
+      else bulk_store(dst, ring + s * kChunkBytes, c.bytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (i >= (uint32_t)kBulkGroups) {   // the group's previous store has finished reading its slot: hand it back
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        mbar_arrive(smem_addr(&empty_bar[(i - kBulkGroups) % kBulkSlots]));
+      }
+    }
+  }
+  if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory stays valid until the stores are done
+  if (tid == 32) OSD_TS_ANY("match_block0_end");
+}
+
+template <typename T>
+bool bulk_eligible(const Args& A) {
+  constexpr int N = Vec<T>::N;
+  for (int l = 0; l < A.nl; ++l)
+    if (A.lv[l].out_elems % N != 0 || A.lv[l].hw < (uint32_t)N) return false;
+  return true;   // feat / out are 16-byte aligned (checked by osd_match_forward)
+}
+
 template <typename T, int MODE>
 int launch(const Args& A, int layout, cudaStream_t stream) {
   const FastDiv div_c = make_fastdiv((uint32_t)A.C);
@@ -254,12 +477,54 @@ int launch(const Args& A, int layout, cudaStream_t stream) {
   int ctas = kNumSMs * per_sm;
   if ((uint32_t)ctas > A.total_chunks) ctas = (int)A.total_chunks;
   if (ctas < 1) return OSD_OK;
+  {
+    static thread_local bool carveout_set = false;   // per <T, MODE> instantiation
+    if (!carveout_set) {
+      OSD_CUDA(prefer_max_shared_carveout(match_product_bulk_kernel<T>));
+      carveout_set = true;
+    }
+  }
+  timeline_mark("match_begin", stream);
+  static int use_bulk = -1;
+  if (use_bulk < 0) {
+    const char* env = getenv("OSD_MATCH_BULK");
+    use_bulk = env ? atoi(env) : 1;
+  }
+  if (MODE == OSD_MATCH_PRODUCT && layout == OSD_LAYOUT_NCHW && use_bulk && bulk_eligible<T>(A)) {
+    const size_t smem = (size_t)kBulkSlots * kChunkBytes + 128;
+    static thread_local bool configured = false;
+    if (!configured) {
+      OSD_CUDA(cudaFuncSetAttribute(match_product_bulk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    static int bulk_ctas = 0;
+    if (bulk_ctas == 0) {
+      const char* env = getenv("OSD_MATCH_BULK_CTAS");
+      bulk_ctas = env ? atoi(env) : kNumSMs;
+      if (bulk_ctas < 1) bulk_ctas = kNumSMs;
+    }
+    int grid = bulk_ctas;
+    if ((uint32_t)grid > A.total_chunks) grid = (int)A.total_chunks;
+    static int l2_hint = -1;
+    if (l2_hint < 0) {
+      const char* env = getenv("OSD_MATCH_L2_EVICT_FIRST");
+      l2_hint = env ? atoi(env) : 1;
+    }
+    Args AB = A;
+    AB.l2_evict_first = l2_hint;
+    match_product_bulk_kernel<T><<<grid, kBulkThreads, smem, stream>>>(AB, div_c);
+    OSD_LAUNCH_CHECK("match_product_bulk_kernel");
+    timeline_mark("match_product_bulk_kernel", stream);
+    return OSD_OK;
+  }
   if (layout == OSD_LAYOUT_NCHW) {
     match_nchw_kernel<T, MODE><<<ctas, kThreads, 0, stream>>>(A, div_c);
     OSD_LAUNCH_CHECK("match_nchw_kernel");
+    timeline_mark("match_nchw_kernel", stream);
   } else {
     match_nhwc_kernel<T, MODE><<<ctas, kThreads, 0, stream>>>(A, div_c);
     OSD_LAUNCH_CHECK("match_nhwc_kernel");
+    timeline_mark("match_nhwc_kernel", stream);
   }
   return OSD_OK;
 }

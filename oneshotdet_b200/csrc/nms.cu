@@ -120,6 +120,7 @@ __device__ __forceinline__ u64 shfl_xor_u64(u64 v, int lane_mask) {
 }
 
 __global__ void __launch_bounds__(kChunkThreads) nms_chunk_sort_kernel(CandLayout L, NmsWorkspace W) {
+  OSD_TS("sort_block0_start");
   __shared__ u64 sk[kChunk];
   __shared__ int lvl_prefix[OSD_MAX_LEVELS + 1];
   const int e = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
@@ -222,6 +223,7 @@ __device__ __forceinline__ int count_less(const u64* __restrict__ run, int len2,
 }
 
 __global__ void __launch_bounds__(kMergeThreads) nms_merge_kernel(CandLayout L, NmsWorkspace W) {
+  OSD_TS("merge_block0_start");
   extern __shared__ u64 staged[];  // up to kMergeStage sorted keys of the other chunks
   __shared__ int lvl_prefix[OSD_MAX_LEVELS + 1];
   const int e = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
@@ -776,6 +778,16 @@ size_t nms_workspace_carve(Carver& c, int64_t E, int64_t max_len, NmsWorkspace* 
 
 int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, const NmsOutputs& O,
             cudaStream_t stream) {
+  {
+    static thread_local bool carveout_set = false;
+    if (!carveout_set) {
+      OSD_CUDA(prefer_max_shared_carveout(nms_chunk_sort_kernel));
+      OSD_CUDA(prefer_max_shared_carveout(nms_merge_kernel));
+      OSD_CUDA(prefer_max_shared_carveout(nms_mask_kernel));
+      OSD_CUDA(prefer_max_shared_carveout(nms_sweep_kernel));
+      carveout_set = true;
+    }
+  }
   const int E = W.E;
   if (E <= 0) return OSD_OK;
   const int max_len = P.max_len;
@@ -787,6 +799,7 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
     dim3 g((unsigned)ceil_div(max_len > 0 ? max_len : 1, kChunk), (unsigned)E);
     nms_chunk_sort_kernel<<<g, kChunkThreads, 0, stream>>>(L, W);
     OSD_LAUNCH_CHECK("nms_chunk_sort_kernel");
+    timeline_mark("nms_chunk_sort_kernel", stream);
     const size_t merge_smem = (size_t)std::min<int64_t>(kMergeStage, (int64_t)align_up((size_t)(max_len > 0 ? max_len : 1), kChunk)) * sizeof(u64);
     static thread_local bool merge_configured = false;
     if (!merge_configured) {
@@ -796,6 +809,7 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
     }
     nms_merge_kernel<<<g, kMergeThreads, merge_smem, stream>>>(L, W);
     OSD_LAUNCH_CHECK("nms_merge_kernel");
+    timeline_mark("nms_merge_kernel", stream);
   }
 
   // ---- mask + sweep, in passes over growing prefixes of the visiting order.  Without early exit there is one
@@ -821,6 +835,7 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
     S.stop = INT_MAX;
     nms_sweep_kernel<<<E, kSweepThreads, sweep_smem, stream>>>(L, W, O, S);
     OSD_LAUNCH_CHECK("nms_sweep_kernel");
+    timeline_mark("nms_sweep_kernel", stream);
   } else {
     MaskArgs M{};
     M.test.thr = P.thr;
@@ -855,10 +870,12 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
       const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * 12);
       nms_mask_kernel<<<grid, kMaskRows, 0, stream>>>(W, M);
       OSD_LAUNCH_CHECK("nms_mask_kernel");
+    timeline_mark("nms_mask_kernel", stream);
       S.blk_begin = prev / 64;
       S.blk_end = hi / 64;
       nms_sweep_kernel<<<E, kSweepThreads, sweep_smem, stream>>>(L, W, O, S);
       OSD_LAUNCH_CHECK("nms_sweep_kernel");
+    timeline_mark("nms_sweep_kernel", stream);
       prev = hi;
     }
   }

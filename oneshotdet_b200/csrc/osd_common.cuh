@@ -14,6 +14,8 @@ namespace osd {
 // ---- host-side error plumbing ---------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+bool timeline_on();
+void timeline_mark(const char* name, cudaStream_t stream);  // no-op unless OSD_TIMELINE=1 / osd_timeline_enable(1)
 
 #define OSD_REQUIRE(cond, ...)            \
   do {                                    \
@@ -47,6 +49,16 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// Every kernel of the two concurrently running streams (matching || post-processing) asks for the same shared
+// memory carve-out.  The L1/shared split is per-SM state: a CTA whose kernel needs a different split cannot become
+// resident on an SM until the CTAs already there have drained -- which, next to a persistent kernel, means "after it
+// ends" (measured: the post-processing chain did not start until the matching kernel finished).
+template <typename K>
+inline cudaError_t prefer_max_shared_carveout(K kernel) {
+  return cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout,
+                              (int)cudaSharedmemCarveoutMaxShared);
+}
 
 // Bump allocator over a caller-provided workspace (256-byte aligned slices).
 struct Carver {
