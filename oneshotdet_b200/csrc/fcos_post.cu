@@ -108,9 +108,9 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads, OSD_S
   __shared__ int warp_tot[33];
   __shared__ int xch[4];   // read by the other CTAs of the cluster: [0] candidates, [1] equal keys, [2] survivors
   __shared__ int s_bin, s_kk, s_eq;
-  int* hist = reinterpret_cast<int*>(sm_dyn);               // [kRadixBins] this CTA's histogram
-  int* red = reinterpret_cast<int*>(sm_dyn) + kRadixBins;   // [kRadixBins] cluster-wide histogram
-  uint32_t* keys = sm_dyn + 2 * kRadixBins;                 // [slice]
+  int* hist0 = reinterpret_cast<int*>(sm_dyn);                  // [2][kRadixBins] this CTA's histograms (ping-pong)
+  int* red = reinterpret_cast<int*>(sm_dyn) + 2 * kRadixBins;   // [kRadixBins] cluster-wide histogram
+  uint32_t* keys = sm_dyn + 3 * kRadixBins;                     // [slice]
 
   const int r = (int)cluster.block_rank();
   const int l = blockIdx.y, e = blockIdx.z, tid = threadIdx.x;
@@ -176,6 +176,10 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads, OSD_S
     for (int pass = 0; pass < 4; ++pass) {
       const int sh = shifts[pass];
       const uint32_t dm = (1u << widths[pass]) - 1u;
+      // ping-pong histograms: the buffer zeroed here was last read by the neighbours two passes ago, and this CTA is
+      // past the cluster barrier of the previous pass, which they only reach after those reads -- so one cluster
+      // barrier per pass is enough (cluster barriers are what slows down next to the matching stream)
+      int* hist = hist0 + (pass & 1) * kRadixBins;
       hist[tid] = 0;   // kRadixBins == kSelThreads
       __syncthreads();
       for (int i0 = 0; i0 < nloc; i0 += kSelThreads) {
@@ -208,7 +212,6 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads, OSD_S
       pmask |= dm << sh;
       kk = s_kk;
       eq_total = s_eq;   // after the last pass: number of keys equal to the threshold key
-      cluster.sync();    // nobody still reads this CTA's histogram (it is zeroed next)
     }
     T = prefix;
     need_eq = kk;
@@ -466,11 +469,11 @@ extern "C" int osd_fcos_postprocess(const osd_fcos_config* cfg, const float* con
   A.cand_loc = buf.cand_loc;
   A.level_count = buf.level_count;
 
-  const size_t smem = (size_t)2 * kRadixBins * sizeof(int) + (size_t)max_slice * sizeof(uint32_t);
+  const size_t smem = (size_t)3 * kRadixBins * sizeof(int) + (size_t)max_slice * sizeof(uint32_t);
   {
     static thread_local size_t configured = 48 * 1024;
     if (smem > configured) {
-      const size_t cap_bytes = (size_t)2 * kRadixBins * sizeof(int) + (size_t)kMaxSlice * sizeof(uint32_t);
+      const size_t cap_bytes = (size_t)3 * kRadixBins * sizeof(int) + (size_t)kMaxSlice * sizeof(uint32_t);
       OSD_CUDA(cudaFuncSetAttribute(fcos_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap_bytes));
       configured = cap_bytes;
     }
