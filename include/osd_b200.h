@@ -343,6 +343,28 @@ typedef struct {
 int osd_roi_pool_workspace_bytes(const osd_roi_pool_desc* desc, size_t* bytes);
 int osd_roi_pool(const osd_roi_pool_desc* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Result hand-off: detections -> COCO detection records -> the reference's JSON file.  SURVEY section 8(f) row 4.
+ *
+ * Replaces  the per-image body of prepare_for_coco_detection
+ *           (maskrcnn_benchmark/data/datasets/evaluation/coco/coco_eval.py:137-156): BoxList.resize to the original
+ *           image size (structures/bounding_box.py:91-127), convert("xywh") (:55-73), tolist(), one dict per box;
+ *           and the json.dump(..., sort_keys=True, indent=4, separators=(',', ':')) of :163-165.
+ * osd_coco_records (device): boxes [E,K,4] / scores [E,K] / count [E] as osd_fcos_postprocess / osd_box_postprocess
+ * emit them; det_wh [E,2] = the (w, h) the detections live in; orig_wh [E,2] = (width, height) of img_info.  Writes
+ * records [sum count, 5] = (x, y, w, h, score), episode-major in detection order, record_episode [sum count], total [1].
+ * osd_coco_write_json (host, no GPU): records on the HOST; writes exactly the bytes CPython's json.dump writes for the
+ * reference's list of dicts {"bbox": [x, y, w, h], "category_id": c, "image_id": i, "score": s}.
+ * ---------------------------------------------------------------------------------------------- */
+int osd_coco_records(const float* boxes, const float* scores, const int32_t* count,
+                     const int32_t* det_wh, const int32_t* orig_wh,
+                     int32_t num_episodes, int32_t rows_per_episode,
+                     float* records, int32_t* record_episode, int32_t* total, void* stream);
+
+int osd_coco_write_json(const float* records, const int32_t* record_episode, int64_t num_records,
+                        const int64_t* image_ids, const int64_t* category_ids, int32_t num_episodes,
+                        const char* path);
+
 #ifdef __cplusplus
 }
 #endif

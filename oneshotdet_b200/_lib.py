@@ -113,6 +113,10 @@ SYMBOLS = {
     "osd_support_pool": (ctypes.c_int, [ctypes.POINTER(SupportPoolDesc), c_void_p]),
     "osd_roi_pool": (ctypes.c_int, [ctypes.POINTER(RoiPoolDesc), c_void_p]),
     "osd_roi_pool_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(RoiPoolDesc), ctypes.POINTER(ctypes.c_size_t)]),
+    "osd_coco_records": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "osd_coco_write_json": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, ctypes.c_int32,
+                                           ctypes.c_char_p]),
     "osd_box_postprocess_plan": (ctypes.c_int, [ctypes.POINTER(BoxPostConfig), ctypes.POINTER(BoxPostPlan)]),
     "osd_box_postprocess": (ctypes.c_int, [ctypes.POINTER(BoxPostConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, ctypes.c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -17,6 +17,9 @@ What is executed (paths relative to /root/reference):
 
   * modeling/poolers.py:93-125 with layers/roi_align.py  Pooler.forward + LevelMapper                         -> pooler_*.npz
 
+  * structures/bounding_box.py:55-127 (BoxList.resize / convert) inside the loop body of
+    data/datasets/evaluation/coco/coco_eval.py:137-165                                                      -> coco_*.npz
+
 Inputs are seeded numpy; they are stored next to the outputs so tests never need the reference.
 """
 from __future__ import annotations
@@ -237,11 +240,56 @@ def pooler_cases():
     pooler_case("r3_adaptive", 1, 32, 4, 384, 384, [(384, 384)], seed=73, resolution=3, sampling=0)
 
 
+def coco_case(name, image_sizes_wh, orig_sizes_wh, counts, seed):
+    """The per-image body of prepare_for_coco_detection (data/datasets/evaluation/coco/coco_eval.py:137-156) with the
+    reference's own BoxList.resize / convert executed, and the json.dump of :163-165.  (The function itself needs
+    pycocotools and a dataset on disk; its dataset bookkeeping is not part of the hand-off format.)"""
+    import json  # noqa: PLC0415
+
+    from maskrcnn_benchmark.structures.bounding_box import BoxList  # noqa: PLC0415
+
+    rng = np.random.RandomState(seed)
+    coco_results = []
+    data = {"image_sizes_wh": np.asarray(image_sizes_wh, dtype=np.int64), "orig_sizes_wh": np.asarray(orig_sizes_wh, dtype=np.int64),
+            "counts": np.asarray(counts, dtype=np.int64), "seed": seed}
+    cats = [int(c) for c in rng.randint(1, 21, len(counts))]
+    data["category_ids"] = np.asarray(cats, dtype=np.int64)
+    for image_id, ((w, h), (ow, oh), n) in enumerate(zip(image_sizes_wh, orig_sizes_wh, counts)):
+        x1 = rng.uniform(0, w - 2, n); y1 = rng.uniform(0, h - 2, n)
+        x2 = np.minimum(x1 + rng.uniform(1, w / 2, n), w - 1); y2 = np.minimum(y1 + rng.uniform(1, h / 2, n), h - 1)
+        boxes = np.stack([x1, y1, x2, y2], 1).astype(np.float32)
+        scores = rng.uniform(0, 1, n).astype(np.float32) ** 3
+        data[f"boxes{image_id}"], data[f"scores{image_id}"] = boxes, scores
+        prediction = BoxList(torch.from_numpy(boxes.copy()), (w, h), mode="xyxy")
+        prediction.add_field("scores", torch.from_numpy(scores.copy()))
+        if len(prediction) == 0:
+            continue
+        prediction = prediction.resize((ow, oh))
+        prediction = prediction.convert("xywh")
+        bl = prediction.bbox.tolist()
+        sl = prediction.get_field("scores").tolist()
+        coco_results.extend([{"image_id": image_id, "category_id": cats[image_id], "bbox": box, "score": sl[k]}
+                             for k, box in enumerate(bl)])
+    text = json.dumps(coco_results, sort_keys=True, indent=4, separators=(',', ':'))
+    data["json"] = np.frombuffer(text.encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, f"coco_{name}.npz"), **data)
+    print(f"coco_{name}.npz:", len(coco_results), "records,", len(text), "bytes of JSON")
+
+
+def coco_cases():
+    # equal ratios (one factor), unequal ratios, an empty image, an upscale
+    coco_case("mixed", [(1333, 800), (1066, 800), (800, 800), (640, 480)], [(500, 300), (500, 375), (400, 400), (1280, 961)],
+              [40, 25, 0, 30], seed=91)
+
+
 def main():
     torch.set_num_threads(1)
     ref_c = import_reference()
     if "--only-box-post" in sys.argv:
         box_post_cases()
+        return
+    if "--only-coco" in sys.argv:
+        coco_cases()
         return
     if "--only-pooler" in sys.argv:
         pooler_cases()
@@ -257,6 +305,7 @@ def main():
     match_case("s3_c64", 2, 3, 64, 64, 96, seed=22)
     box_post_cases()
     pooler_cases()
+    coco_cases()
 
 
 if __name__ == "__main__":
