@@ -252,7 +252,9 @@ def run_b200_arm(args):
             print(f"[bench] CUDA-graph capture failed ({exc}); launching eagerly", file=sys.stderr)
             torch.cuda.synchronize()
 
-    gatherer = DetectionGatherer(BATCH, pipe.post.plan.out_capacity, dev, ep_off) if world > 1 else None
+    # detections are gathered in groups of `--gather-every` steps (the reference gathers once, after the whole dataset)
+    gatherer = (DetectionGatherer(BATCH, pipe.post.plan.out_capacity, dev, ep_off, steps_per_gather=args.gather_every)
+                if world > 1 else None)
 
     def step():
         res = step_fn()
@@ -429,6 +431,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fusion", action="store_true")
     ap.add_argument("--serial", action="store_true", help="one stream: matching then post-processing, no overlap")
+    ap.add_argument("--gather-every", type=int, default=10,
+                    help="N>1: steps per NCCL all-gather of the detections (1 = every step)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -44,46 +44,66 @@ def unpack_detections(dets: torch.Tensor, counts: torch.Tensor, num_episodes: in
 
 
 class DetectionGatherer:
-    """Double-buffered, asynchronous gather of the per-step detections: the step's results are snapshotted into a
-    packed payload [E_local, K + 1, 6] (rows 0..K-1: x1, y1, x2, y2, score, global episode id; row K: the count in
-    column 0) and ONE all_gather_into_tensor is issued with async_op=True, so NCCL moves batch i over NVLink while
-    the kernels of batch i+1 already run.  ``submit`` waits for the gather issued two steps earlier before reusing its
-    buffers; ``finish`` drains everything."""
+    """Double-buffered, asynchronous gather of the detections: every step's results are snapshotted into a packed
+    payload [E_local, K + 1, 6] (rows 0..K-1: x1, y1, x2, y2, score, global episode id; row K: the count in column 0);
+    ``steps_per_gather`` consecutive payloads form one group, and ONE all_gather_into_tensor per group is issued with
+    async_op=True, so NCCL moves group g over NVLink while the kernels of group g+1 already run.  The reference gathers
+    once, after the whole dataset (engine/inference.py:133-152); ``steps_per_gather=1`` gathers every step (lowest
+    latency to the consumer), larger groups amortise the collective's launch cost (scaling measurements in DESIGN
+    section 7).  ``submit`` waits for the gather issued two groups earlier before reusing its buffers; ``finish`` issues
+    the gather of a partially filled group and drains everything."""
 
-    def __init__(self, e_local: int, k: int, device, episode_offset: int = 0, group=None):
+    def __init__(self, e_local: int, k: int, device, episode_offset: int = 0, group=None, steps_per_gather: int = 1):
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-        self.e, self.k = e_local, k
+        self.e, self.k, self.m = e_local, k, max(1, int(steps_per_gather))
         self.payload, self.out, self.work = [], [], [None, None]
         for _ in range(2):
-            p = torch.zeros((e_local, k + 1, 6), dtype=torch.float32, device=device)
-            p[:, :k, 5] = torch.arange(episode_offset, episode_offset + e_local, device=device, dtype=torch.float32).view(-1, 1)
+            p = torch.zeros((self.m, e_local, k + 1, 6), dtype=torch.float32, device=device)
+            p[:, :, :k, 5] = torch.arange(episode_offset, episode_offset + e_local, device=device,
+                                          dtype=torch.float32).view(1, -1, 1)
             self.payload.append(p)
-            self.out.append(torch.empty((self.world * e_local, k + 1, 6), dtype=torch.float32, device=device))
-        self.i = 0
+            self.out.append(torch.empty((self.world * self.m, e_local, k + 1, 6), dtype=torch.float32, device=device))
+        self.i = 0           # steps submitted
+        self.filled = [0, 0]  # steps of the group currently held by each slot
+
+    def _issue(self, slot):
+        if self.world > 1:
+            self.work[slot] = dist.all_gather_into_tensor(self.out[slot], self.payload[slot], group=self.group, async_op=True)
+        else:
+            self.out[slot].copy_(self.payload[slot])
 
     def submit(self, boxes, scores, count):
-        slot = self.i & 1
+        """Snapshot one step; returns (slot, row) of the group buffer that will hold it after the gather."""
+        g, row = divmod(self.i, self.m)
+        slot = g & 1
         self.i += 1
-        if self.work[slot] is not None:
-            self.work[slot].wait()
-        p = self.payload[slot]
+        if row == 0:
+            if self.work[slot] is not None:   # the gather issued two groups ago still reads this slot's payload
+                self.work[slot].wait()
+                self.work[slot] = None
+            self.filled[slot] = 0
+        p = self.payload[slot][row]
         p[:, :self.k, :4].copy_(boxes)
         p[:, :self.k, 4].copy_(scores)
         p[:, self.k, 0].copy_(count)
-        if self.world > 1:
-            self.work[slot] = dist.all_gather_into_tensor(self.out[slot], p, group=self.group, async_op=True)
-        else:
-            self.out[slot].copy_(p)
-        return slot
+        self.filled[slot] = row + 1
+        if row == self.m - 1:
+            self._issue(slot)
+        return slot, row
 
     def finish(self):
-        for w in self.work:
+        g, row = divmod(self.i, self.m)
+        if row != 0:                  # a partially filled group: gather what is there (stale rows are ignored by result())
+            self._issue(g & 1)
+            self.i = (g + 1) * self.m
+        for j, w in enumerate(self.work):
             if w is not None:
                 w.wait()
         self.work = [None, None]
 
-    def result(self, slot):
-        """(dets [E_total, K, 6], counts int32 [E_total]) of a finished slot."""
-        o = self.out[slot]
+    def result(self, slot, row: int = 0):
+        """(dets [E_total, K, 6], counts int32 [E_total]) of step ``row`` of a finished group ``slot``; episodes are in
+        rank order (rank r owns the contiguous block r of the batch, see shard_range)."""
+        o = self.out[slot].view(self.world, self.m, self.e, self.k + 1, 6)[:, row].reshape(self.world * self.e, self.k + 1, 6)
         return o[:, :self.k], o[:, self.k, 0].to(torch.int32)

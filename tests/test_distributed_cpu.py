@@ -88,27 +88,31 @@ def _gatherer_worker(rank, world, port, q):
         from oneshotdet_b200.distributed import DetectionGatherer
 
         e, k = 3, 4
-        g = DetectionGatherer(e, k, torch.device("cpu"), episode_offset=rank * e)
         ok = True
-        slots = []
-        for step in range(5):   # more steps than buffers: exercises the reuse wait
-            gen = torch.Generator().manual_seed(100 * step + rank)
-            boxes = torch.rand(e, k, 4, generator=gen)
-            scores = torch.rand(e, k, generator=gen)
-            count = torch.randint(0, k + 1, (e,), generator=gen, dtype=torch.int32)
-            slots.append((g.submit(boxes, scores, count), step))
-        g.finish()
-        slot, step = slots[-1]
-        dets, counts = g.result(slot)
-        for r in range(world):
+
+        def synth(step, r):
             gen = torch.Generator().manual_seed(100 * step + r)
-            boxes = torch.rand(e, k, 4, generator=gen)
-            scores = torch.rand(e, k, generator=gen)
-            count = torch.randint(0, k + 1, (e,), generator=gen, dtype=torch.int32)
-            blk = dets[r * e:(r + 1) * e]
-            ok = ok and torch.equal(blk[..., :4], boxes) and torch.equal(blk[..., 4], scores)
-            ok = ok and torch.equal(counts[r * e:(r + 1) * e], count)
-            ok = ok and blk[:, 0, 5].tolist() == [float(r * e + i) for i in range(e)]
+            return (torch.rand(e, k, 4, generator=gen), torch.rand(e, k, generator=gen),
+                    torch.randint(0, k + 1, (e,), generator=gen, dtype=torch.int32))
+
+        # per-step gathers (5 steps > 2 buffers: exercises the reuse wait), then groups of 3 with a partial last group
+        for m, steps in ((1, 5), (3, 8)):
+            g = DetectionGatherer(e, k, torch.device("cpu"), episode_offset=rank * e, steps_per_gather=m)
+            where = [g.submit(*synth(step, rank)) for step in range(steps)]
+            g.finish()
+            last_group = (steps - 1) // m
+            for step in range(steps):
+                if step // m < last_group - 1:
+                    continue                     # that group's buffers have been reused since
+                slot, row = where[step]
+                assert (slot, row) == ((step // m) & 1, step % m)
+                dets, counts = g.result(slot, row)
+                for r in range(world):
+                    boxes, scores, count = synth(step, r)
+                    blk = dets[r * e:(r + 1) * e]
+                    ok = ok and torch.equal(blk[..., :4], boxes) and torch.equal(blk[..., 4], scores)
+                    ok = ok and torch.equal(counts[r * e:(r + 1) * e], count)
+                    ok = ok and blk[:, 0, 5].tolist() == [float(r * e + i) for i in range(e)]
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
