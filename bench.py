@@ -8,7 +8,8 @@ siamese FCOS R-50-FPN geometry, 800x1333 target padded to 800x1344, C=256, 1 sho
 parameters 0 / 6000 / 0.8 / 2000): the product matching of P3-P7 (one launch), then score -> per-level top-k ->
 decode/clip -> batched NMS -> post-NMS top-n.  The FCOS head between the two stages is outside the path: head
 outputs are synthetic and resident.  With N > 1 every rank owns 16 episodes (weak scaling) and
-each step ends with the all-gather of the [16, 2000, 6] detections over NCCL.
+every step's detections (the post-processing stage's result block: boxes, scores, indices, counts) go to all ranks
+with one asynchronous NCCL all-gather that overlaps the next step (--gather packed: [16, 2001, 6] payloads in groups).
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same metric through
 EpisodePipeline.run_host with pinned HOST buffers (H2D of all inputs + D2H of the detections inside the timed
@@ -219,7 +220,7 @@ def run_b200_arm(args):
     import torch.distributed as dist
 
     from oneshotdet_b200 import ops
-    from oneshotdet_b200.distributed import DetectionGatherer
+    from oneshotdet_b200.distributed import BlockGatherer, DetectionGatherer
     from oneshotdet_b200.pipeline import EpisodePipeline, PostParams
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,7 +238,8 @@ def run_b200_arm(args):
     steps = args.steps
 
     pipe = EpisodePipeline(BATCH, HEIGHT, WIDTH, [IMAGE_SIZE] * BATCH, channels=CHANNELS, shots=SHOTS,
-                           params=PostParams(**PARAMS), match_mode="product", device=dev)
+                           params=PostParams(**PARAMS), match_mode="product", device=dev,
+                           double_buffer=(world > 1 and args.gather == "block"))
     fill_inputs(pipe, seed=2000 + rank)
     ep_off = rank * BATCH
 
@@ -252,14 +254,24 @@ def run_b200_arm(args):
             print(f"[bench] CUDA-graph capture failed ({exc}); launching eagerly", file=sys.stderr)
             torch.cuda.synchronize()
 
-    # detections are gathered in groups of `--gather-every` steps (the reference gathers once, after the whole dataset)
-    gatherer = (DetectionGatherer(BATCH, pipe.post.plan.out_capacity, dev, ep_off, steps_per_gather=args.gather_every)
-                if world > 1 else None)
+    # N > 1: the step's detections go to every rank with one asynchronous NCCL all-gather.  "block" (default): the
+    # post-processing outputs of a step are one contiguous result block in a double-buffered pipeline and that block is
+    # gathered as is, every step, without packing kernels.  "packed": [E, K+1, 6] payloads packed by copy kernels and
+    # gathered in groups of --gather-every steps (the reference gathers once, after the whole dataset).
+    gatherer = None
+    if world > 1:
+        if args.gather == "block":
+            gatherer = BlockGatherer(BATCH, pipe.post.plan.out_capacity, dev)
+        else:
+            gatherer = DetectionGatherer(BATCH, pipe.post.plan.out_capacity, dev, ep_off, steps_per_gather=args.gather_every)
 
     def step():
         res = step_fn()
-        if gatherer is not None:   # snapshot + asynchronous NCCL all-gather, overlapped with the next step
-            gatherer.submit(res.boxes, res.scores, res.count)
+        if gatherer is not None:   # asynchronous: NCCL moves step i over NVLink while step i+1 computes
+            if args.gather == "block":
+                gatherer.submit(res.block)
+            else:
+                gatherer.submit(res.boxes, res.scores, res.count)
         return res
 
     for _ in range(warmup):
@@ -431,6 +443,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fusion", action="store_true")
     ap.add_argument("--serial", action="store_true", help="one stream: matching then post-processing, no overlap")
+    ap.add_argument("--gather", choices=["block", "packed"], default="block",
+                    help="N>1: gather the step's result block as is (default) or pack [E,K+1,6] payloads")
     ap.add_argument("--gather-every", type=int, default=10,
                     help="N>1: steps per NCCL all-gather of the detections (1 = every step)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")

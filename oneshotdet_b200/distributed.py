@@ -102,8 +102,54 @@ class DetectionGatherer:
                 w.wait()
         self.work = [None, None]
 
-    def result(self, slot, row: int = 0):
+    def result(self, slot, row: int = 0):  # noqa: D401  (packed-payload mode)
         """(dets [E_total, K, 6], counts int32 [E_total]) of step ``row`` of a finished group ``slot``; episodes are in
         rank order (rank r owns the contiguous block r of the batch, see shard_range)."""
         o = self.out[slot].view(self.world, self.m, self.e, self.k + 1, 6)[:, row].reshape(self.world * self.e, self.k + 1, 6)
         return o[:, :self.k], o[:, self.k, 0].to(torch.int32)
+
+
+class BlockGatherer:
+    """Copy-free variant for a double-buffered pipeline (``EpisodePipeline(double_buffer=True)``): the post-processing
+    stage writes boxes | scores | index | count of a step into ONE result block (``FcosResult.block``), and that block is
+    what goes over NVLink -- no packing kernels.  ``submit(block)`` issues one asynchronous ``all_gather_into_tensor`` of
+    the block; before issuing it makes the current stream wait for the gather two steps back, whose source block the next
+    step will overwrite.  ``result(slot)`` returns the (boxes, scores, index, count) views of every rank's block."""
+
+    def __init__(self, e_local: int, k: int, device, group=None):
+        from . import ops
+
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.e, self.k = e_local, k
+        _, self.block_bytes = ops.result_block_layout(e_local, k)
+        self.out = [torch.empty((self.world * self.block_bytes,), dtype=torch.uint8, device=device) for _ in range(2)]
+        self.work = [None, None]
+        self.i = 0
+
+    def submit(self, block):
+        slot = self.i & 1
+        self.i += 1
+        if self.work[slot] is not None:
+            self.work[slot].wait()          # stream-side wait: the block written two steps ago has been shipped
+            self.work[slot] = None
+        if block.numel() != self.block_bytes:
+            raise ValueError(f"result block of {block.numel()} bytes, expected {self.block_bytes}")
+        if self.world > 1:
+            self.work[slot] = dist.all_gather_into_tensor(self.out[slot], block, group=self.group, async_op=True)
+        else:
+            self.out[slot].copy_(block)
+        return slot
+
+    def finish(self):
+        for w in self.work:
+            if w is not None:
+                w.wait()
+        self.work = [None, None]
+
+    def result(self, slot):
+        """List over ranks of (boxes [E,K,4], scores [E,K], index [E,K], count [E]) views of the gathered blocks."""
+        from . import ops
+
+        blocks = self.out[slot].view(self.world, self.block_bytes)
+        return [ops.result_block(self.e, self.k, blocks.device, blocks[r])[1] for r in range(self.world)]

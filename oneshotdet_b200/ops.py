@@ -114,6 +114,7 @@ class FcosResult:
     count: torch.Tensor        # [B] int32 valid rows per episode
     plan: FcosPlan
     workspace: torch.Tensor    # keeps the intermediates alive for inspection
+    block: torch.Tensor = None  # uint8: the ONE allocation boxes | scores | index | count are views of (multi-GPU payload)
 
     def _view(self, off, dtype, shape):
         n = 1
@@ -138,6 +139,29 @@ class FcosResult:
         return self._view(self.plan.off_kept_count, torch.int32, (self.boxes.size(0),))
 
     num_levels: int = 0
+
+
+def result_block_layout(b: int, k: int):
+    """Byte offsets of boxes fp32 [b,k,4] | scores fp32 [b,k] | index int32 [b,k] | count int32 [b] inside a result block
+    (each part 256-byte aligned) and the block size."""
+    def up(x):
+        return (x + 255) // 256 * 256
+    o_boxes = 0
+    o_scores = up(o_boxes + b * k * 16)
+    o_index = up(o_scores + b * k * 4)
+    o_count = up(o_index + b * k * 4)
+    return (o_boxes, o_scores, o_index, o_count), up(o_count + b * 4)
+
+
+def result_block(b: int, k: int, device, block: torch.Tensor | None = None):
+    """(block uint8, (boxes, scores, index, count) views).  ``block`` given: views of an existing (e.g. gathered) block."""
+    (o_boxes, o_scores, o_index, o_count), size = result_block_layout(b, k)
+    if block is None:
+        block = torch.zeros(size, dtype=torch.uint8, device=device)
+    def view(off, nbytes, dtype, shape):
+        return block[off:off + nbytes].view(dtype).view(*shape)
+    return block, (view(o_boxes, b * k * 16, torch.float32, (b, k, 4)), view(o_scores, b * k * 4, torch.float32, (b, k)),
+                   view(o_index, b * k * 4, torch.int32, (b, k)), view(o_count, b * 4, torch.int32, (b,)))
 
 
 def fcos_config(level_shapes, strides, batch, pre_nms_thresh, pre_nms_top_n, nms_thresh, post_nms_top_n, min_size,
@@ -202,17 +226,16 @@ class PreparedFcos:
             raise OsdError(f"fcos_postprocess: {b} episodes but {hw.numel() // 2} image sizes")
         self.hw = hw
         k = self.plan.out_capacity
-        out_boxes = torch.empty((b, k, 4), dtype=torch.float32, device=dev)
-        out_scores = torch.empty((b, k), dtype=torch.float32, device=dev)
-        out_index = torch.empty((b, k), dtype=torch.int32, device=dev)
-        out_count = torch.zeros((b,), dtype=torch.int32, device=dev)
+        # one allocation for the four outputs, so that a multi-GPU gather can ship the step's result as a single buffer
+        block, (out_boxes, out_scores, out_index, out_count) = result_block(b, k, dev)
         if workspace is not None:
             ws = workspace
         elif private_workspace:  # results (candidates, kept counts) survive unrelated calls
             ws = torch.empty(self.plan.workspace_bytes, dtype=torch.uint8, device=dev)
         else:
             ws = _workspace.get(dev, self.plan.workspace_bytes)
-        self.result = FcosResult(out_boxes, out_scores, out_index, out_count, self.plan, ws, num_levels=len(shapes))
+        self.result = FcosResult(out_boxes, out_scores, out_index, out_count, self.plan, ws, num_levels=len(shapes),
+                                 block=block)
         nl = len(shapes)
         arr = ctypes.c_void_p * nl
         self._cls = arr(*[c.data_ptr() for c in self.cls])

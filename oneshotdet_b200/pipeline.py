@@ -35,7 +35,8 @@ class PostParams:
 class EpisodePipeline:
     def __init__(self, batch: int, height: int, width: int, image_sizes, channels: int = 256, shots: int = 1,
                  strides=FPN_STRIDES, params: PostParams | None = None, match_mode: str = "product",
-                 device="cuda", dtype=torch.float32, early_exit: bool = True, strict_iou: bool = False):
+                 device="cuda", dtype=torch.float32, early_exit: bool = True, strict_iou: bool = False,
+                 double_buffer: bool = False):
         self.device = torch.device(device)
         self.batch, self.channels, self.shots = batch, channels, shots
         self.params = params or PostParams()
@@ -54,6 +55,15 @@ class EpisodePipeline:
         self.post = ops.PreparedFcos(self.cls, self.reg, self.ctr, self.strides, image_sizes, p.pre_nms_thresh,
                                      p.pre_nms_top_n, p.nms_thresh, p.fpn_post_nms_top_n, p.min_size, strict_iou,
                                      early_exit, private_workspace=True)
+        # double_buffer: a second set of OUTPUT tensors (same inputs, same workspace -- steps are stream-ordered);
+        # consecutive steps alternate between the two, so a consumer (the multi-GPU gather) can still read step i while
+        # step i+1 runs
+        self.posts = [self.post]
+        if double_buffer:
+            self.posts.append(ops.PreparedFcos(self.cls, self.reg, self.ctr, self.strides, image_sizes, p.pre_nms_thresh,
+                                               p.pre_nms_top_n, p.nms_thresh, p.fpn_post_nms_top_n, p.min_size, strict_iou,
+                                               early_exit, workspace=self.post.result.workspace))
+        self._step = 0
         self._host_out = None
         self._streams = None
         self._graph = None
@@ -63,7 +73,12 @@ class EpisodePipeline:
         """One pass of the hot path over the resident batch: 1 matching launch + the post-processing launches,
         back to back on the current stream."""
         self.match()
-        return self.post()
+        return self._next_post()()
+
+    def _next_post(self):
+        post = self.posts[self._step % len(self.posts)]
+        self._step += 1
+        return post
 
     def run_overlapped(self) -> ops.FcosResult:
         """The same work software-pipelined over two streams: the HBM-bound matching stream and the latency-bound
@@ -82,7 +97,7 @@ class EpisodePipeline:
         with torch.cuda.stream(s_match):
             self.match()
         with torch.cuda.stream(s_post):
-            res = self.post()
+            res = self._next_post()()
         cur.wait_stream(s_match)
         cur.wait_stream(s_post)
         return res
@@ -99,12 +114,19 @@ class EpisodePipeline:
                 step()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            res = step()
-        self._graph = graph
+        graphs = []
+        for _ in self.posts:   # one graph per output buffer set; replay alternates between them
+            self._step = len(graphs)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                res = step()
+            graphs.append((graph, res))
+        self._graph = graphs
+        self._step = 0
 
         def replay():
+            graph, res = graphs[self._step % len(graphs)]
+            self._step += 1
             graph.replay()
             return res
 

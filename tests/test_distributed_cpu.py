@@ -130,3 +130,55 @@ def test_async_detection_gatherer_world_size_2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def _block_gatherer_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oneshotdet_b200 import ops
+        from oneshotdet_b200.distributed import BlockGatherer
+
+        e, k = 3, 5
+        g = BlockGatherer(e, k, torch.device("cpu"))
+        blocks = [ops.result_block(e, k, torch.device("cpu")) for _ in range(2)]   # the double-buffered step outputs
+
+        def fill(views, step, r):
+            gen = torch.Generator().manual_seed(1000 * step + r)
+            views[0].copy_(torch.rand(e, k, 4, generator=gen))
+            views[1].copy_(torch.rand(e, k, generator=gen))
+            views[2].copy_(torch.randint(0, 100, (e, k), generator=gen, dtype=torch.int32))
+            views[3].copy_(torch.randint(0, k + 1, (e,), generator=gen, dtype=torch.int32))
+
+        ok = True
+        for step in range(5):
+            block, views = blocks[step & 1]
+            fill(views, step, rank)
+            slot = g.submit(block)
+            assert slot == step & 1
+        g.finish()
+        for step in (3, 4):                                   # the two groups still resident
+            per_rank = g.result(step & 1)
+            assert len(per_rank) == world
+            for r in range(world):
+                _, want = ops.result_block(e, k, torch.device("cpu"))
+                fill(want, step, r)
+                ok = ok and all(torch.equal(a, b) for a, b in zip(per_rank[r], want))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_block_gatherer_world_size_2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_block_gatherer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(0, True), (1, True)]

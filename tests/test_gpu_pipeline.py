@@ -70,3 +70,38 @@ def test_pack_detections_layout():
     assert d.shape == (2, res.boxes.shape[1], 6) and c.dtype == torch.int32
     assert torch.equal(d[..., :4], res.boxes) and torch.equal(d[..., 4], res.scores)
     assert d[0, 0, 5].item() == 10.0 and d[1, 0, 5].item() == 11.0
+
+
+def test_double_buffered_graph_steps_and_result_block():
+    """double_buffer=True: consecutive steps alternate between two output sets (eager and CUDA-graph replay); each
+    step's boxes | scores | index | count are views of ONE result block, which is what the multi-GPU gather ships."""
+    from oneshotdet_b200 import ops
+    from oneshotdet_b200.distributed import BlockGatherer
+    from oneshotdet_b200.pipeline import EpisodePipeline, PostParams
+
+    sizes = [(250, 320), (256, 300), (256, 320)]
+    p = PostParams(0.0, 400, 0.7, 100, 0.0)
+    pipe = EpisodePipeline(3, 256, 320, sizes, channels=32, shots=2, params=p, device=DEV, double_buffer=True)
+    feats, supp = orc.synth_features(3, 2, 32, 256, 320, seed=5)
+    cls, reg, ctr = orc.synth_head_outputs(3, 256, 320, seed=6)
+    for dst, src in zip(pipe.input_tensors(), feats + supp + cls + reg + ctr):
+        dst.copy_(src.to(DEV))
+    r0 = pipe.run()
+    r1 = pipe.run()
+    assert r0 is not r1 and r0.block.data_ptr() != r1.block.data_ptr()
+    a, b = snapshot(r0), snapshot(r1)
+    assert a[0] == b[0] and all(torch.equal(x, y) for x, y in zip(a[1] + a[2], b[1] + b[2]))
+    # the four outputs are views of the block
+    _, views = ops.result_block(3, r0.boxes.size(1), DEV, r0.block)
+    assert all(v.data_ptr() == t.data_ptr() for v, t in zip(views, (r0.boxes, r0.scores, r0.index, r0.count)))
+    replay = pipe.capture(overlapped=True)
+    g0, g1, g2 = replay(), replay(), replay()
+    assert g0 is g2 and g0 is not g1
+    c0, c1 = snapshot(g0), snapshot(g1)
+    assert c0[0] == a[0] == c1[0] and all(torch.equal(x, y) for x, y in zip(a[1] + a[2], c1[1] + c1[2]))
+    # single-process gatherer: the gathered block parses back to the same tensors
+    g = BlockGatherer(3, r0.boxes.size(1), torch.device(DEV))
+    slot = g.submit(g1.block)
+    g.finish()
+    (bx, sc, ix, ct), = g.result(slot)
+    assert torch.equal(bx, g1.boxes) and torch.equal(sc, g1.scores) and torch.equal(ct, g1.count)
