@@ -390,6 +390,10 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         const float bias = oc_ok ? A.bias[(size_t)t.level * A.bias_level_stride + (size_t)t.img * A.bias_img_stride + oc] : 0.f;
         uint32_t r[32];
         tmem_ld32(taddr, r);
+        // the previous bulk store of this warp must have read the stage before it is rewritten; waiting here rather
+        // than right after issuing it lets the store overlap this tile's TMEM load
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
         tmem_ld_wait();
         float s1 = 0.f, s2 = 0.f;
         // bias, statistics, and the row (channel) of this lane into the swizzled stage: 16-byte chunk c of row
@@ -415,8 +419,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           __syncwarp();
           if (lane == 0 && oc0 < A.Cout) {
             tma_store_2d(&out_maps.m[t.level], stage, t.px0 + pxh, t.img * A.Cout + oc0);
-            tma_store_commit();
-            tma_store_wait_read();   // the stage may be rewritten once the bulk copy has read it
+            tma_store_commit();      // (waited for at the top of the next accumulator tile)
           }
           __syncwarp();
         } else {
