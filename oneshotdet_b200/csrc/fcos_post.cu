@@ -13,6 +13,8 @@
 namespace cg = cooperative_groups;
 
 namespace osd {
+// Debug aid (-DOSD_DEBUG_TS): %globaltimer stamps at the phase boundaries of one P3 CTA, read back with
+// osd_debug_select_stamps() -- how the phase times next to the matching stream in DESIGN section 4 were measured.
 #ifdef OSD_DEBUG_TS
 __device__ unsigned long long g_sel_ts[8];
 #define OSD_STAMP(k)                                                                       \
@@ -32,9 +34,7 @@ namespace {
 constexpr int kCl = 8;              // CTAs per cluster = per (episode, level)
 constexpr int kSelThreads = 256;
 constexpr int kSelLoads = 9;          // loads in flight per thread and array while scoring (9 x 256 >= a 2100-location slice)
-#ifndef OSD_SEL_MINB
-#define OSD_SEL_MINB 5               // <= 48 registers: 5 CTAs per SM next to the matching kernel's CTA
-#endif
+constexpr int kSelMinBlocks = 5;      // launch bound: <= 48 registers, 5 CTAs per SM next to the matching kernel's CTA
 constexpr int kRadixBins = 256;     // radix-select digits: 8 + 8 + 8 + 7 bits (== kSelThreads: thread t owns bin t)
 constexpr int kMaxRounds = 3;       // 63 * 256 locations per round and CTA
 constexpr int kMaxSlice = kMaxRounds * 63 * kSelThreads;   // 48 384 locations per CTA (193 KB of keys)
@@ -101,7 +101,7 @@ __device__ __forceinline__ Decoded decode_clip(float dl, float dt, float dr, flo
 // level in its own shared memory; the radix-select histograms are combined through distributed shared memory
 // (every CTA sums the kCl histograms and runs the same bin search), and the ordered compaction uses the slice
 // totals exchanged the same way.  The P3 level (16 800 locations) is thus worked on by 8 SMs instead of one.
-__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads, OSD_SEL_MINB) fcos_select_kernel(SelectArgs A) {
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kSelThreads, kSelMinBlocks) fcos_select_kernel(SelectArgs A) {
   OSD_STAMP(0);
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ uint32_t sm_dyn[];

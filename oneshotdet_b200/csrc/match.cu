@@ -17,13 +17,7 @@ namespace osd {
 namespace {
 
 constexpr int kThreads = 256;
-#ifndef OSD_MATCH_VEC
-#define OSD_MATCH_VEC 4
-#endif
-#ifndef OSD_MATCH_MINB
-#define OSD_MATCH_MINB 5
-#endif
-constexpr int kVecPerThread = OSD_MATCH_VEC;         // independent 128-bit loads in flight per thread
+constexpr int kVecPerThread = 4;                     // independent 128-bit loads in flight per thread
 constexpr int kChunkVec = kThreads * kVecPerThread;  // 1024 x 16 B = 16 KB of output per chunk
 
 struct Level {
@@ -102,7 +96,7 @@ __device__ __forceinline__ float nchw_value(const Args& A, const Level& L, uint3
 }
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads, OSD_MATCH_MINB) match_nchw_kernel(Args A, FastDiv div_c) {
+__global__ void __launch_bounds__(kThreads, 5) match_nchw_kernel(Args A, FastDiv div_c) {
   constexpr int N = Vec<T>::N;
   // no shared memory, no barriers: every warp streams independently; the pooled support scalar of a plane is a
   // 4-byte read that stays in L1 (B*C*S values per level)
@@ -187,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, OSD_MATCH_MINB) match_nchw_kernel(Ar
 // so a vector never leaves its pixel nor its half.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads, OSD_MATCH_MINB) match_nhwc_kernel(Args A, FastDiv div_c) {
+__global__ void __launch_bounds__(kThreads, 5) match_nhwc_kernel(Args A, FastDiv div_c) {
   constexpr int N = Vec<T>::N;
   for (uint32_t chunk = blockIdx.x; chunk < A.total_chunks; chunk += gridDim.x) {
     int li = 0;
@@ -256,20 +250,13 @@ __global__ void __launch_bounds__(kThreads, OSD_MATCH_MINB) match_nhwc_kernel(Ar
 // two consumer groups scale their chunk in place and hand it to cp.async.bulk shared->global.  In-flight bytes live
 // in shared memory, so the kernel holds 288 threads x ~40 registers per SM and leaves the rest to the other stream.
 // ---------------------------------------------------------------------------------------------
-#ifndef OSD_BULK_MINB
-#define OSD_BULK_MINB 5      // caps the kernel at 40 registers/thread: the other stream's CTAs need the register file
-#endif
-#ifndef OSD_BULK_BACKOFF_NS
-#define OSD_BULK_BACKOFF_NS 200
-#endif
-#ifndef OSD_BULK_GROUPS
-#define OSD_BULK_GROUPS 2
-#endif
-#ifndef OSD_BULK_SLOTS
-#define OSD_BULK_SLOTS 6     // measured on one box, step / kernel alone: 5: 0.183 / 0.161 ms, 6: 0.181 / 0.145, 7: 0.192 / 0.135,
-#endif                       // 8: 0.204 / 0.136 -- deeper queues make the kernel itself faster and its neighbours slower
-constexpr int kBulkSlots = OSD_BULK_SLOTS;                                  // x 16 KB ring
-constexpr int kBulkGroups = OSD_BULK_GROUPS;
+// Ring depth, measured on one box as (two-stream step / kernel alone): 5 slots 0.183 / 0.161 ms, 6: 0.181 / 0.145,
+// 7: 0.192 / 0.135, 8: 0.204 / 0.136 -- deeper queues make the kernel itself faster and its neighbours slower.
+constexpr int kBulkSlots = 6;                                  // x 16 KB ring
+constexpr int kBulkGroups = 2;
+constexpr int kBulkMinBlocks = 5;   // launch bound that caps the kernel at 40 registers/thread: the other stream's CTAs
+                                    // need the register file
+constexpr unsigned kBulkBackoffNs = 200;
 constexpr int kBulkGroupThreads = 128;
 constexpr int kBulkThreads = 32 + kBulkGroups * kBulkGroupThreads;
 constexpr uint32_t kChunkBytes = kChunkVec * 16;
@@ -294,9 +281,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) return;
-#ifndef OSD_BULK_NO_BACKOFF
-    __nanosleep(OSD_BULK_BACKOFF_NS);   // waiting warps must not eat the issue slots of the other stream's CTAs on this SM
-#endif
+    __nanosleep(kBulkBackoffNs);   // waiting warps should not eat the issue slots of the other stream's CTAs on this SM
     if (++spins > kBulkSpinLimit) __trap();
   }
 }
@@ -345,8 +330,7 @@ __device__ __forceinline__ ChunkRef locate_chunk(const Args& A, uint32_t chunk) 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kBulkThreads, OSD_BULK_MINB) match_product_bulk_kernel(Args A, FastDiv div_c) {
-  OSD_TS("match_block0_start");
+__global__ void __launch_bounds__(kBulkThreads, kBulkMinBlocks) match_product_bulk_kernel(Args A, FastDiv div_c) {
   constexpr int N = Vec<T>::N;
   extern __shared__ __align__(128) uint8_t ring_raw[];
   __shared__ __align__(8) uint64_t full_bar[kBulkSlots], empty_bar[kBulkSlots];
@@ -391,11 +375,7 @@ __global__ void __launch_bounds__(kBulkThreads, OSD_BULK_MINB) match_product_bul
     uint4* slot = reinterpret_cast<uint4*>(ring_ptr + s * kChunkBytes);
     const uint32_t nv = c.bytes >> 4;
     const uint32_t e_first = c.v0 * N;
-#ifdef OSD_BULK_NO_FASTPATH
-    if (false) {
-#else
     if (L.hw >= kChunkVec * N) {
-#endif
       // large planes (P3, P4: 94 % of the bytes): the chunk touches at most two planes, so the two pooled scalars are
       // fetched once per chunk and a vector only compares its element range with the plane boundary
       const uint32_t p0 = fdiv(e_first, L.div_hw);
@@ -450,7 +430,6 @@ __global__ void __launch_bounds__(kBulkThreads, OSD_BULK_MINB) match_product_bul
     }
   }
   if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory stays valid until the stores are done
-  if (tid == 32) OSD_TS_ANY("match_block0_end");
 }
 
 template <typename T>

@@ -120,7 +120,6 @@ __device__ __forceinline__ u64 shfl_xor_u64(u64 v, int lane_mask) {
 }
 
 __global__ void __launch_bounds__(kChunkThreads) nms_chunk_sort_kernel(CandLayout L, NmsWorkspace W) {
-  OSD_TS("sort_block0_start");
   __shared__ u64 sk[kChunk];
   __shared__ int lvl_prefix[OSD_MAX_LEVELS + 1];
   const int e = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
@@ -223,7 +222,6 @@ __device__ __forceinline__ int count_less(const u64* __restrict__ run, int len2,
 }
 
 __global__ void __launch_bounds__(kMergeThreads) nms_merge_kernel(CandLayout L, NmsWorkspace W) {
-  OSD_TS("merge_block0_start");
   extern __shared__ u64 staged[];  // up to kMergeStage sorted keys of the other chunks
   __shared__ int lvl_prefix[OSD_MAX_LEVELS + 1];
   const int e = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;

@@ -5,30 +5,6 @@
 
 namespace osd {
 
-// Debug aid (-DOSD_DEBUG_TS): block 0 / thread 0 prints the GPU global timer at kernel entry / exit.
-#ifdef OSD_DEBUG_TS
-#include <cstdio>
-#define OSD_TS(tag)                                                                                          \
-  do {                                                                                                       \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {                         \
-      unsigned long long _t;                                                                                 \
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                                 \
-      printf("TS %s %llu\n", tag, _t);                                                                       \
-    }                                                                                                        \
-  } while (0)
-#define OSD_TS_ANY(tag)                                                                                      \
-  do {                                                                                                       \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {                                             \
-      unsigned long long _t;                                                                                 \
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                                 \
-      printf("TS %s %llu\n", tag, _t);                                                                       \
-    }                                                                                                        \
-  } while (0)
-#else
-#define OSD_TS(tag) do {} while (0)
-#define OSD_TS_ANY(tag) do {} while (0)
-#endif
-
 // Exclusive prefix sum of `v` over the thread block; `total` receives the block sum.
 // warp_tot: 33 ints of shared memory.  Contains __syncthreads(): call from uniform control flow.
 __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot, int& total) {
