@@ -98,3 +98,45 @@ def test_torch_extension_loads_and_refuses_cpu_tensors():
     assert _C_torch.version() == _lib.load().osd_version()
     with pytest.raises(RuntimeError, match="no CPU path"):
         _C_torch.nms(torch.zeros(4, 4), torch.zeros(4), 0.5)
+
+
+def test_second_stage_and_handoff_entry_points_validate_without_a_gpu(lib, tmp_path):
+    """Plans and argument checks of the 'next'-row entry points run on the CPU box (no kernel is launched)."""
+    cfg = _lib.BoxPostConfig()
+    plan = _lib.BoxPostPlan()
+    cfg.batch, cfg.rois_per_image, cfg.num_logits, cfg.reg_columns, cfg.reg_offset, cfg.score_mode = 16, 2000, 2, 8, 4, 0
+    for k, w in enumerate((10.0, 10.0, 5.0, 5.0)):
+        cfg.weights[k] = w
+    cfg.detections_per_img = 100
+    assert lib.osd_box_postprocess_plan(ctypes.byref(cfg), ctypes.byref(plan)) == 0
+    assert plan.cand_capacity == 2000 and plan.out_capacity == 100 and plan.workspace_bytes > 16 * 2000 * 24
+    cfg.reg_columns = 6                                    # class 1 would read columns [4, 8)
+    assert lib.osd_box_postprocess_plan(ctypes.byref(cfg), ctypes.byref(plan)) == -1
+    assert b"regression columns" in lib.osd_last_error()
+    cfg.reg_columns, cfg.num_logits = 8, 1                 # softmax needs two logits
+    assert lib.osd_box_postprocess_plan(ctypes.byref(cfg), ctypes.byref(plan)) == -1
+    assert b"num_logits" in lib.osd_last_error()
+
+    d = _lib.RoiPoolDesc()
+    d.num_levels, d.batch, d.rois_per_image, d.channels, d.pooled_size, d.sampling_ratio = 2, 2, 10, 8, 7, 2
+    d.k_min, d.k_max = 3, 4
+    for l, (h, w) in enumerate(((32, 40), (16, 20))):
+        d.height[l], d.width[l], d.spatial_scale[l] = h, w, 1.0 / (8 << l)
+    need = ctypes.c_size_t(0)
+    assert lib.osd_roi_pool_workspace_bytes(ctypes.byref(d), ctypes.byref(need)) == 0
+    assert need.value >= 2 * 8 * (32 * 40 + 16 * 20) * 4
+    d.k_max = 7                                            # 5 mapper levels for 2 feature levels
+    assert lib.osd_roi_pool(ctypes.byref(d), None) == -1
+    assert b"LevelMapper" in lib.osd_last_error()
+
+    # the JSON writer is a host function: it works here
+    import numpy as np
+
+    rec = np.asarray([[1.5, 2.0, 3.25, 4.0, 0.5]], np.float32)
+    ep = np.asarray([0], np.int32)
+    img, cat = np.asarray([42], np.int64), np.asarray([7], np.int64)
+    path = str(tmp_path / "r.json").encode()
+    assert lib.osd_coco_write_json(rec.ctypes.data, ep.ctypes.data, 1, img.ctypes.data, cat.ctypes.data, 1, path) == 0
+    import json
+
+    assert json.load(open(path)) == [{"bbox": [1.5, 2.0, 3.25, 4.0], "category_id": 7, "image_id": 42, "score": 0.5}]
