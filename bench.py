@@ -259,7 +259,7 @@ def run_b200_arm(args):
     # gathered as is, every step, without packing kernels.  "packed": [E, K+1, 6] payloads packed by copy kernels and
     # gathered in groups of --gather-every steps (the reference gathers once, after the whole dataset).
     gatherer = None
-    if world > 1:
+    if world > 1 and args.gather != "none":
         if args.gather == "block":
             gatherer = BlockGatherer(BATCH, pipe.post.plan.out_capacity, dev)
         else:
@@ -424,6 +424,9 @@ def run_b200_arm(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
                 "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak",
+                "gather": (("none (DIAGNOSIS RUN: not a multi-GPU measurement)" if args.gather == "none" else
+                            "result block, every step, async" if args.gather == "block" else
+                            f"packed payloads, every {args.gather_every} steps, async") if world > 1 else None),
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(n_gpus),
                 "roofline": roofline, "stages": stages, "fusion_mode": fusion, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks,
@@ -443,8 +446,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fusion", action="store_true")
     ap.add_argument("--serial", action="store_true", help="one stream: matching then post-processing, no overlap")
-    ap.add_argument("--gather", choices=["block", "packed"], default="block",
-                    help="N>1: gather the step's result block as is (default) or pack [E,K+1,6] payloads")
+    ap.add_argument("--gather", choices=["block", "packed", "none"], default="block",
+                    help="N>1: gather the step's result block as is (default), pack [E,K+1,6] payloads, or (diagnosis "
+                         "only: not a valid multi-GPU measurement) no gather at all")
     ap.add_argument("--gather-every", type=int, default=10,
                     help="N>1: steps per NCCL all-gather of the detections (1 = every step)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")

@@ -35,6 +35,7 @@ struct Args {
   int nl, B, S, C, Cout, mode;
   uint32_t total_chunks;
   int l2_evict_first;    // bulk kernel: tag the streamed lines evict-first in L2
+  int sched_slot;        // bulk kernel: which pair of dynamic-scheduler counters this launch uses
   FastDiv div_cout;      // q / Cout (NCHW concat: plane -> episode; NHWC: offset -> pixel)
   Level lv[OSD_MAX_LEVELS];
 };
@@ -329,11 +330,20 @@ __device__ __forceinline__ ChunkRef locate_chunk(const Args& A, uint32_t chunk) 
   return c;
 }
 
+// Dynamic chunk scheduler: CTAs draw 16 KB chunks from a global counter, so an SM that shares its cycles with the other
+// stream's CTAs (post-processing kernels, the NCCL all-gather) simply takes fewer chunks instead of finishing last.
+// g_sched[slot] = {next chunk, CTAs finished}; the last CTA to finish resets the pair for the next launch.  Launches
+// that may overlap in time use different slots (the host rotates through kSchedSlots; a captured graph keeps its slot).
+constexpr int kSchedSlots = 64;
+constexpr uint32_t kNoChunk = 0xffffffffu;
+__device__ unsigned int g_sched[kSchedSlots][2];
+
 template <typename T>
 __global__ void __launch_bounds__(kBulkThreads, kBulkMinBlocks) match_product_bulk_kernel(Args A, FastDiv div_c) {
   constexpr int N = Vec<T>::N;
   extern __shared__ __align__(128) uint8_t ring_raw[];
   __shared__ __align__(8) uint64_t full_bar[kBulkSlots], empty_bar[kBulkSlots];
+  __shared__ uint32_t slot_chunk[kBulkSlots];   // which chunk the producer put into each ring slot (kNoChunk: stop)
   const uint32_t ring = (smem_addr(ring_raw) + 127u) & ~127u;
   uint8_t* ring_ptr = ring_raw + (ring - smem_addr(ring_raw));
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -345,20 +355,33 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkMinBlocks) match_product_bu
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  // this CTA's chunks: blockIdx.x, blockIdx.x + gridDim.x, ...
-  const uint32_t n_my = A.total_chunks > blockIdx.x ? (A.total_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp == 0) {
     if (tid == 0) {
-      for (uint32_t i = 0; i < n_my; ++i) {
+      unsigned int* sched = g_sched[A.sched_slot];
+      int stops = 0;   // one stop mark per consumer group (group g consumes slots of iterations i = g mod kBulkGroups)
+      for (uint32_t i = 0; stops < kBulkGroups; ++i) {
         const uint32_t s = i % kBulkSlots;
         if (i >= (uint32_t)kBulkSlots) mbar_wait(smem_addr(&empty_bar[s]), ((i / kBulkSlots) - 1) & 1);
-        const ChunkRef c = locate_chunk<T>(A, blockIdx.x + i * gridDim.x);
+        const uint32_t chunk = stops ? kNoChunk : atomicAdd(&sched[0], 1u);
         const uint32_t bar = smem_addr(&full_bar[s]);
+        if (chunk >= A.total_chunks) {
+          slot_chunk[s] = kNoChunk;
+          mbar_arrive(bar);
+          ++stops;
+          continue;
+        }
+        slot_chunk[s] = chunk;
+        const ChunkRef c = locate_chunk<T>(A, chunk);
         mbar_expect_tx(bar, c.bytes);
         const uint8_t* src = static_cast<const uint8_t*>(A.lv[c.level].feat) + (size_t)c.v0 * 16;
         if (A.l2_evict_first) bulk_load_hint(ring + s * kChunkBytes, src, c.bytes, bar, l2_evict_first_policy());
         else bulk_load(ring + s * kChunkBytes, src, c.bytes, bar);
+      }
+      // the last CTA out resets the counters (nobody draws from them any more)
+      if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {
+        sched[0] = 0u;
+        sched[1] = 0u;
       }
     }
     return;
@@ -366,12 +389,14 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkMinBlocks) match_product_bu
 
   const int g = (warp - 1) / (kBulkGroupThreads / 32);
   const int t = tid - 32 - g * kBulkGroupThreads;
-  for (uint32_t i = g; i < n_my; i += kBulkGroups) {
+  for (uint32_t i = g;; i += kBulkGroups) {
     const uint32_t s = i % kBulkSlots;
-    const ChunkRef c = locate_chunk<T>(A, blockIdx.x + i * gridDim.x);
+    mbar_wait(smem_addr(&full_bar[s]), (i / kBulkSlots) & 1);
+    const uint32_t chunk = slot_chunk[s];
+    if (chunk == kNoChunk) break;
+    const ChunkRef c = locate_chunk<T>(A, chunk);
     const Level& L = A.lv[c.level];
     const T* supp = static_cast<const T*>(L.supp);
-    mbar_wait(smem_addr(&full_bar[s]), (i / kBulkSlots) & 1);
     uint4* slot = reinterpret_cast<uint4*>(ring_ptr + s * kChunkBytes);
     const uint32_t nv = c.bytes >> 4;
     const uint32_t e_first = c.v0 * N;
@@ -491,6 +516,9 @@ int launch(const Args& A, int layout, cudaStream_t stream) {
     }
     Args AB = A;
     AB.l2_evict_first = l2_hint;
+    static thread_local int next_slot = 0;
+    AB.sched_slot = next_slot;
+    next_slot = (next_slot + 1) % kSchedSlots;
     match_product_bulk_kernel<T><<<grid, kBulkThreads, smem, stream>>>(AB, div_c);
     OSD_LAUNCH_CHECK("match_product_bulk_kernel");
     timeline_mark("match_product_bulk_kernel", stream);
