@@ -232,11 +232,8 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # The per-step all-gather is small (643 KB per rank) and runs next to the step's own kernels: two channels and
-        # the low-latency protocol keep NCCL's CTAs from taking SM cycles away from them (2 GPUs, ms per step: NCCL
-        # defaults 0.182, 2 channels 0.179, 2 channels + LL 0.174, 1 channel 0.226; no gather at all 0.172).
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
-        os.environ.setdefault("NCCL_PROTO", "LL")
+        # NCCL is left at its defaults: fewer channels / the LL protocol help the 643 KB gather at 2 GPUs (0.174 vs
+        # 0.182 ms per step) but starve it at 8 (0.26 - 0.46 ms), see DESIGN section 7.
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     warmup = max(args.warmup, 3)
