@@ -8,7 +8,9 @@
 // multiply a single rounded fp32 product: fp32 results are bit-identical to the reference expression.
 #include <cuda_bf16.h>
 
+#include <atomic>
 #include <cstdlib>
+#include <cstring>
 
 #include "osd_common.cuh"
 #include "osd_device_utils.cuh"
@@ -333,8 +335,11 @@ __device__ __forceinline__ ChunkRef locate_chunk(const Args& A, uint32_t chunk) 
 // Dynamic chunk scheduler: CTAs draw 16 KB chunks from a global counter, so an SM that shares its cycles with the other
 // stream's CTAs (post-processing kernels, the NCCL all-gather) simply takes fewer chunks instead of finishing last.
 // g_sched[slot] = {next chunk, CTAs finished}; the last CTA to finish resets the pair for the next launch.  Launches
-// that may overlap in time use different slots (the host rotates through kSchedSlots; a captured graph keeps its slot).
+// Launches that may overlap in time must not share a slot: eager launches rotate through the first kEagerSlots, a launch
+// recorded into a CUDA graph gets one of the remaining slots for good (the graph replays with it); when those run out
+// the launch uses static round-robin chunks (sched_slot < 0).
 constexpr int kSchedSlots = 64;
+constexpr int kEagerSlots = 32;
 constexpr uint32_t kNoChunk = 0xffffffffu;
 __device__ unsigned int g_sched[kSchedSlots][2];
 
@@ -358,12 +363,13 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkMinBlocks) match_product_bu
 
   if (warp == 0) {
     if (tid == 0) {
-      unsigned int* sched = g_sched[A.sched_slot];
+      const bool dynamic = A.sched_slot >= 0;
+      unsigned int* sched = g_sched[dynamic ? A.sched_slot : 0];
       int stops = 0;   // one stop mark per consumer group (group g consumes slots of iterations i = g mod kBulkGroups)
       for (uint32_t i = 0; stops < kBulkGroups; ++i) {
         const uint32_t s = i % kBulkSlots;
         if (i >= (uint32_t)kBulkSlots) mbar_wait(smem_addr(&empty_bar[s]), ((i / kBulkSlots) - 1) & 1);
-        const uint32_t chunk = stops ? kNoChunk : atomicAdd(&sched[0], 1u);
+        const uint32_t chunk = stops ? kNoChunk : (dynamic ? atomicAdd(&sched[0], 1u) : blockIdx.x + i * gridDim.x);
         const uint32_t bar = smem_addr(&full_bar[s]);
         if (chunk >= A.total_chunks) {
           slot_chunk[s] = kNoChunk;
@@ -379,7 +385,7 @@ __global__ void __launch_bounds__(kBulkThreads, kBulkMinBlocks) match_product_bu
         else bulk_load(ring + s * kChunkBytes, src, c.bytes, bar);
       }
       // the last CTA out resets the counters (nobody draws from them any more)
-      if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {
+      if (dynamic && atomicAdd(&sched[1], 1u) == gridDim.x - 1) {
         sched[0] = 0u;
         sched[1] = 0u;
       }
@@ -516,9 +522,20 @@ int launch(const Args& A, int layout, cudaStream_t stream) {
     }
     Args AB = A;
     AB.l2_evict_first = l2_hint;
-    static thread_local int next_slot = 0;
-    AB.sched_slot = next_slot;
-    next_slot = (next_slot + 1) % kSchedSlots;
+    {
+      static std::atomic<int> next_eager{0}, next_captured{kEagerSlots};
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      OSD_CUDA(cudaStreamIsCapturing(stream, &cap));
+      const char* sched_env = getenv("OSD_MATCH_SCHED");   // "static": round-robin chunks (read per launch: tests toggle it)
+      if (sched_env && strcmp(sched_env, "static") == 0) {
+        AB.sched_slot = -1;
+      } else if (cap == cudaStreamCaptureStatusNone) {
+        AB.sched_slot = next_eager.fetch_add(1) % kEagerSlots;
+      } else {
+        const int slot = next_captured.fetch_add(1);
+        AB.sched_slot = slot < kSchedSlots ? slot : -1;   // out of dedicated slots: static chunk assignment
+      }
+    }
     match_product_bulk_kernel<T><<<grid, kBulkThreads, smem, stream>>>(AB, div_c);
     OSD_LAUNCH_CHECK("match_product_bulk_kernel");
     timeline_mark("match_product_bulk_kernel", stream);

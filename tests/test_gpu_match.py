@@ -113,3 +113,22 @@ def test_matching_module_dropin():
     out = m([f.to(DEV) for f in feats], [s.to(DEV) for s in supp], 2)
     for o, e in zip(out, orc.match_product(feats, supp, 2)):
         assert torch.equal(o.cpu(), e)
+
+
+def test_static_and_dynamic_chunk_scheduling_agree(monkeypatch):
+    """The bulk-copy kernel draws chunks from a global counter (default) or, when the dedicated counter slots of captured
+    launches run out, round-robin; both must give the reference product, also for many back-to-back launches (the
+    counters are reset by the last CTA of each launch)."""
+    import oneshotdet_b200 as osd
+
+    feats, supp = orc.synth_features(2, 2, 64, 200, 264, seed=77)
+    want = orc.match_product(feats, supp, 2)
+    df, ds = [f.to(DEV) for f in feats], [x.to(DEV) for x in supp]
+    for mode in ("dynamic", "static"):
+        if mode == "static":
+            monkeypatch.setenv("OSD_MATCH_SCHED", "static")
+        for _ in range(70):                       # more launches than counter slots
+            out = osd.match_forward(df, ds, 2)
+        torch.cuda.synchronize()
+        for o, e in zip(out, want):
+            assert torch.equal(o.cpu(), e), mode
