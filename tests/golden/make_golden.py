@@ -17,6 +17,7 @@ What is executed (paths relative to /root/reference):
 
   * modeling/poolers.py:93-125 with layers/roi_align.py  Pooler.forward + LevelMapper                         -> pooler_*.npz
 
+  * layers/scale.py + torch.exp as in modeling/rpn/fcos/fcos.py:95-97                                       -> fcos_head_tail.npz
   * structures/bounding_box.py:55-127 (BoxList.resize / convert) inside the loop body of
     data/datasets/evaluation/coco/coco_eval.py:137-165                                                      -> coco_*.npz
 
@@ -276,6 +277,23 @@ def coco_case(name, image_sizes_wh, orig_sizes_wh, counts, seed):
     print(f"coco_{name}.npz:", len(coco_results), "records,", len(text), "bytes of JSON")
 
 
+def head_tail_case():
+    """The tail of FCOSHead.forward for the regression branch (modeling/rpn/fcos/fcos.py:95-97): the reference's own
+    Scale module (layers/scale.py) and torch.exp, executed on seeded raw bbox_pred maps."""
+    from maskrcnn_benchmark.layers import Scale  # noqa: PLC0415
+
+    rng = np.random.RandomState(17)
+    data = {}
+    for l, (h, w, init) in enumerate([(25, 34, 1.0), (13, 17, 0.83), (7, 9, 1.37)]):
+        raw = torch.from_numpy(rng.normal(1.5 + l, 0.8, (2, 4, h, w)).astype(np.float32))
+        scale = Scale(init_value=init)
+        with torch.no_grad():
+            out = torch.exp(scale(raw))
+        data[f"raw{l}"], data[f"scale{l}"], data[f"out{l}"] = raw.numpy(), np.float32(init), out.numpy()
+    np.savez_compressed(os.path.join(HERE, "fcos_head_tail.npz"), **data)
+    print("fcos_head_tail.npz written")
+
+
 def coco_cases():
     # equal ratios (one factor), unequal ratios, an empty image, an upscale
     coco_case("mixed", [(1333, 800), (1066, 800), (800, 800), (640, 480)], [(500, 300), (500, 375), (400, 400), (1280, 961)],
@@ -287,6 +305,9 @@ def main():
     ref_c = import_reference()
     if "--only-box-post" in sys.argv:
         box_post_cases()
+        return
+    if "--only-head-tail" in sys.argv:
+        head_tail_case()
         return
     if "--only-coco" in sys.argv:
         coco_cases()
@@ -306,6 +327,7 @@ def main():
     box_post_cases()
     pooler_cases()
     coco_cases()
+    head_tail_case()
 
 
 if __name__ == "__main__":

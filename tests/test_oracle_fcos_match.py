@@ -92,3 +92,12 @@ def test_matching_matches_reference(golden_dir, name):
         assert cat[l].shape[1] == 2 * c and s >= 1
         np.testing.assert_allclose(conv1[l].numpy(), z[f"conv1_{l}"], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(fused[l].numpy(), z[f"fused{l}"], rtol=1e-4, atol=1e-5)
+
+
+def test_head_tail_restatement_matches_executed_reference(golden_dir):
+    """oracle.fcos_head_tail (exp(x * scale), fcos.py:95-97) against the reference's Scale module + torch.exp executed
+    in the build container: bit-exact (same ATen ops)."""
+    z = np.load(os.path.join(golden_dir, "fcos_head_tail.npz"))
+    for l in range(3):
+        got = orc.fcos_head_tail(torch.from_numpy(z[f"raw{l}"]), float(z[f"scale{l}"]))
+        np.testing.assert_array_equal(got.numpy(), z[f"out{l}"])
