@@ -41,6 +41,7 @@ typedef unsigned long long u64;
 
 struct IouTest {
   float thr, thr_lo, thr_hi;
+  float c_lo;   // (thr / (1 + thr)) * (1 - 2^-19): inter < c_lo * (area_a + area_b)  =>  IoU < thr for certain
   int strict;
   int force_exact;
 };
@@ -277,9 +278,8 @@ __global__ void __launch_bounds__(kMergeThreads) nms_merge_kernel(CandLayout L, 
 // ------------------------------------------------------------------------------------------------
 // 2. IoU bitmask.  Persistent CTAs walk (row block of 128) x (column group of 256) tiles of all episodes;
 //    thread = one row, 64 pairs per 64-bit word, column boxes broadcast from shared memory.
-//    The inner loop is branch-free: two masks are built per word -- `sub` (inter > thr_hi*u: certainly
-//    suppressed) and `sup` (inter >= thr_lo*u: possibly suppressed); only bits in sup & ~sub (IoU within
-//    4e-6 of the threshold) take the IEEE division afterwards.
+//    The inner loop is branch-free and builds one mask per word -- the pairs a conservative, division-free test
+//    cannot rule out (see pair_bit); only those take the reference's full arithmetic afterwards.
 // ------------------------------------------------------------------------------------------------
 struct PairTerms {
   float inter, uni;
@@ -311,31 +311,38 @@ __device__ __forceinline__ bool iou_hit_exact(const float4& a, float aa, const f
   return T.strict ? (q > T.thr) : (q >= T.thr);
 }
 
-// Both compares become integer subtractions whose sign bit is funnel-shifted into the mask (1 IADD + 1 SHF per
-// compare instead of FSETP + SEL + LOP3): every operand is a non-negative finite float in a regular episode, so
-// the float order equals the order of the bit patterns.  Bits arrive MSB-first and are reversed per 32 pairs.
-__device__ __forceinline__ void pair_bits(const float4& rb, float ra, const float4& cb, float ca, const IouTest& T,
-                                          uint32_t& sub, uint32_t& sup) {
-  const PairTerms t = pair_terms(rb, ra, cb, ca);
-  const int ib = __float_as_int(t.inter);
-  const int d_hi = __float_as_int(__fmul_rn(T.thr_hi, t.uni)) - ib;      // < 0  <=>  inter >  thr_hi * u
-  const int d_lo = __float_as_int(__fmul_rn(T.thr_lo, t.uni)) - ib - 1;  // < 0  <=>  inter >= thr_lo * u
-  sub = __funnelshift_l((uint32_t)d_hi, sub, 1);
-  sup = __funnelshift_l((uint32_t)d_lo, sup, 1);
+// Conservative filter, one mask per word.  IoU >= thr  <=>  inter >= (thr / (1 + thr)) * (area_a + area_b) in exact
+// arithmetic; the reference's three roundings (the sum, the subtraction, the division) move that boundary by less than
+// 2^-22 relative, so  inter < c_lo * fl(area_a + area_b)  with c_lo = thr/(1+thr) * (1 - 2^-19) proves "not suppressed"
+// (inter and the sum are computed with the reference's own operations).  Everything else -- the true hits and the
+// pairs within 2^-19 of the threshold, well under 1 % of the pairs -- is decided by the reference's arithmetic
+// including the IEEE division.  The compare is an integer subtraction whose sign bit is funnel-shifted into the mask
+// (every operand is a non-negative finite float in a regular episode, so float order = bit-pattern order); bits
+// arrive MSB-first and are reversed per 32 pairs.  13 + 3 instructions per pair instead of 13 + 7 for two masks.
+__device__ __forceinline__ void pair_bit(const float4& rb, float ra, const float4& cb, float ca, const IouTest& T,
+                                         uint32_t& sup) {
+  const float xx1 = fmaxf(rb.x, cb.x), yy1 = fmaxf(rb.y, cb.y);
+  const float xx2 = fminf(rb.z, cb.z), yy2 = fminf(rb.w, cb.w);
+  const float w = fmaxf(__fadd_rn(__fsub_rn(xx2, xx1), 1.0f), 0.0f);
+  const float h = fmaxf(__fadd_rn(__fsub_rn(yy2, yy1), 1.0f), 0.0f);
+  const float inter = __fmul_rn(w, h);
+  const float sum = __fadd_rn(ra, ca);
+  const int d = __float_as_int(__fmul_rn(T.c_lo, sum)) - __float_as_int(inter) - 1;   // < 0  <=>  inter >= c_lo * sum
+  sup = __funnelshift_l((uint32_t)d, sup, 1);
 }
 
 __device__ __forceinline__ u64 row_word_fast(const float4& rb, float ra, const float4* __restrict__ cb,
                                              const float* __restrict__ ca, const IouTest& T) {
-  uint32_t sub_lo = 0, sub_hi = 0, sup_lo = 0, sup_hi = 0;
+  uint32_t sup_lo = 0, sup_hi = 0;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) pair_bits(rb, ra, cb[j], ca[j], T, sub_lo, sup_lo);
+  for (int j = 0; j < 32; ++j) pair_bit(rb, ra, cb[j], ca[j], T, sup_lo);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) pair_bits(rb, ra, cb[32 + j], ca[32 + j], T, sub_hi, sup_hi);
-  u64 sub = ((u64)__brev(sub_hi) << 32) | __brev(sub_lo);
-  u64 amb = (((u64)__brev(sup_hi) << 32) | __brev(sup_lo)) & ~sub;
-  while (amb) {  // rare: IoU within 2^-18 of the threshold -> decide with the IEEE division
-    const int j = __ffsll((long long)amb) - 1;
-    amb &= amb - 1ull;
+  for (int j = 0; j < 32; ++j) pair_bit(rb, ra, cb[32 + j], ca[32 + j], T, sup_hi);
+  u64 cand = ((u64)__brev(sup_hi) << 32) | __brev(sup_lo);
+  u64 sub = 0ull;
+  while (cand) {  // the candidates: decide with the reference's arithmetic (IEEE division)
+    const int j = __ffsll((long long)cand) - 1;
+    cand &= cand - 1ull;
     const PairTerms t = pair_terms(rb, ra, cb[j], ca[j]);
     const float q = __fdiv_rn(t.inter, t.uni);
     if (T.strict ? (q > T.thr) : (q >= T.thr)) sub |= (1ull << j);
@@ -841,6 +848,7 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
     M.test.force_exact = !(P.thr > 0.0f && std::isfinite(P.thr));
     M.test.thr_lo = (float)((double)P.thr * (1.0 - 1.0 / 524288.0));
     M.test.thr_hi = (float)((double)P.thr * (1.0 + 1.0 / 524288.0));
+    M.test.c_lo = (float)((double)P.thr / (1.0 + (double)P.thr) * (1.0 - 1.0 / 524288.0));
     const int NPu = (int)align_up((size_t)(max_len > 0 ? max_len : 1), 64);
     const bool early = P.early_exit && P.post_top_n > 0;
     S.stop = early ? P.post_top_n + 1 : INT_MAX;
