@@ -14,6 +14,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """Make sure the product library (and the thin torch extension) are built and current -- a no-op when the built
+    files that travel with the tree are up to date.  A failure here is not swallowed: the product has no fallback."""
+    from oneshotdet_b200 import build as osd_build
+
+    osd_build.build()
+    osd_build.build_torch_extension()
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch
