@@ -5,7 +5,6 @@ Tolerances: boxes are single IEEE add/sub/clamp of identical fp32 inputs -> bit-
 sigmoid; the device's expf and ATen's (Sleef) differ by a few ulp, so scores are compared with rtol 2e-6
 (written below) and the NMS stage is checked bit-exactly *at the NMS boundary*: the oracle is fed the very
 candidates the GPU produced and must return identical indices and counts."""
-import os
 
 import numpy as np
 import pytest
