@@ -17,6 +17,8 @@ What is executed (paths relative to /root/reference):
 
   * modeling/poolers.py:93-125 with layers/roi_align.py  Pooler.forward + LevelMapper                         -> pooler_*.npz
 
+  * modeling/roi_heads/box_head/box_head.py:81-257  ROIBoxHead.forward at eval (pooler, compress_dim_conv,
+    feature_aggreg, fc6/fc7, FPNPredictor, PostProcessor), config from config/defaults.py                   -> box_head_*.npz
   * layers/scale.py + torch.exp as in modeling/rpn/fcos/fcos.py:95-97                                       -> fcos_head_tail.npz
   * structures/bounding_box.py:55-127 (BoxList.resize / convert) inside the loop body of
     data/datasets/evaluation/coco/coco_eval.py:137-165                                                      -> coco_*.npz
@@ -277,6 +279,76 @@ def coco_case(name, image_sizes_wh, orig_sizes_wh, counts, seed):
     print(f"coco_{name}.npz:", len(coco_results), "records,", len(text), "bytes of JSON")
 
 
+def box_head_case(name="c64", batch=2, rois=24, channels=64, height=256, width=320, seed=101):
+    """The reference's whole second stage, executed: ROIBoxHead.forward at eval
+    (modeling/roi_heads/box_head/box_head.py:81-257) = FPN2ROIFeatureExtractor (Pooler) -> cat with the expanded support
+    -> compress_dim_conv -> feature_aggreg -> fc6 -> fc7 -> FPNPredictor -> PostProcessor.  Built from the reference's own
+    config defaults (a stub replaces the missing yacs package) with the shipped yaml's ROI_BOX_HEAD settings, 64 channels
+    and MLP_HEAD_DIM 64 to keep the fixture small.  Every stage's output is recorded through forward hooks."""
+    sys.path.insert(0, os.path.join(HERE, "_stubs"))
+    from maskrcnn_benchmark.config import cfg as ref_cfg  # noqa: PLC0415
+    from maskrcnn_benchmark.modeling.roi_heads.box_head.box_head import ROIBoxHead  # noqa: PLC0415
+    from maskrcnn_benchmark.structures.bounding_box import BoxList  # noqa: PLC0415
+
+    cfg = ref_cfg.clone()
+    cfg.merge_from_list(["MODEL.DEVICE", "cpu", "MODEL.ROI_HEADS.USE_FPN", True,
+                         "MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION", 7,
+                         "MODEL.ROI_BOX_HEAD.POOLER_SCALES", (0.125, 0.0625, 0.03125, 0.015625, 0.0078125),
+                         "MODEL.ROI_BOX_HEAD.POOLER_SAMPLING_RATIO", 2,
+                         "MODEL.ROI_BOX_HEAD.FEATURE_EXTRACTOR", "FPN2ROIFeatureExtractor",
+                         "MODEL.ROI_BOX_HEAD.PREDICTOR", "FPNPredictor", "MODEL.ROI_BOX_HEAD.NUM_CLASSES", 2,
+                         "MODEL.ROI_BOX_HEAD.MLP_HEAD_DIM", 64,
+                         "FEW_SHOT.SECOND_STAGE_METHOD", "concat", "FEW_SHOT.POOLING", "ROI"])
+    assert cfg.FEW_SHOT.SECOND_STAGE_CLS_LOSS == "ce_loss" and not cfg.FEW_SHOT.NEG_SUPPORT.TURN_ON
+    torch.manual_seed(seed)
+    head = ROIBoxHead(cfg, channels).eval()
+    with torch.no_grad():   # exercise the affine terms and the biases
+        for m in head.modules():
+            if isinstance(m, torch.nn.GroupNorm):
+                torch.nn.init.normal_(m.weight, mean=1.0, std=0.1)
+                torch.nn.init.normal_(m.bias, std=0.1)
+        torch.nn.init.normal_(head.predictor.cls_score.bias, std=0.5)
+    image_sizes = [(height - 6, width), (height, width - 20)][:batch]
+    feats, _ = orc.synth_features(batch, 1, channels, height, width, seed)
+    boxes_t = orc.synth_rois(batch, rois, image_sizes, seed + 1, lo=24.0)
+    proposals = [BoxList(boxes_t[i].clone(), (int(image_sizes[i][1]), int(image_sizes[i][0])), mode="xyxy") for i in range(batch)]
+    g = torch.Generator().manual_seed(seed + 2)
+    supp = torch.randn((batch, 1, channels, 7, 7), generator=g)
+    target_ids = [3 + i for i in range(batch)]
+    taps = {}
+
+    def tap(key):
+        def hook(_m, _inp, out):
+            taps[key] = [o.detach().clone() for o in out] if isinstance(out, tuple) else out.detach().clone()
+        return hook
+
+    head.feature_extractor.register_forward_hook(tap("pooled"))
+    head.compress_dim_conv.register_forward_hook(tap("compressed"))
+    head.feature_aggreg.register_forward_hook(tap("aggregated"))
+    head.fc7.register_forward_hook(tap("fc7"))
+    head.predictor.register_forward_hook(tap("predictor"))
+    with torch.no_grad():
+        _x, result, _ = head(tuple(feats), proposals, features_supp_roipooled=supp, target_ids=target_ids)
+    data = {"batch": batch, "rois": rois, "channels": channels, "height": height, "width": width, "seed": seed,
+            "image_sizes": np.asarray(image_sizes, dtype=np.int64), "boxes": boxes_t.numpy(), "supp": supp.numpy(),
+            "target_ids": np.asarray(target_ids, dtype=np.int64),
+            "pooled": taps["pooled"].numpy(), "compressed": taps["compressed"].numpy(),
+            "aggregated": taps["aggregated"].numpy(), "fc7_pre_relu": taps["fc7"].numpy(),
+            "class_logits": taps["predictor"][0].numpy(), "box_regression": taps["predictor"][1].numpy(),
+            "params": np.asarray([cfg.MODEL.ROI_HEADS.SCORE_THRESH, cfg.MODEL.ROI_HEADS.NMS,
+                                  cfg.MODEL.ROI_HEADS.DETECTIONS_PER_IMG], dtype=np.float64),
+            "weights": np.asarray(cfg.MODEL.ROI_HEADS.BBOX_REG_WEIGHTS, dtype=np.float64)}
+    for k, v in head.state_dict().items():
+        data["w_" + k] = v.numpy()
+    for i, bl in enumerate(result):
+        data[f"out_boxes{i}"] = bl.bbox.numpy().astype(np.float32)
+        data[f"out_scores{i}"] = bl.get_field("scores").numpy().astype(np.float32)
+        data[f"out_labels{i}"] = bl.get_field("labels").numpy().astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, f"box_head_{name}.npz"), **data)
+    print(f"box_head_{name}.npz:", [len(b) for b in result], "detections;",
+          {k: tuple(v.shape) for k, v in data.items() if k in ("pooled", "compressed", "aggregated", "class_logits")})
+
+
 def head_tail_case():
     """The tail of FCOSHead.forward for the regression branch (modeling/rpn/fcos/fcos.py:95-97): the reference's own
     Scale module (layers/scale.py) and torch.exp, executed on seeded raw bbox_pred maps."""
@@ -306,6 +378,9 @@ def main():
     if "--only-box-post" in sys.argv:
         box_post_cases()
         return
+    if "--only-box-head" in sys.argv:
+        box_head_case()
+        return
     if "--only-head-tail" in sys.argv:
         head_tail_case()
         return
@@ -328,6 +403,7 @@ def main():
     pooler_cases()
     coco_cases()
     head_tail_case()
+    box_head_case()
 
 
 if __name__ == "__main__":
