@@ -20,7 +20,12 @@ def pytest_sessionstart(session):
     from oneshotdet_b200 import build as osd_build
 
     osd_build.build()
-    osd_build.build_torch_extension()
+    try:   # the thin torch extension is a second binding of the same kernels; its own tests skip when it is absent
+        osd_build.build_torch_extension()
+    except Exception as exc:  # noqa: BLE001
+        import warnings
+
+        warnings.warn(f"oneshotdet_b200._C_torch could not be built: {exc}")
 
 
 def pytest_collection_modifyitems(config, items):
