@@ -22,6 +22,7 @@ import argparse
 import json
 import os
 import statistics
+import subprocess
 import sys
 import threading
 import time
@@ -73,14 +74,14 @@ def fill_inputs(pipe, seed):
 # post-processing restated with the same ATen ops (oracle) + the reference's own nms_cpu when it was compiled
 # ------------------------------------------------------------------------------------------------------
 class CpuReference:
-    def __init__(self, episodes=1, seed=7):
+    def __init__(self, episodes=1, seed=7, threads=None):
         import torch
 
         from oracle import build_ref
         from oracle import oracle as orc
 
         self.orc, self.torch = orc, torch
-        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_num_threads(threads or os.cpu_count() or 1)
         self.cores = torch.get_num_threads()
         ref = None
         try:
@@ -117,6 +118,40 @@ class CpuReference:
                 f"construction (no OpenMP)")
 
 
+def cpu_multi_process_throughput(processes=None, timed_steps=2):
+    """The same CPU path run as `processes` independent single-threaded workers (one episode stream each) -- what the host
+    cores deliver when the reference's per-image loop is data-parallelised over processes, since its nms_cpu cannot use a
+    second thread.  Every worker is this script with --ref-worker; the aggregate rate is the sum of the workers' rates
+    (they overlap for the whole timed part: all start by importing torch and running one warm-up step)."""
+    processes = processes or (os.cpu_count() or 1)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--ref-worker", str(100 + i), "--steps",
+                               str(timed_steps)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env)
+             for i in range(processes)]
+    rate, ok = 0.0, 0
+    for pr in procs:
+        try:
+            out, _ = pr.communicate(timeout=300)
+            rate += float(out.strip().splitlines()[-1])
+            ok += 1
+        except Exception:  # noqa: BLE001  (a worker that died only lowers the reported rate)
+            pr.kill()
+    return {"value": rate, "unit": UNIT, "processes": ok, "threads_per_process": 1,
+            "what": "independent single-threaded workers, one episode per step each; sum of the workers' rates"}
+
+
+def run_ref_worker(seed, steps):
+    ref = CpuReference(episodes=1, seed=seed, threads=1)
+    ref.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref.step()
+    print(steps * ref.episodes / (time.perf_counter() - t0), flush=True)
+    return 0
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -139,7 +174,8 @@ def run_reference_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
-                             "sample": ref.sample_text()},
+                             "sample": ref.sample_text(),
+                             "multi_process": None if args.no_multi_process else cpu_multi_process_throughput()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -421,7 +457,8 @@ def run_b200_arm(args):
         ref.step()
         ts = [sum(ref.step()) for _ in range(4)]
         cpu = {"value": ref.episodes / statistics.median(ts), "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
-               "sample": ref.sample_text() + f"; median of 4 steps, {statistics.median(ts):.3f} s/episode"}
+               "sample": ref.sample_text() + f"; median of 4 steps, {statistics.median(ts):.3f} s/episode",
+               "multi_process": None if args.no_multi_process else cpu_multi_process_throughput()}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
@@ -446,6 +483,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-multi-process", action="store_true",
+                    help="skip the multi-process variant of the CPU baseline (cpu_baseline.multi_process)")
+    ap.add_argument("--ref-worker", type=int, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--no-fusion", action="store_true")
     ap.add_argument("--serial", action="store_true", help="one stream: matching then post-processing, no overlap")
     ap.add_argument("--gather", choices=["block", "packed", "none"], default="block",
@@ -455,6 +495,8 @@ def main():
                     help="N>1: steps per NCCL all-gather of the detections (1 = every step)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
+    if args.ref_worker is not None:
+        return run_ref_worker(args.ref_worker, max(1, args.steps))
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_b200_arm(args)
