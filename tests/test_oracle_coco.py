@@ -54,3 +54,20 @@ def test_writer_reports_bad_arguments(tmp_path):
         write_coco_json(np.zeros((1, 5), np.float32), np.array([3], np.int32), [0], [1], tmp_path / "x.json")
     with pytest.raises(RuntimeError, match="cannot open"):
         write_coco_json(np.zeros((1, 5), np.float32), np.array([0], np.int32), [0], [1], tmp_path / "no" / "dir" / "x.json")
+
+
+def test_native_writer_on_random_float32_bit_patterns(tmp_path):
+    """Every finite float32 must print exactly as CPython's repr of the widened double: 100 000 random bit patterns
+    (normals of every exponent, denormals, both signs); 1 M were checked once by hand."""
+    from oneshotdet_b200.evaluation import write_coco_json
+
+    rng = np.random.RandomState(321)
+    vals = rng.randint(0, 2 ** 32, size=100_000, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    vals = vals[np.isfinite(vals)]
+    n = len(vals) // 5
+    rec = vals[:n * 5].reshape(n, 5).copy()
+    path = tmp_path / "fuzz.json"
+    write_coco_json(rec, np.zeros(n, np.int32), [1], [2], path)
+    want = orc.coco_results_json([{"image_id": 1, "category_id": 2, "bbox": [float(x) for x in r[:4]], "score": float(r[4])}
+                                  for r in rec])
+    assert path.read_text() == want
