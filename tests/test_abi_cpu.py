@@ -140,3 +140,23 @@ def test_second_stage_and_handoff_entry_points_validate_without_a_gpu(lib, tmp_p
     import json
 
     assert json.load(open(path)) == [{"bbox": [1.5, 2.0, 3.25, 4.0], "category_id": 7, "image_id": 42, "score": 0.5}]
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/osd_b200.h compiles as C99 and a C program links libosd_b200.so and uses the GPU-free entry points."""
+    import json
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    src = os.path.join(ROOT, "tests", "c", "abi_smoke.c")
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.join(ROOT, "oneshotdet_b200", "lib")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                        "-L", libdir, "-losd_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = str(tmp_path / "r.json")
+    r = subprocess.run([exe, out], capture_output=True, text=True)
+    assert r.returncode == 0 and "c-abi ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+    assert json.load(open(out)) == [{"bbox": [1.5, 2.0, 3.25, 4.0], "category_id": 3, "image_id": 7, "score": 0.10000000149011612}]
