@@ -7,6 +7,8 @@ What is executed (paths relative to /root/reference):
                                                         ``maskrcnn_benchmark._C`` before anything imports it
   * tests/test_nms.py                                   the reference's own known-answer tests; their inputs and
                                                         expected indices are recorded into nms_kat.json
+  * tests/test_box_coder.py                             the reference's known-answer vector for BoxCoder.decode
+                                                        (modeling/box_coder.py:52-95)          -> box_coder_kat.json
   * maskrcnn_benchmark/modeling/rpn/fcos/inference.py   FCOSPostProcessor.forward            -> fcos_post_*.npz
   * maskrcnn_benchmark/modeling/rpn/fcos/fcos.py        FCOSModule.compute_locations_per_level (unbound) -> same
   * modeling/detector/generalized_rcnn.py:100-104,306-311   batch_pooling + product expression -> match_*.npz
@@ -349,6 +351,40 @@ def box_head_case(name="c64", batch=2, rois=24, channels=64, height=256, width=3
           {k: tuple(v.shape) for k, v in data.items() if k in ("pooled", "compressed", "aggregated", "class_logits")})
 
 
+def record_box_coder_kat():
+    """Run the reference's tests/test_box_coder.py (its own known-answer vector for BoxCoder.decode) with a recording
+    shim around the reference decode."""
+    import importlib  # noqa: PLC0415
+
+    from maskrcnn_benchmark.modeling import box_coder as ref_bc  # noqa: PLC0415
+
+    calls = []
+    orig = ref_bc.BoxCoder.decode
+
+    def recording_decode(self, rel_codes, boxes):
+        out = orig(self, rel_codes, boxes)
+        calls.append({"weights": [float(w) for w in self.weights], "deltas": rel_codes.numpy().astype(np.float32).tolist(),
+                      "boxes": boxes.numpy().astype(np.float32).tolist(), "decoded": out.numpy().astype(np.float32).tolist()})
+        return out
+
+    ref_bc.BoxCoder.decode = recording_decode
+    sys.path.insert(0, os.path.join(REF, "tests"))
+    mod = importlib.import_module("test_box_coder")
+    result = unittest.TextTestRunner(verbosity=0).run(unittest.defaultTestLoader.loadTestsFromModule(mod))
+    ref_bc.BoxCoder.decode = orig
+    assert result.wasSuccessful() and calls, "reference test_box_coder.py failed against its own BoxCoder"
+    # the test's own expected values (it asserts |decoded - gt| <= 1e-4): keep them next to what the reference computed
+    import re  # noqa: PLC0415
+
+    src = open(os.path.join(REF, "tests", "test_box_coder.py")).read()
+    gt_block = src[src.index("gt_bbox = ("):src.index("results = box_coder.decode")]
+    gt = [float(v) for v in re.findall(r"-?\d+\.\d+", gt_block)]
+    calls[0]["expected_by_the_test"] = np.asarray(gt, np.float32).reshape(-1, 4).tolist()
+    with open(os.path.join(HERE, "box_coder_kat.json"), "w") as f:
+        json.dump({"source": "tests/test_box_coder.py (TestBoxCoder.test_box_decoder, atol 1e-4)", "cases": calls}, f)
+    print("box_coder_kat.json:", len(calls), "case(s)")
+
+
 def head_tail_case():
     """The tail of FCOSHead.forward for the regression branch (modeling/rpn/fcos/fcos.py:95-97): the reference's own
     Scale module (layers/scale.py) and torch.exp, executed on seeded raw bbox_pred maps."""
@@ -378,6 +414,9 @@ def main():
     if "--only-box-post" in sys.argv:
         box_post_cases()
         return
+    if "--only-box-coder" in sys.argv:
+        record_box_coder_kat()
+        return
     if "--only-box-head" in sys.argv:
         box_head_case()
         return
@@ -404,6 +443,7 @@ def main():
     coco_cases()
     head_tail_case()
     box_head_case()
+    record_box_coder_kat()
 
 
 if __name__ == "__main__":

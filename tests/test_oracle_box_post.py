@@ -59,3 +59,18 @@ def test_roi_count_limits_rows():
     np.testing.assert_array_equal(full[0][0], part[0][0])
     assert part[1][0].shape[0] == 17
     np.testing.assert_array_equal(full[1][0][:17], part[1][0])
+
+
+def test_box_decode_against_the_reference_known_answer(golden_dir):
+    """tests/test_box_coder.py of the reference (its own KAT, atol 1e-4), recorded by running it against the reference's
+    BoxCoder: the restatement must equal what the reference computed bit for bit and satisfy the test's expectation."""
+    import json
+
+    with open(os.path.join(golden_dir, "box_coder_kat.json")) as f:
+        cases = json.load(f)["cases"]
+    assert cases
+    for c in cases:
+        out = orc.box_decode(torch.tensor(c["deltas"], dtype=torch.float32), torch.tensor(c["boxes"], dtype=torch.float32),
+                             tuple(c["weights"])).numpy()
+        np.testing.assert_array_equal(out, np.asarray(c["decoded"], dtype=np.float32))
+        np.testing.assert_allclose(out, np.asarray(c["expected_by_the_test"], dtype=np.float32), atol=1e-4)
