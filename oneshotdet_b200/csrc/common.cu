@@ -1,6 +1,7 @@
 // Error plumbing, version and device checks of libosd_b200.so.
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -49,6 +50,35 @@ void timeline_mark(const char* name, cudaStream_t stream) {
   cudaEventRecord(ev, stream);
   std::lock_guard<std::mutex> lock(g_tl_mutex);
   g_marks.push_back({name, ev});
+}
+
+namespace {
+std::mutex g_attr_mutex;
+std::map<std::pair<int, const void*>, size_t> g_smem_set;
+std::map<std::pair<int, const void*>, bool> g_carveout_set;
+}  // namespace
+
+int ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  int dev = 0;
+  OSD_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  auto key = std::make_pair(dev, kernel);
+  auto it = g_smem_set.find(key);
+  if (it != g_smem_set.end() && it->second >= bytes) return OSD_OK;
+  OSD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  g_smem_set[key] = bytes;
+  return OSD_OK;
+}
+
+int ensure_max_shared_carveout(const void* kernel) {
+  int dev = 0;
+  OSD_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  auto key = std::make_pair(dev, kernel);
+  if (g_carveout_set.count(key)) return OSD_OK;
+  OSD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  g_carveout_set[key] = true;
+  return OSD_OK;
 }
 
 }  // namespace osd

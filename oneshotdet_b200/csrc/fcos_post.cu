@@ -471,19 +471,11 @@ extern "C" int osd_fcos_postprocess(const osd_fcos_config* cfg, const float* con
 
   const size_t smem = (size_t)3 * kRadixBins * sizeof(int) + (size_t)max_slice * sizeof(uint32_t);
   {
-    static thread_local size_t configured = 48 * 1024;
-    if (smem > configured) {
-      const size_t cap_bytes = (size_t)3 * kRadixBins * sizeof(int) + (size_t)kMaxSlice * sizeof(uint32_t);
-      OSD_CUDA(cudaFuncSetAttribute(fcos_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap_bytes));
-      configured = cap_bytes;
-    }
-  }
-  {
-    static thread_local bool carveout_set = false;
-    if (!carveout_set) {
-      OSD_CUDA(prefer_max_shared_carveout(fcos_select_kernel));
-      carveout_set = true;
-    }
+    const size_t cap_bytes = (size_t)3 * kRadixBins * sizeof(int) + (size_t)kMaxSlice * sizeof(uint32_t);
+    int rc2 = ensure_dynamic_smem(reinterpret_cast<const void*>(fcos_select_kernel), cap_bytes);
+    if (rc2 != OSD_OK) return rc2;
+    rc2 = ensure_max_shared_carveout(reinterpret_cast<const void*>(fcos_select_kernel));
+    if (rc2 != OSD_OK) return rc2;
   }
   // cluster of kCl CTAs along x per (level, episode); __cluster_dims__ on the kernel makes <<<>>> launch clusters
   dim3 grid((unsigned)kCl, (unsigned)cfg->num_levels, (unsigned)cfg->batch);

@@ -26,6 +26,8 @@
 
 #include "osd_common.cuh"
 #include "osd_device_utils.cuh"
+#include "osd_tc.cuh"
+#include "fusion_internal.cuh"
 
 namespace osd {
 namespace {
@@ -39,119 +41,8 @@ constexpr int kTmaWarp = 16, kMmaWarp = 17;
 constexpr int kThreads = 32 * 18;
 constexpr int kStageBytesPerWarp = 4096;              // epilogue transpose buffer: 32 rows x 32 fp32
 constexpr int kMaxStages = 4;
-constexpr uint32_t kSpinLimit = 1u << 26;  // a lost arrival traps instead of hanging the GPU
 
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > kSpinLimit) __trap();
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem] . B[smem], bf16 x bf16 -> fp32, issued by one thread
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on an mbarrier when every MMA issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (thread = TMEM lane)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor (sm_100 format, cf. cute/arch/mma_sm100_desc.hpp SmemDescriptor):
-//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |
-//   [46,48) version = 1 | [61,64) layout type (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= 1ull << 46;
-  d |= 2ull << 61;
-  return d;
-}
-
-// Instruction descriptor for kind::f16 (cute/arch/mma_sm100_desc.hpp InstrDescriptor):
-//   [4,6) D format (1 = F32) | [7,10) A format (1 = BF16) | [10,13) B format (1 = BF16) | 15 A major (0 = K) |
-//   16 B major (1 = MN) | [17,23) N >> 3 | [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(m >> 4) << 24);
-}
+using namespace tc;
 
 // ------------------------------------------------------------------------------------------------
 // kernel arguments
@@ -205,10 +96,6 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvArgs& A, int tile) {
   return t;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&v);
-}
 
 // ------------------------------------------------------------------------------------------------
 // the GEMM kernel
@@ -516,6 +403,7 @@ struct CoefArgs {
   const double* stats;  // [nl, B, 32, 2]
   const float* gn_w;
   const float* gn_b;
+  const float* fold_bias;  // [nl, B, C] or nullptr: bias the consumer adds before normalising, absorbed into the shift
   float2* coef;         // [nl, B, C]
   int hw[OSD_MAX_LEVELS];
 };
@@ -530,7 +418,9 @@ __global__ void __launch_bounds__(512) fusion_gn_coef_kernel(CoefArgs A) {
     const double var = fmax(st[1] * inv_cnt - mean * mean, 0.0);
     const float rstd = (float)(1.0 / sqrt(var + (double)A.eps));
     const float sc = A.gn_w[c] * rstd;
-    A.coef[((size_t)l * A.B + b) * A.C + c] = make_float2(sc, A.gn_b[c] - (float)mean * sc);
+    float sh = A.gn_b[c] - (float)mean * sc;
+    if (A.fold_bias) sh = fmaf(A.fold_bias[((size_t)l * A.B + b) * A.C + c], sc, sh);
+    A.coef[((size_t)l * A.B + b) * A.C + c] = make_float2(sc, sh);
   }
 }
 
@@ -603,9 +493,7 @@ __global__ void __launch_bounds__(kGnThreads, 5) fusion_gn_lrelu_kernel(GnArgs A
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+}  // namespace
 
 int get_encode_fn(EncodeTiledFn* out) {
   static EncodeTiledFn fn = nullptr;
@@ -623,17 +511,16 @@ int get_encode_fn(EncodeTiledFn* out) {
   return OSD_OK;
 }
 
-// bf16 weights [rows, cols] row-major -> 2-D tensor map, box = 64 (K) x 128 (rows), 128-byte swizzle;
-// rows past the end (Cout < 128) are zero-filled by the TMA unit
-int make_weight_map(const void* w, int rows, int cols, CUtensorMap* map) {
+int make_bf16_map(const void* base, int64_t rows, int64_t cols, int64_t pitch_elems, int box_cols, int box_rows,
+                  CUtensorMap* map) {
   EncodeTiledFn fn;
   int rc = get_encode_fn(&fn);
   if (rc != OSD_OK) return rc;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kUmmaM};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstride, box, estr,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -641,6 +528,14 @@ int make_weight_map(const void* w, int rows, int cols, CUtensorMap* map) {
     return OSD_ERR_CUDA;
   }
   return OSD_OK;
+}
+
+namespace {
+
+// bf16 weights [rows, cols] row-major -> 2-D tensor map, box = 64 (K) x 128 (rows), 128-byte swizzle;
+// rows past the end (Cout < 128) are zero-filled by the TMA unit
+int make_weight_map(const void* w, int rows, int cols, CUtensorMap* map) {
+  return make_bf16_map(w, rows, cols, cols, kBlockK, kUmmaM, map);
 }
 
 struct ConvPlan {
@@ -689,11 +584,8 @@ int launch_conv(const CUtensorMap& map, ConvArgs& A, cudaStream_t stream) {
   A.stages = p.stages;
   A.num_mt = (A.Cout + kUmmaM - 1) / kUmmaM;
   A.num_kc = A.Cin / kBlockK;
-  static thread_local size_t configured = 0;
-  if (p.smem > configured) {
-    OSD_CUDA(cudaFuncSetAttribute(conv1x1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = 227 * 1024;
-  }
+  rc = ensure_dynamic_smem(reinterpret_cast<const void*>(conv1x1_tc_kernel), 227 * 1024);
+  if (rc != OSD_OK) return rc;
   if (A.total_tiles <= 0) return OSD_OK;
   const int grid = A.total_tiles < kNumSMs ? A.total_tiles : kNumSMs;
   OutMaps om;
@@ -712,23 +604,61 @@ int launch_conv(const CUtensorMap& map, ConvArgs& A, cudaStream_t stream) {
 }
 
 }  // namespace
+
+int fusion_launch_gn_coef(int nl, int B, int C, float eps, const double* stats, const float* gn_w, const float* gn_b,
+                          const float* fold_bias, float2* coef, const int32_t* hw, cudaStream_t stream) {
+  CoefArgs K{};
+  K.nl = nl; K.B = B; K.C = C; K.eps = eps; K.stats = stats; K.gn_w = gn_w; K.gn_b = gn_b; K.fold_bias = fold_bias;
+  K.coef = coef;
+  for (int l = 0; l < nl; ++l) K.hw[l] = hw[l];
+  fusion_gn_coef_kernel<<<nl * B, 512, 0, stream>>>(K);
+  OSD_LAUNCH_CHECK("fusion_gn_coef_kernel");
+  return OSD_OK;
+}
+
+int fusion_launch_gn_lrelu(int nl, int B, int C, float slope, float* const* y, const float2* coef, const int32_t* hw,
+                           cudaStream_t stream) {
+  GnArgs G{};
+  G.nl = nl; G.slope = slope;
+  uint64_t chunks = 0;
+  for (int l = 0; l < nl; ++l) {
+    GnLevel& L = G.lv[l];
+    L.y = y[l];
+    L.coef = coef + (size_t)l * B * C;
+    L.hw = (uint32_t)hw[l];
+    L.elems = (uint32_t)((size_t)B * C * hw[l]);
+    L.chunk_begin = (uint32_t)chunks;
+    L.div_hw = make_fastdiv(L.hw);
+    chunks += ((uint64_t)L.elems + 4ull * kGnChunk - 1) / (4ull * kGnChunk);
+  }
+  G.total_chunks = (uint32_t)chunks;
+  const int ctas = (int)std::min<uint64_t>(chunks, (uint64_t)kNumSMs * 16);
+  if (ctas > 0) {
+    fusion_gn_lrelu_kernel<<<ctas, kGnThreads, 0, stream>>>(G);
+    OSD_LAUNCH_CHECK("fusion_gn_lrelu_kernel");
+  }
+  return OSD_OK;
+}
+
 }  // namespace osd
 
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
-static size_t fusion_carve(const osd_fusion_desc* d, osd::Carver& c, float** y1, double** stats1, double** stats2,
-                           float** bias_eff, float2** coef1 = nullptr, float2** coef2 = nullptr) {
-  size_t elems = 0;
-  for (int l = 0; l < d->num_levels; ++l) elems += (size_t)d->batch * 2 * d->channels * d->hw[l];
-  *stats1 = c.take<double>((size_t)d->num_levels * d->batch * 64);
-  *stats2 = c.take<double>((size_t)d->num_levels * d->batch * 64);
-  *bias_eff = c.take<float>((size_t)d->num_levels * d->batch * 2 * d->channels);
-  float2* k1 = c.take<float2>((size_t)d->num_levels * d->batch * 2 * d->channels);
-  float2* k2 = c.take<float2>((size_t)d->num_levels * d->batch * d->channels);
-  if (coef1) *coef1 = k1;
-  if (coef2) *coef2 = k2;
-  *y1 = d->stage == OSD_FUSION_CONV1 ? nullptr : c.take<float>(elems);
+static size_t fusion_carve(const osd_fusion_desc* d, osd::Carver& c, osd::FusionWorkspace* ws) {
+  const size_t per = (size_t)d->num_levels * d->batch;
+  ws->stats1 = c.take<double>(per * 64);
+  ws->stats2 = c.take<double>(per * 64);
+  ws->bias_eff = c.take<float>(per * 2 * d->channels);
+  ws->coef1 = c.take<float2>(per * 2 * d->channels);
+  ws->coef2 = c.take<float2>(per * d->channels);
+  ws->xb = nullptr;
+  if (d->stage == OSD_FUSION_FULL) {
+    size_t elems = 0;
+    for (int l = 0; l < d->num_levels; ++l)
+      elems += (size_t)d->batch * d->channels * (size_t)osd::fusion_xb_pitch(d->hw[l]);
+    ws->xb = c.take<uint16_t>(elems);
+  }
   return c.total();
 }
 
@@ -751,9 +681,8 @@ extern "C" int osd_fusion_workspace_bytes(const osd_fusion_desc* d, size_t* byte
   if (rc != OSD_OK) return rc;
   OSD_REQUIRE(bytes != nullptr, "osd_fusion_workspace_bytes: bytes is null");
   osd::Carver c(nullptr);
-  float *y1, *be;
-  double *s1, *s2;
-  *bytes = fusion_carve(d, c, &y1, &s1, &s2, &be);
+  osd::FusionWorkspace ws;
+  *bytes = fusion_carve(d, c, &ws);
   return OSD_OK;
 }
 
@@ -766,10 +695,8 @@ extern "C" int osd_fusion_forward(const osd_fusion_desc* d, void* workspace, siz
   OSD_REQUIRE(d->w1x_bf16 && d->w1s_t && d->b1, "osd_fusion_forward: conv1 weights are null");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   Carver c(workspace);
-  float *y1, *bias_eff;
-  double *stats1, *stats2;
-  float2 *coef1, *coef2;
-  const size_t need = fusion_carve(d, c, &y1, &stats1, &stats2, &bias_eff, &coef1, &coef2);
+  FusionWorkspace ws;
+  const size_t need = fusion_carve(d, c, &ws);
   if (need > workspace_bytes) {
     set_error("osd_fusion_forward: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
     return OSD_ERR_WORKSPACE;
@@ -778,97 +705,38 @@ extern "C" int osd_fusion_forward(const osd_fusion_desc* d, void* workspace, siz
   const bool full = d->stage == OSD_FUSION_FULL;
   if (full)
     OSD_REQUIRE(d->w2_bf16 && d->b2 && d->gn1_w && d->gn1_b && d->gn2_w && d->gn2_b, "osd_fusion_forward: conv2 / GroupNorm parameters are null");
-  OSD_CUDA(cudaMemsetAsync(stats1, 0, sizeof(double) * (size_t)nl * B * 64, stream));
-  OSD_CUDA(cudaMemsetAsync(stats2, 0, sizeof(double) * (size_t)nl * B * 64, stream));
 
-  // ---- folded bias
+  // ---- folded bias: W1s . mean_s(support) + b1 per (level, episode)
   BiasArgs BA{};
   BA.nl = nl; BA.B = B; BA.S = d->shots; BA.C = C; BA.Cout = C2;
   for (int l = 0; l < nl; ++l) {
     OSD_REQUIRE(d->feat[l] && d->supp[l] && d->out[l], "osd_fusion_forward: null pointer at level %d", l);
     BA.supp[l] = static_cast<const float*>(d->supp[l]);
   }
-  BA.w1s_t = d->w1s_t; BA.b1 = d->b1; BA.bias_eff = bias_eff;
+  BA.w1s_t = d->w1s_t; BA.b1 = d->b1; BA.bias_eff = ws.bias_eff;
   fusion_bias_kernel<<<dim3((unsigned)(nl * B), (unsigned)((C2 + 63) / 64)), 256, (C + 256) * sizeof(float), stream>>>(BA);
   OSD_LAUNCH_CHECK("fusion_bias_kernel");
 
-  // ---- conv1: x [B,C,HW] -> y1 [B,2C,HW] (+ folded bias, GroupNorm-1 statistics)
+  if (full) return fusion_full_forward(d, ws, stream);
+
+  // ---- stage CONV1: x [B,C,HW] -> out [B,2C,HW] (+ folded bias)
   CUtensorMap map1;
   rc = make_weight_map(d->w1x_bf16, C2, C, &map1);
   if (rc != OSD_OK) return rc;
   ConvArgs A1{};
   A1.nl = nl; A1.B = B; A1.Cin = C; A1.Cout = C2; A1.xform = 0; A1.eps = d->gn_eps; A1.slope = d->lrelu_slope;
-  A1.bias = bias_eff; A1.bias_level_stride = B * C2; A1.bias_img_stride = C2;
-  A1.stats_out = stats1;
+  A1.bias = ws.bias_eff; A1.bias_level_stride = B * C2; A1.bias_img_stride = C2;
+  A1.stats_out = nullptr;
   int tiles = 0;
-  size_t y1_off = 0;
   for (int l = 0; l < nl; ++l) {
     ConvLevel& L = A1.lv[l];
     L.in = static_cast<const float*>(d->feat[l]);
-    L.out = full ? y1 + y1_off : static_cast<float*>(d->out[l]);
+    L.out = static_cast<float*>(d->out[l]);
     L.hw = d->hw[l];
     L.tiles_per_img = (d->hw[l] + kBlockN - 1) / kBlockN;
     L.tile_begin = tiles;
     tiles += B * L.tiles_per_img;
-    y1_off += (size_t)B * C2 * d->hw[l];
   }
   A1.total_tiles = tiles;
-  rc = launch_conv(map1, A1, stream);
-  if (rc != OSD_OK || !full) return rc;
-
-  // ---- GroupNorm-1 coefficients, then conv2: LeakyReLU(GN1(y1)) [B,2C,HW] -> y2 [B,C,HW] (+ b2, GN-2 statistics)
-  CoefArgs K1{};
-  K1.nl = nl; K1.B = B; K1.C = C2; K1.eps = d->gn_eps; K1.stats = stats1; K1.gn_w = d->gn1_w; K1.gn_b = d->gn1_b;
-  K1.coef = coef1;
-  for (int l = 0; l < nl; ++l) K1.hw[l] = d->hw[l];
-  fusion_gn_coef_kernel<<<nl * B, 512, 0, stream>>>(K1);
-  OSD_LAUNCH_CHECK("fusion_gn_coef_kernel");
-
-  CUtensorMap map2;
-  rc = make_weight_map(d->w2_bf16, C, C2, &map2);
-  if (rc != OSD_OK) return rc;
-  ConvArgs A2{};
-  A2.nl = nl; A2.B = B; A2.Cin = C2; A2.Cout = C; A2.xform = 1; A2.eps = d->gn_eps; A2.slope = d->lrelu_slope;
-  A2.bias = d->b2; A2.bias_level_stride = 0; A2.bias_img_stride = 0;
-  A2.coef_in = coef1;
-  A2.stats_out = stats2;
-  for (int l = 0; l < nl; ++l) {
-    ConvLevel& L = A2.lv[l];
-    L.in = A1.lv[l].out;
-    L.out = static_cast<float*>(d->out[l]);
-    L.hw = d->hw[l];
-    L.tiles_per_img = A1.lv[l].tiles_per_img;
-    L.tile_begin = A1.lv[l].tile_begin;
-  }
-  A2.total_tiles = tiles;
-  rc = launch_conv(map2, A2, stream);
-  if (rc != OSD_OK) return rc;
-
-  // ---- GroupNorm-2 + LeakyReLU in place (streaming pass)
-  CoefArgs K2{};
-  K2.nl = nl; K2.B = B; K2.C = C; K2.eps = d->gn_eps; K2.stats = stats2; K2.gn_w = d->gn2_w; K2.gn_b = d->gn2_b;
-  K2.coef = coef2;
-  for (int l = 0; l < nl; ++l) K2.hw[l] = d->hw[l];
-  fusion_gn_coef_kernel<<<nl * B, 512, 0, stream>>>(K2);
-  OSD_LAUNCH_CHECK("fusion_gn_coef_kernel");
-  GnArgs G{};
-  G.nl = nl; G.slope = d->lrelu_slope;
-  uint64_t chunks = 0;
-  for (int l = 0; l < nl; ++l) {
-    GnLevel& L = G.lv[l];
-    L.y = static_cast<float*>(d->out[l]);
-    L.coef = coef2 + (size_t)l * B * C;
-    L.hw = (uint32_t)d->hw[l];
-    L.elems = (uint32_t)((size_t)B * C * d->hw[l]);
-    L.chunk_begin = (uint32_t)chunks;
-    L.div_hw = make_fastdiv(L.hw);
-    chunks += ((uint64_t)L.elems + 4ull * kGnChunk - 1) / (4ull * kGnChunk);
-  }
-  G.total_chunks = (uint32_t)chunks;
-  const int ctas = (int)std::min<uint64_t>(chunks, (uint64_t)kNumSMs * 16);
-  if (ctas > 0) {
-    fusion_gn_lrelu_kernel<<<ctas, kGnThreads, 0, stream>>>(G);
-    OSD_LAUNCH_CHECK("fusion_gn_lrelu_kernel");
-  }
-  return OSD_OK;
+  return launch_conv(map1, A1, stream);
 }

@@ -1,0 +1,711 @@
+// The full 1x1 fusion module as a back-to-back GEMM on tcgen05 (sm_100a), hand-written: no CUTLASS.
+//
+// Reference: `compress_dim_conv` (maskrcnn_benchmark/modeling/roi_heads/box_head/box_head.py:43-54) applied to
+// cat((x, support.expand_as(x)), dim=1) (:147-149):
+//     Conv1x1(2C -> 2C) + GroupNorm(32, 2C) + LeakyReLU(0.2) + Conv1x1(2C -> C) + GroupNorm(32, C) + LeakyReLU(0.2)
+//
+// Round 1 ran the two convolutions as two GEMM launches with an fp32 [B, 2C, HW] intermediate in HBM (written once, read
+// once) and streamed every weight byte from L2 once per 64 pixels; it was bound by that L2 stream and by the 2.9 GB of
+// DRAM traffic.  Here:
+//
+//  * PIXELS are the UMMA M dimension (tile = 128 pixels = the 128 TMEM lanes), channels are N.  The activations
+//    [C, 128 px] (NCHW rows, pixel-contiguous) are the MN-major A operand; the weights [Cout, Cin] row-major are the K-major
+//    B operand (TMA, 128-byte swizzle, 16 KB stages of 128 rows x 64 K).  One pass over the weights serves 128 pixels.
+//  * conv1 accumulates 128 output channels at a time into a TMEM chunk D1 [128 px x 128 ch] (two chunk buffers).
+//    The chunk's epilogue warps read it (tcgen05.ld, thread = pixel), apply GroupNorm-1 (scale/shift per channel, the
+//    folded support bias absorbed into the shift) and LeakyReLU, convert to bf16 and write the result back INTO THE
+//    SAME TMEM COLUMNS (tcgen05.st) -- as the K-major A operand of conv2:  D2 [128 px x C] += y1_chunk . W2[:, chunk]^T
+//    (tcgen05.mma with A in tensor memory).  The 2C-channel intermediate never leaves the SM.
+//  * D2's epilogue adds b2, accumulates GroupNorm-2 statistics and stores NCHW rows straight from registers: for a
+//    fixed channel the 32 lanes of a warp are 32 consecutive pixels = one 128-byte line per store instruction.
+//  * GroupNorm is a reduction over all pixels of an (episode, level), so the module is three passes:
+//      A  x (fp32) -> bf16 smem tile (+ a bf16 copy of x in the workspace) -> conv1 -> statistics of GroupNorm-1 only
+//      B  bf16 x (TMA) -> conv1 -> GN1 + LeakyReLU -> conv2 (+ b2) -> raw y2 to `out` + statistics of GroupNorm-2
+//      C  out = LeakyReLU(GN2(out)) in place (streaming kernel in fusion_conv.cu)
+//    DRAM: A reads 4C and writes 2C bytes per pixel, B reads 2C and writes 4C, C reads and writes 4C: 20C (1.84 GB at
+//    16 x 22 400 pixels, C = 256) instead of 32C; weights from L2: 1.5 x 512 KB per 128 pixels instead of 512 KB per 64.
+//
+// Warp roles.  Pass A (14 warps): 0-3 statistics epilogue (one TMEM lane quadrant each), 4-11 activation producers
+// (fp32 rows -> bf16, st.shared into the swizzled operand layout and st.global into the bf16 copy), 12 TMA (weights),
+// 13 MMA issuer + TMEM owner.  Pass B (16 warps): 0-3 chunk epilogue (GN1 -> TMEM), 4-11 output epilogue (two warps
+// per lane quadrant, half of the output channels each), 12 TMA (weights), 13 TMA (activations), 14 MMA issuer.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "fusion_internal.cuh"
+#include "osd_common.cuh"
+#include "osd_tc.cuh"
+
+namespace osd {
+namespace {
+using namespace tc;
+
+constexpr int kTileM = 128;             // pixels per tile (UMMA M, TMEM lanes)
+constexpr int kChunk = 128;             // conv1 output channels per chunk (UMMA N of conv1, K of one conv2 block)
+constexpr int kStageK = 64;             // K elements per weight stage (one 128-byte swizzle row of bf16)
+constexpr int kStageBytes = 128 * 128;  // 16 KB: 128 rows x 64 K
+constexpr int kStages = 5;
+constexpr int kUmmaK = 16;
+constexpr uint32_t kD2Col = 256;        // TMEM columns: D1/y1 chunk buffers at 0 and 128, D2 at 256..511
+
+constexpr int kThreadsA = 32 * 14;
+constexpr int kThreadsB = 32 * 16;
+
+struct FLevel {
+  const float* in;        // [B, C, hw] fp32 (pass A)
+  __nv_bfloat16* xb;      // [B*C, pitch] bf16 copy (written by pass A, read through TMA by pass B)
+  float* out;             // [B, C, hw] fp32 (pass B)
+  int hw, pitch;
+  int tiles_per_img;      // ceil(hw / 128)
+  int tile_begin;
+};
+
+struct FArgs {
+  int nl, B;
+  int total_tiles;
+  int store;              // pass B: write y2 to out
+  int final_xform;        // pass B: apply GroupNorm-2 + LeakyReLU in the output epilogue (coef2), else raw y2 (+ b2)
+  float slope;
+  const float* bias1;     // [nl, B, 2C] folded conv1 bias (pass A statistics)
+  const float2* coef1;    // [nl, B, 2C] GN1 (scale, shift incl. folded bias) (pass B)
+  const float* b2;        // [C]
+  const float2* coef2;    // [nl, B, C] GN2 (scale, shift) (pass B with final_xform)
+  double* stats1;         // [nl, B, 32, 2] (pass A)
+  double* stats2;         // [nl, B, 32, 2] (pass B, may be null)
+  FLevel lv[OSD_MAX_LEVELS];
+};
+
+struct XMaps {
+  CUtensorMap m[OSD_MAX_LEVELS];
+};
+
+struct TileInfo {
+  int level, img, px0, nvalid;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const FArgs& A, int tile) {
+  int li = 0;
+#pragma unroll
+  for (int k = 1; k < OSD_MAX_LEVELS; ++k)
+    if (k < A.nl && tile >= A.lv[k].tile_begin) li = k;
+  const int local = tile - A.lv[li].tile_begin;
+  const int tpi = A.lv[li].tiles_per_img;
+  TileInfo t;
+  t.level = li;
+  t.img = local / tpi;
+  t.px0 = (local - t.img * tpi) * kTileM;
+  t.nvalid = min(kTileM, A.lv[li].hw - t.px0);
+  return t;
+}
+
+// shared-memory plan (offsets from the 1024-byte aligned base)
+template <int C>
+struct Smem {
+  static constexpr uint32_t x_bytes = C * 256;                 // one activation tile: [C rows][128 px] bf16
+  static constexpr uint32_t x_off = 0;
+  static constexpr uint32_t w_off = 2 * x_bytes;
+  static constexpr uint32_t aux_off = w_off + kStages * kStageBytes;
+  // aux: pass A: bias1 [2][2C] floats; pass B: coef1 [2][2C] float2, b2 [C] floats, coef2 [2][C] float2
+  static constexpr uint32_t aux_bytes = 2 * 2 * C * 8 + C * 4 + 2 * C * 8;
+  static constexpr uint32_t bar_off = aux_off + aux_bytes;
+  static constexpr uint32_t total = bar_off + 256 + 1024;       // barriers + alignment slack
+};
+
+struct Bars {
+  uint32_t w_full, w_empty;      // [kStages] each
+  uint32_t x_full, x_empty;      // [2]
+  uint32_t d1_full, d1_done;     // [2]: conv1 chunk accumulated / chunk epilogue finished (y1 written or D1 drained)
+  uint32_t d2_full, d2_empty;    // [1]
+  uint32_t tmem_slot;
+};
+__device__ __forceinline__ Bars make_bars(uint32_t base) {
+  Bars b;
+  b.w_full = base;
+  b.w_empty = base + 8u * kStages;
+  b.x_full = base + 16u * kStages;
+  b.x_empty = b.x_full + 16u;
+  b.d1_full = b.x_full + 32u;
+  b.d1_done = b.x_full + 48u;
+  b.d2_full = b.x_full + 64u;
+  b.d2_empty = b.x_full + 72u;
+  b.tmem_slot = b.x_full + 80u;
+  return b;
+}
+
+// conv1 block for one chunk: D1[buf] = x_tile . W1x[chunk rows]^T, K = C in stages of 64
+template <int C>
+__device__ __forceinline__ void issue_conv1(const Bars& bar, uint32_t sX, uint32_t sW, uint32_t tmem_d, uint32_t& wc) {
+  constexpr uint32_t idesc = make_idesc_ex(kTileM, kChunk, /*a_mn=*/1, /*b_mn=*/0);
+#pragma unroll 1
+  for (int kc = 0; kc < C / kStageK; ++kc, ++wc) {
+    const uint32_t s = wc % kStages, ph = (wc / kStages) & 1u;
+    mbar_wait(bar.w_full + 8u * s, ph);
+    tc_fence_after();
+#pragma unroll
+    for (int k16 = 0; k16 < kStageK / kUmmaK; ++k16) {
+      // A: MN-major SW128: 64-pixel atoms are x_bytes/2 apart (LBO), 8-channel groups 1024 B apart (SBO)
+      const uint32_t kgrp = (uint32_t)(kc * kStageK + k16 * kUmmaK) >> 3;
+      const uint64_t adesc = make_smem_desc(sX + kgrp * 1024u, (uint32_t)C * 128u, 1024u);
+      // B: K-major SW128: 8-row groups 1024 B apart (SBO), K advances by 32 B inside the swizzle row
+      const uint64_t bdesc = make_smem_desc(sW + s * kStageBytes + k16 * 32u, 16u, 1024u);
+      umma_bf16(tmem_d, adesc, bdesc, idesc, (kc | k16) != 0 ? 1u : 0u);
+    }
+    umma_commit(bar.w_empty + 8u * s);
+  }
+}
+
+// conv2 block for one chunk: D2 (+)= y1[buf] (TMEM, 128 px x 128 ch bf16) . W2[:, chunk]^T
+template <int C>
+__device__ __forceinline__ void issue_conv2(const Bars& bar, uint32_t sW, uint32_t tmem_base, uint32_t buf, bool first_chunk,
+                                            uint32_t& wc) {
+  constexpr int N2 = C < 128 ? C : 128;
+  constexpr uint32_t idesc = make_idesc_ex(kTileM, N2, /*a_mn=*/0, /*b_mn=*/0);
+#pragma unroll 1
+  for (int h = 0; h < (C + 127) / 128; ++h) {
+#pragma unroll 1
+    for (int kc2 = 0; kc2 < kChunk / kStageK; ++kc2, ++wc) {
+      const uint32_t s = wc % kStages, ph = (wc / kStages) & 1u;
+      mbar_wait(bar.w_full + 8u * s, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int k16 = 0; k16 < kStageK / kUmmaK; ++k16) {
+        const uint32_t a_taddr = tmem_base + buf * (uint32_t)kChunk + (uint32_t)(kc2 * 4 + k16) * 8u;   // 16 bf16 = 8 columns
+        const uint64_t bdesc = make_smem_desc(sW + s * kStageBytes + k16 * 32u, 16u, 1024u);
+        umma_bf16_ts(tmem_base + kD2Col + (uint32_t)h * 128u, a_taddr, bdesc, idesc,
+                     (!first_chunk || (kc2 | k16) != 0) ? 1u : 0u);
+      }
+      umma_commit(bar.w_empty + 8u * s);
+    }
+  }
+}
+
+__device__ __forceinline__ void load_weight_stage(const Bars& bar, uint32_t sW, const CUtensorMap* map, int col, int row,
+                                                  uint32_t& wc) {
+  const uint32_t s = wc % kStages, ph = (wc / kStages) & 1u;
+  mbar_wait(bar.w_empty + 8u * s, ph ^ 1u);
+  mbar_expect_tx(bar.w_full + 8u * s, kStageBytes);
+  tma_load_2d(sW + s * kStageBytes, map, col, row, bar.w_full + 8u * s);
+  ++wc;
+}
+
+template <int NV>
+__device__ __forceinline__ void warp_reduce_add(float (&v)[NV]) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass A: conv1 statistics (+ bf16 copy of x)
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(kThreadsA, 1)
+fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A) {
+  using S = Smem<C>;
+  constexpr int C2 = 2 * C;
+  constexpr int NCH = C2 / kChunk;          // conv1 chunks per tile
+  constexpr int GS = C2 / 32;               // channels per GroupNorm-1 group
+  constexpr int NG = 32 / GS;               // groups per 32-column batch
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sX = smem_base + S::x_off, sW = smem_base + S::w_off;
+  float* sBias = reinterpret_cast<float*>(gen_base + S::aux_off);   // [2][C2]
+  const Bars bar = make_bars(smem_base + S::bar_off);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&tmap_w1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar.w_full + 8u * s, 1);
+      mbar_init(bar.w_empty + 8u * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar.x_full + 8u * s, 8);    // producer warps
+      mbar_init(bar.x_empty + 8u * s, 1);
+      mbar_init(bar.d1_full + 8u * s, 1);
+      mbar_init(bar.d1_done + 8u * s, 4);   // statistics warps
+    }
+    fence_barrier_init();
+  }
+  if (warp == 13) tmem_alloc(bar.tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (bar.tmem_slot - smem_base));
+
+  if (warp == 12) {
+    // ===================== TMA: weight stages, in the order the MMA warp consumes them =====================
+    if (lane == 0) {
+      uint32_t wc = 0;
+      for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x)
+        for (int j = 0; j < NCH; ++j)
+          for (int kc = 0; kc < C / kStageK; ++kc) load_weight_stage(bar, sW, &tmap_w1, kc * kStageK, j * kChunk, wc);
+    }
+  } else if (warp == 13) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t wc = 0, g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t xb = it & 1u;
+        mbar_wait(bar.x_full + 8u * xb, (it >> 1) & 1u);
+        tc_fence_after();
+        for (int j = 0; j < NCH; ++j, ++g) {
+          const uint32_t b = g & 1u, u = g >> 1;
+          mbar_wait(bar.d1_done + 8u * b, (u & 1u) ^ 1u);   // statistics warps drained the chunk two back
+          tc_fence_after();
+          issue_conv1<C>(bar, sX + xb * S::x_bytes, sW, tmem_base + b * (uint32_t)kChunk, wc);
+          umma_commit(bar.d1_full + 8u * b);
+        }
+        umma_commit(bar.x_empty + 8u * xb);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== activation producers (warps 4-11) =====================
+    const int pw = warp - 4;
+    const int chunk = lane & 15;       // 16-byte bf16 chunk = 8 pixels; 16 chunks = 128 pixels
+    const int rsub = lane >> 4;        // row inside the pair this warp handles per round
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+      const TileInfo t = decode_tile(A, tile);
+      const FLevel& L = A.lv[t.level];
+      const int px = t.px0 + chunk * 8;
+      const float* src = L.in + (size_t)t.img * C * L.hw + px;
+      __nv_bfloat16* dstg = L.xb + (size_t)t.img * C * L.pitch + px;
+      const bool vec_ok = ((L.hw & 3) == 0) && (px + 8 <= L.hw);
+      const int nleft = L.hw - px;     // valid pixels from this chunk's start (may be <= 0)
+      constexpr int kRounds = (C / 16) < 8 ? (C / 16) : 8;   // 16 rows per round, up to 128 rows per batch
+#pragma unroll 1
+      for (int kh = 0; kh < C; kh += 128) {
+        float v[kRounds][8];
+#pragma unroll
+        for (int u = 0; u < kRounds; ++u) {
+          const int k = kh + u * 16 + pw * 2 + rsub;
+          const float* p = src + (size_t)k * L.hw;
+          if (vec_ok) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+            v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
+            v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[u][q] = (q < nleft) ? __ldg(p + q) : 0.f;
+          }
+        }
+        if (kh == 0) mbar_wait(bar.x_empty + 8u * buf, ph ^ 1u);
+#pragma unroll
+        for (int u = 0; u < kRounds; ++u) {
+          const int k = kh + u * 16 + pw * 2 + rsub;
+          uint4 pk;
+          pk.x = pack_bf16x2(v[u][0], v[u][1]);
+          pk.y = pack_bf16x2(v[u][2], v[u][3]);
+          pk.z = pack_bf16x2(v[u][4], v[u][5]);
+          pk.w = pack_bf16x2(v[u][6], v[u][7]);
+          const uint32_t dst = sX + buf * S::x_bytes + (uint32_t)(chunk >> 3) * (uint32_t)(C * 128) + (uint32_t)(k >> 3) * 1024u +
+                               (uint32_t)(k & 7) * 128u + (uint32_t)(((chunk & 7) ^ (k & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+          if (nleft > 0) *reinterpret_cast<uint4*>(dstg + (size_t)k * L.pitch) = pk;
+        }
+      }
+      fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar.x_full + 8u * buf);
+    }
+  } else {
+    // ===================== GroupNorm-1 statistics (warps 0-3; thread = pixel) =====================
+    const int q = warp;   // TMEM lane quadrant
+    uint32_t it = 0, g = 0;
+    for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
+      const TileInfo t = decode_tile(A, tile);
+      const bool valid = (q * 32 + lane) < t.nvalid;
+      const size_t plane = (size_t)t.level * A.B + t.img;
+      float* sb = sBias + (it & 1u) * C2;
+      for (int c = threadIdx.x; c < C2; c += 128) sb[c] = __ldg(A.bias1 + plane * C2 + c);
+      named_bar_sync(1, 128);
+      double* so = A.stats1 + plane * 64;
+      for (int j = 0; j < NCH; ++j, ++g) {
+        const uint32_t b = g & 1u;
+        mbar_wait(bar.d1_full + 8u * b, (g >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < kChunk; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + b * (uint32_t)kChunk + (uint32_t)c0, r);
+          tmem_ld_wait();
+          if (c0 == kChunk - 32) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar.d1_done + 8u * b);   // the chunk buffer may be overwritten
+          }
+          float acc[2 * NG];
+#pragma unroll
+          for (int i = 0; i < 2 * NG; ++i) acc[i] = 0.f;
+          const float* bp = sb + j * kChunk + c0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float y = __uint_as_float(r[i]) + bp[i];
+            if (valid) {
+              acc[2 * (i / GS)] += y;
+              acc[2 * (i / GS) + 1] = fmaf(y, y, acc[2 * (i / GS) + 1]);
+            }
+          }
+          warp_reduce_add(acc);
+          if (lane == 0) {
+            const int g0 = (j * kChunk + c0) / GS;
+#pragma unroll
+            for (int i = 0; i < NG; ++i) {
+              atomicAdd(so + 2 * (g0 + i), (double)acc[2 * i]);
+              atomicAdd(so + 2 * (g0 + i) + 1, (double)acc[2 * i + 1]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass B: conv1 -> GN1 + LeakyReLU -> conv2 (+ b2) [-> GN2 + LeakyReLU] -> out, GroupNorm-2 statistics
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(kThreadsB, 1)
+fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
+                  const __grid_constant__ XMaps xmaps, const FArgs A) {
+  using S = Smem<C>;
+  constexpr int C2 = 2 * C;
+  constexpr int NCH = C2 / kChunk;
+  constexpr int GS2 = C / 32;               // channels per GroupNorm-2 group
+  constexpr int NG2 = 32 / GS2;             // groups per 32-column batch
+  constexpr int kColsPerWarp = C / 2;       // output epilogue: two warps per lane quadrant
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sX = smem_base + S::x_off, sW = smem_base + S::w_off;
+  float2* sCoef1 = reinterpret_cast<float2*>(gen_base + S::aux_off);            // [2][C2]
+  float* sB2 = reinterpret_cast<float*>(gen_base + S::aux_off + 2 * C2 * 8);    // [C]
+  float2* sCoef2 = reinterpret_cast<float2*>(gen_base + S::aux_off + 2 * C2 * 8 + C * 4);   // [2][C]
+  const Bars bar = make_bars(smem_base + S::bar_off);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&tmap_w1);
+    tma_prefetch_desc(&tmap_w2);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar.w_full + 8u * s, 1);
+      mbar_init(bar.w_empty + 8u * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar.x_full + 8u * s, 1);    // expect_tx arrival of the TMA warp
+      mbar_init(bar.x_empty + 8u * s, 1);
+      mbar_init(bar.d1_full + 8u * s, 1);
+      mbar_init(bar.d1_done + 8u * s, 4);   // chunk epilogue warps
+    }
+    mbar_init(bar.d2_full, 1);
+    mbar_init(bar.d2_empty, 8);             // output epilogue warps
+    fence_barrier_init();
+  }
+  if (warp == 14) tmem_alloc(bar.tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (bar.tmem_slot - smem_base));
+
+  // Per tile the tensor pipe runs   C1(0) C1(1) | C2(0) C1(2) | C2(1) C1(3) | C2(2) | C2(3)   (conv1 one chunk ahead of
+  // conv2; the next tile's C1(0) C1(1) follow at once, which is the window in which the output epilogue drains D2).
+  if (warp == 12) {
+    // ===================== TMA: weight stages in consumption order =====================
+    if (lane == 0) {
+      uint32_t wc = 0;
+      for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
+        auto w1 = [&](int j) {
+          for (int kc = 0; kc < C / kStageK; ++kc) load_weight_stage(bar, sW, &tmap_w1, kc * kStageK, j * kChunk, wc);
+        };
+        auto w2 = [&](int j) {
+          for (int h = 0; h < (C + 127) / 128; ++h)
+            for (int kc2 = 0; kc2 < kChunk / kStageK; ++kc2)
+              load_weight_stage(bar, sW, &tmap_w2, j * kChunk + kc2 * kStageK, h * 128, wc);
+        };
+        w1(0);
+        if (NCH > 1) w1(1);
+        for (int j = 0; j < NCH; ++j) {
+          w2(j);
+          if (j + 2 < NCH) w1(j + 2);
+        }
+      }
+    }
+  } else if (warp == 13) {
+    // ===================== TMA: activation tiles (bf16 copy written by pass A) =====================
+    if (lane == 0) {
+      for (int l = 0; l < A.nl; ++l) tma_prefetch_desc(&xmaps.m[l]);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u;
+        const TileInfo t = decode_tile(A, tile);
+        mbar_wait(bar.x_empty + 8u * buf, ((it >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(bar.x_full + 8u * buf, S::x_bytes);
+        // two boxes of 64 pixels x C rows: exactly the two MN-major swizzle atoms of the A operand
+        tma_load_2d(sX + buf * S::x_bytes, &xmaps.m[t.level], t.px0, t.img * C, bar.x_full + 8u * buf);
+        tma_load_2d(sX + buf * S::x_bytes + S::x_bytes / 2, &xmaps.m[t.level], t.px0 + 64, t.img * C, bar.x_full + 8u * buf);
+      }
+    }
+  } else if (warp == 14) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t wc = 0, g0 = 0, it = 0;
+      for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it, g0 += NCH) {
+        const uint32_t xb = it & 1u;
+        const uint32_t sXt = sX + xb * S::x_bytes;
+        mbar_wait(bar.x_full + 8u * xb, (it >> 1) & 1u);
+        tc_fence_after();
+        // chunk g uses TMEM buffer g & 1.  The buffer's previous user is chunk g-2: its conv2 block was issued before
+        // this conv1 block (the tensor pipe executes in issue order) and this thread waited for that chunk's epilogue
+        // before issuing it, so no further wait is needed here.
+        auto c1 = [&](int j) {
+          const uint32_t b = (g0 + j) & 1u;
+          issue_conv1<C>(bar, sXt, sW, tmem_base + b * (uint32_t)kChunk, wc);
+          umma_commit(bar.d1_full + 8u * b);
+          if (j == NCH - 1) umma_commit(bar.x_empty + 8u * xb);   // the activation tile may be refilled
+        };
+        c1(0);
+        if (NCH > 1) c1(1);
+        for (int j = 0; j < NCH; ++j) {
+          const uint32_t g = g0 + j, b = g & 1u;
+          mbar_wait(bar.d1_done + 8u * b, (g >> 1) & 1u);          // y1 chunk written to TMEM
+          if (j == 0) mbar_wait(bar.d2_empty, (it & 1u) ^ 1u);     // previous tile's output drained
+          tc_fence_after();
+          issue_conv2<C>(bar, sW, tmem_base, b, j == 0, wc);
+          if (j == NCH - 1) umma_commit(bar.d2_full);
+          if (j + 2 < NCH) c1(j + 2);
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ===================== chunk epilogue (warps 0-3; thread = pixel): GN1 + LeakyReLU, y1 -> TMEM =====================
+    const int q = warp;
+    const float slope = A.slope;
+    uint32_t it = 0, g = 0;
+    for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
+      const TileInfo t = decode_tile(A, tile);
+      const size_t plane = (size_t)t.level * A.B + t.img;
+      float2* sc = sCoef1 + (it & 1u) * C2;
+      for (int c = threadIdx.x; c < C2; c += 128) sc[c] = __ldg(A.coef1 + plane * C2 + c);
+      named_bar_sync(1, 128);
+      for (int j = 0; j < NCH; ++j, ++g) {
+        const uint32_t b = g & 1u;
+        mbar_wait(bar.d1_full + 8u * b, (g >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t tbuf = tmem_base + ((uint32_t)(q * 32) << 16) + b * (uint32_t)kChunk;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kChunk; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tbuf + (uint32_t)c0, r);
+          tmem_ld_wait();
+          const float4* cf = reinterpret_cast<const float4*>(sc + j * kChunk + c0);   // (scale, shift) x 2 channels
+          uint32_t p[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 k = cf[i];
+            float a = fmaf(__uint_as_float(r[2 * i]), k.x, k.y);
+            float c = fmaf(__uint_as_float(r[2 * i + 1]), k.z, k.w);
+            a = a > 0.f ? a : a * slope;
+            c = c > 0.f ? c : c * slope;
+            p[i] = pack_bf16x2(a, c);
+          }
+          // in place: bf16 channels [c0, c0+32) of this pixel -> columns [c0/2, c0/2+16) of the same chunk buffer (all
+          // of them were read by this thread already)
+          tmem_st16(tbuf + (uint32_t)(c0 >> 1), p);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar.d1_done + 8u * b);
+      }
+    }
+  } else if (warp < 12) {
+    // ===================== output epilogue (warps 4-11; thread = pixel) =====================
+    const int q = warp & 3, hh = (warp - 4) >> 2;   // lane quadrant, channel half
+    const float slope = A.slope;
+    for (int c = threadIdx.x - 128; c < C; c += 256) sB2[c] = __ldg(A.b2 + c);
+    named_bar_sync(2, 256);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
+      const TileInfo t = decode_tile(A, tile);
+      const FLevel& L = A.lv[t.level];
+      const int pl = q * 32 + lane;
+      const bool valid = pl < t.nvalid;
+      const size_t plane = (size_t)t.level * A.B + t.img;
+      float2* sc2 = sCoef2 + (it & 1u) * C;
+      if (A.final_xform) {
+        for (int c = threadIdx.x - 128; c < C; c += 256) sc2[c] = __ldg(A.coef2 + plane * C + c);
+        named_bar_sync(2, 256);
+      }
+      double* so = A.stats2 ? A.stats2 + plane * 64 : nullptr;
+      float* obase = L.out + (size_t)t.img * C * L.hw + t.px0 + pl;
+      mbar_wait(bar.d2_full, it & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < kColsPerWarp; cb += 32) {
+        const int c0 = hh * kColsPerWarp + cb;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kD2Col + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (cb == kColsPerWarp - 32) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar.d2_empty);   // D2 may be overwritten by the next tile's conv2
+        }
+        float acc[2 * NG2];
+#pragma unroll
+        for (int i = 0; i < 2 * NG2; ++i) acc[i] = 0.f;
+        float* op = obase + (size_t)c0 * L.hw;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float y = __uint_as_float(r[i]) + sB2[c0 + i];
+          if (valid) {
+            acc[2 * (i / GS2)] += y;
+            acc[2 * (i / GS2) + 1] = fmaf(y, y, acc[2 * (i / GS2) + 1]);
+          }
+          if (A.final_xform) {
+            const float2 k = sc2[c0 + i];
+            y = fmaf(y, k.x, k.y);
+            y = y > 0.f ? y : y * slope;
+          }
+          if (valid && A.store) op[(size_t)i * L.hw] = y;
+        }
+        if (so) {
+          warp_reduce_add(acc);
+          if (lane == 0) {
+            const int gg = c0 / GS2;
+#pragma unroll
+            for (int i = 0; i < NG2; ++i) {
+              atomicAdd(so + 2 * (gg + i), (double)acc[2 * i]);
+              atomicAdd(so + 2 * (gg + i) + 1, (double)acc[2 * i + 1]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 14) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int C>
+int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t stream) {
+  using S = Smem<C>;
+  static_assert(S::total <= 227 * 1024, "shared-memory plan exceeds 227 KB");
+  const int C2 = 2 * C, B = d->batch, nl = d->num_levels;
+  const size_t per = (size_t)nl * B;
+  OSD_CUDA(cudaMemsetAsync(ws.stats1, 0, sizeof(double) * per * 64, stream));
+  OSD_CUDA(cudaMemsetAsync(ws.stats2, 0, sizeof(double) * per * 64, stream));
+  timeline_mark("fusion_begin", stream);
+
+  CUtensorMap map1, map2;
+  XMaps xm;
+  memset(&xm, 0, sizeof(xm));
+  int rc = make_bf16_map(d->w1x_bf16, C2, C, C, kStageK, 128, &map1);
+  if (rc != OSD_OK) return rc;
+  rc = make_bf16_map(d->w2_bf16, C, C2, C2, kStageK, 128, &map2);
+  if (rc != OSD_OK) return rc;
+
+  FArgs A{};
+  A.nl = nl; A.B = B; A.slope = d->lrelu_slope;
+  A.bias1 = ws.bias_eff; A.coef1 = ws.coef1; A.b2 = d->b2; A.coef2 = ws.coef2;
+  A.stats1 = ws.stats1; A.stats2 = ws.stats2;
+  int tiles = 0;
+  size_t xb_off = 0;
+  int32_t hw[OSD_MAX_LEVELS];
+  float* outs[OSD_MAX_LEVELS];
+  for (int l = 0; l < nl; ++l) {
+    FLevel& L = A.lv[l];
+    L.in = static_cast<const float*>(d->feat[l]);
+    L.out = static_cast<float*>(d->out[l]);
+    L.hw = d->hw[l];
+    L.pitch = (int)fusion_xb_pitch(d->hw[l]);
+    L.xb = static_cast<__nv_bfloat16*>(ws.xb) + xb_off;
+    xb_off += (size_t)B * C * L.pitch;
+    L.tiles_per_img = (d->hw[l] + kTileM - 1) / kTileM;
+    L.tile_begin = tiles;
+    tiles += B * L.tiles_per_img;
+    hw[l] = d->hw[l];
+    outs[l] = L.out;
+    // columns = valid pixels (the pad up to the pitch reads as zero), rows = B*C
+    rc = make_bf16_map(L.xb, (int64_t)B * C, L.hw, L.pitch, 64, C, &xm.m[l]);
+    if (rc != OSD_OK) return rc;
+  }
+  A.total_tiles = tiles;
+  if (tiles <= 0) return OSD_OK;
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+
+  rc = ensure_dynamic_smem(reinterpret_cast<const void*>(fusion_stats1_kernel<C>), S::total);
+  if (rc != OSD_OK) return rc;
+  rc = ensure_dynamic_smem(reinterpret_cast<const void*>(fusion_b2b_kernel<C>), S::total);
+  if (rc != OSD_OK) return rc;
+
+  // ---- pass A: GroupNorm-1 statistics (+ bf16 copy of the features)
+  fusion_stats1_kernel<C><<<grid, kThreadsA, S::total, stream>>>(map1, A);
+  OSD_LAUNCH_CHECK("fusion_stats1_kernel");
+  timeline_mark("fusion_stats1_kernel", stream);
+  rc = fusion_launch_gn_coef(nl, B, C2, d->gn_eps, ws.stats1, d->gn1_w, d->gn1_b, ws.bias_eff, ws.coef1, hw, stream);
+  if (rc != OSD_OK) return rc;
+
+  // ---- pass B: fused conv1 -> GN1 -> LeakyReLU -> conv2; raw y2 (+ b2) to out, GroupNorm-2 statistics
+  static const bool recompute = [] { const char* e = getenv("OSD_FUSION_RECOMPUTE"); return e && e[0] == '1'; }();
+  A.store = recompute ? 0 : 1;
+  A.final_xform = 0;
+  fusion_b2b_kernel<C><<<grid, kThreadsB, S::total, stream>>>(map1, map2, xm, A);
+  OSD_LAUNCH_CHECK("fusion_b2b_kernel");
+  timeline_mark("fusion_b2b_kernel", stream);
+  rc = fusion_launch_gn_coef(nl, B, C, d->gn_eps, ws.stats2, d->gn2_w, d->gn2_b, nullptr, ws.coef2, hw, stream);
+  if (rc != OSD_OK) return rc;
+
+  if (recompute) {
+    // ---- pass C': the fused chain once more with GroupNorm-2 + LeakyReLU in the output epilogue (no y2 round trip)
+    A.store = 1;
+    A.final_xform = 1;
+    A.stats2 = nullptr;
+    fusion_b2b_kernel<C><<<grid, kThreadsB, S::total, stream>>>(map1, map2, xm, A);
+    OSD_LAUNCH_CHECK("fusion_b2b_kernel");
+    timeline_mark("fusion_b2b_kernel(final)", stream);
+    return OSD_OK;
+  }
+  // ---- pass C: GroupNorm-2 + LeakyReLU in place
+  rc = fusion_launch_gn_lrelu(nl, B, C, d->lrelu_slope, outs, ws.coef2, hw, stream);
+  timeline_mark("fusion_gn_lrelu_kernel", stream);
+  return rc;
+}
+
+}  // namespace
+
+int fusion_full_forward(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t stream) {
+  switch (d->channels) {
+    case 64: return run_full<64>(d, ws, stream);
+    case 128: return run_full<128>(d, ws, stream);
+    case 256: return run_full<256>(d, ws, stream);
+  }
+  set_error("osd_fusion: channels must be 64, 128 or 256 (got %d)", d->channels);
+  return OSD_ERR_INVALID;
+}
+
+}  // namespace osd

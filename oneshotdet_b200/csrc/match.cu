@@ -488,11 +488,8 @@ int launch(const Args& A, int layout, cudaStream_t stream) {
   if ((uint32_t)ctas > A.total_chunks) ctas = (int)A.total_chunks;
   if (ctas < 1) return OSD_OK;
   {
-    static thread_local bool carveout_set = false;   // per <T, MODE> instantiation
-    if (!carveout_set) {
-      OSD_CUDA(prefer_max_shared_carveout(match_product_bulk_kernel<T>));
-      carveout_set = true;
-    }
+    int rc2 = ensure_max_shared_carveout(reinterpret_cast<const void*>(match_product_bulk_kernel<T>));
+    if (rc2 != OSD_OK) return rc2;
   }
   timeline_mark("match_begin", stream);
   static int use_bulk = -1;
@@ -502,10 +499,9 @@ int launch(const Args& A, int layout, cudaStream_t stream) {
   }
   if (MODE == OSD_MATCH_PRODUCT && layout == OSD_LAYOUT_NCHW && use_bulk && bulk_eligible<T>(A)) {
     const size_t smem = (size_t)kBulkSlots * kChunkBytes + 128;
-    static thread_local bool configured = false;
-    if (!configured) {
-      OSD_CUDA(cudaFuncSetAttribute(match_product_bulk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
+    {
+      int rc2 = ensure_dynamic_smem(reinterpret_cast<const void*>(match_product_bulk_kernel<T>), smem);
+      if (rc2 != OSD_OK) return rc2;
     }
     static int bulk_ctas = 0;
     if (bulk_ctas == 0) {

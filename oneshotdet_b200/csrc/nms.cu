@@ -784,13 +784,11 @@ size_t nms_workspace_carve(Carver& c, int64_t E, int64_t max_len, NmsWorkspace* 
 int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, const NmsOutputs& O,
             cudaStream_t stream) {
   {
-    static thread_local bool carveout_set = false;
-    if (!carveout_set) {
-      OSD_CUDA(prefer_max_shared_carveout(nms_chunk_sort_kernel));
-      OSD_CUDA(prefer_max_shared_carveout(nms_merge_kernel));
-      OSD_CUDA(prefer_max_shared_carveout(nms_mask_kernel));
-      OSD_CUDA(prefer_max_shared_carveout(nms_sweep_kernel));
-      carveout_set = true;
+    const void* ks[4] = {reinterpret_cast<const void*>(nms_chunk_sort_kernel), reinterpret_cast<const void*>(nms_merge_kernel),
+                         reinterpret_cast<const void*>(nms_mask_kernel), reinterpret_cast<const void*>(nms_sweep_kernel)};
+    for (const void* k : ks) {
+      int rc2 = ensure_max_shared_carveout(k);
+      if (rc2 != OSD_OK) return rc2;
     }
   }
   const int E = W.E;
@@ -806,11 +804,9 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
     OSD_LAUNCH_CHECK("nms_chunk_sort_kernel");
     timeline_mark("nms_chunk_sort_kernel", stream);
     const size_t merge_smem = (size_t)std::min<int64_t>(kMergeStage, (int64_t)align_up((size_t)(max_len > 0 ? max_len : 1), kChunk)) * sizeof(u64);
-    static thread_local bool merge_configured = false;
-    if (!merge_configured) {
-      OSD_CUDA(cudaFuncSetAttribute(nms_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(kMergeStage * sizeof(u64))));
-      merge_configured = true;
+    {
+      int rc2 = ensure_dynamic_smem(reinterpret_cast<const void*>(nms_merge_kernel), kMergeStage * sizeof(u64));
+      if (rc2 != OSD_OK) return rc2;
     }
     nms_merge_kernel<<<g, kMergeThreads, merge_smem, stream>>>(L, W);
     OSD_LAUNCH_CHECK("nms_merge_kernel");
@@ -823,13 +819,9 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
   const size_t sweep_smem = std::max(((size_t)W.NW + (size_t)(kSweepDepth + 1) * kSweepThreads * kSweepPre) * sizeof(u64),
                                      (size_t)W.NW * (2 * sizeof(u64) + sizeof(int)) + 64);
   {
-    static thread_local size_t configured = 48 * 1024;
-    if (sweep_smem > configured) {
-      OSD_REQUIRE(sweep_smem <= 220 * 1024, "nms: %d candidates per episode exceed the sweep capacity", max_len);
-      OSD_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sweep_smem));
-      configured = sweep_smem;
-    }
+    OSD_REQUIRE(sweep_smem <= 220 * 1024, "nms: %d candidates per episode exceed the sweep capacity", max_len);
+    int rc2 = ensure_dynamic_smem(reinterpret_cast<const void*>(nms_sweep_kernel), sweep_smem);
+    if (rc2 != OSD_OK) return rc2;
   }
   SweepArgs S{};
   S.passthrough = P.passthrough;

@@ -60,6 +60,13 @@ inline cudaError_t prefer_max_shared_carveout(K kernel) {
                               (int)cudaSharedmemCarveoutMaxShared);
 }
 
+// Kernel attributes are per-DEVICE state: these remember what has been configured per (device, kernel), so a process
+// (or thread) that drives several GPUs configures every one of them.  `bytes` is the dynamic shared memory of the
+// launch; the opt-in limit is raised whenever it exceeds what was set before (static shared memory on top of it is the
+// reason there is no "only above 48 KB" shortcut).
+int ensure_dynamic_smem(const void* kernel, size_t bytes);
+int ensure_max_shared_carveout(const void* kernel);
+
 // Bump allocator over a caller-provided workspace (256-byte aligned slices).
 struct Carver {
   char* base;

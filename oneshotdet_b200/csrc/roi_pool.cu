@@ -314,11 +314,8 @@ extern "C" int osd_roi_pool(const osd_roi_pool_desc* d, void* stream_) {
   nchw_to_nhwc_kernel<<<tgrid, 256, 0, stream>>>(T);
   OSD_LAUNCH_CHECK("nchw_to_nhwc_kernel");
   {
-    static thread_local size_t configured = 48 * 1024;
-    if (stage_bytes > configured) {
-      OSD_CUDA(cudaFuncSetAttribute(roi_pool_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = 200 * 1024;
-    }
+    int rc2 = ensure_dynamic_smem(reinterpret_cast<const void*>(roi_pool_nhwc_kernel), 200 * 1024);
+    if (rc2 != OSD_OK) return rc2;
   }
   roi_pool_nhwc_kernel<<<(unsigned)n, kPoolThreads, stage_bytes, stream>>>(A);
   OSD_LAUNCH_CHECK("roi_pool_nhwc_kernel");
