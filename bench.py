@@ -1,31 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- matching + FCOS post-processing + NMS throughput (episodes/s) on N B200s of one box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
 
-A step = one pass of the hot path over one batch of 16 synthetic episodes per GPU (BASELINE.json configs[1]:
-siamese FCOS R-50-FPN geometry, 800x1333 target padded to 800x1344, C=256, 1 shot, two-stage post-processing
-parameters 0 / 6000 / 0.8 / 2000): the product matching of P3-P7 (one launch), then score -> per-level top-k ->
-decode/clip -> batched NMS -> post-NMS top-n.  The FCOS head between the two stages is outside the path: head
-outputs are synthetic and resident.  With N > 1 every rank owns 16 episodes (weak scaling) and
-every step's detections (the post-processing stage's result block: boxes, scores, indices, counts) go to all ranks
-with one asynchronous NCCL all-gather that overlaps the next step (--gather packed: [16, 2001, 6] payloads in groups).
+A step = one pass of the hot path over one batch of synthetic episodes per GPU.  The headline workload is
+BASELINE.json configs[1] ("config2": siamese FCOS R-50-FPN geometry, 16 episodes, 800x1333 target padded to 800x1344,
+C=256, 1 shot, two-stage post-processing parameters 0 / 6000 / 0.8 / 2000): the product matching of P3-P7 (one
+launch), then score -> per-level top-k -> decode/clip -> batched NMS -> post-NMS top-n.  The FCOS head between the two
+stages is outside the path: head outputs are synthetic and resident.  With N > 1 every rank
+owns its episodes (weak scaling) and every step's detections (the post-processing stage's result block) are pushed to
+all ranks over NVLink peer memory on the copy engines (--gather peer; --gather block: one asynchronous NCCL all-gather
+per step); one NCCL all-gather of the final step's block closes the timed region and is checked against the pushed copy.
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same metric through
-EpisodePipeline.run_host with pinned HOST buffers (H2D of all inputs + D2H of the detections inside the timed
-region), `roofline` describes the dominant streaming kernel, `cpu_baseline` the reference's CPU path timed on
-this box's host cores on a bounded sample.  `--impl reference` times that CPU path alone.
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same metric through the public
+host-buffer API (H2D of all inputs + D2H of the detections inside the timed region), `roofline` describes the dominant
+streaming kernel, `cpu_baseline` the reference's CPU path timed on this box's host cores on a bounded sample,
+`workloads` the other BASELINE configs (config4, config5) and the NMS worst cases, each with a parity spot check.
+`--impl reference` times the reference's own CPU path alone (rank 0 only under torchrun: `cpu_processes: 1`).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
 import sys
 import threading
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -33,29 +37,52 @@ if ROOT not in sys.path:
 
 METRIC = "matching+NMS episodes/s"
 UNIT = "episodes/s"
-BATCH = 16
-HEIGHT, WIDTH = 800, 1344          # 800x1333 zero-padded to a multiple of 32 (structures/image_list.py:56-63)
-IMAGE_SIZE = (800, 1333)
-CHANNELS, SHOTS = 256, 1
-PARAMS = dict(pre_nms_thresh=0.0, pre_nms_top_n=6000, nms_thresh=0.8, fpn_post_nms_top_n=2000, min_size=0.0)
-WORKLOAD = ("configs[1]: siamese FCOS R-50-FPN geometry, 16 episodes/GPU, 800x1333 (padded 800x1344), C=256, "
-            "1 shot, fp32 product matching + score/top-k(6000)/decode/NMS(0.8)/top-2000")
+CHANNELS = 256
+TWO_STAGE = dict(pre_nms_thresh=0.0, pre_nms_top_n=6000, nms_thresh=0.8, fpn_post_nms_top_n=2000, min_size=0.0)
+# single-stage branch of make_fcos_postprocessor (modeling/rpn/fcos/inference.py:326-336) with the stress values of
+# BASELINE configs[4]; post-NMS cut = TEST.DETECTIONS_PER_IMG (config/defaults.py: 100)
+STRESS = dict(pre_nms_thresh=0.01, pre_nms_top_n=1000, nms_thresh=0.6, fpn_post_nms_top_n=100, min_size=0.0)
+
+WORKLOADS = {
+    "config2": dict(batch=16, height=800, width=1344, image=(800, 1333), shots=1, params=TWO_STAGE, heads="spread",
+                    early_exit=True,
+                    text="configs[1]: siamese FCOS R-50-FPN geometry, 16 episodes/GPU, 800x1333 (padded 800x1344), C=256, "
+                         "1 shot, fp32 product matching + score/top-k(6000)/decode/NMS(0.8)/top-2000"),
+    "config4": dict(batch=64, height=1024, width=1024, image=(1024, 1024), shots=5, params=TWO_STAGE, heads="spread",
+                    early_exit=True,
+                    text="configs[3]: 64 episodes/GPU, 1024x1024 targets, 5-shot averaged support embedding, C=256, two-stage "
+                         "post-processing parameters"),
+    "config5": dict(batch=20, height=800, width=1344, image=(800, 1333), shots=1, params=STRESS, heads="spread",
+                    early_exit=True,
+                    text="configs[4] NMS stress: 20 episodes (classes) sharing one 800x1333 image size, score_thresh 0.01, "
+                         "1000 pre-NMS candidates per level, NMS 0.6, 100 detections"),
+    "nms_full": dict(batch=16, height=800, width=1344, image=(800, 1333), shots=1, params=TWO_STAGE, heads="clustered",
+                     early_exit=True,
+                     text="configs[1] geometry with clustered head outputs (one box shape per level -> long suppression "
+                          "chains): the early exit misses, the second NMS pass and the dense sweep run"),
+    "nms_noexit": dict(batch=16, height=800, width=1344, image=(800, 1333), shots=1, params=TWO_STAGE, heads="spread",
+                       early_exit=False,
+                       text="configs[1] inputs with early_exit=False: the full 11 600-candidate problem per episode "
+                            "(67.3 M IoU pairs), what the CPU arm pays"),
+}
+LEVELS_TEXT = {(800, 1344): "P3-P7 100x168,50x84,25x42,13x21,7x11", (1024, 1024): "P3-P7 128x128,64x64,32x32,16x16,8x8"}
 
 
-def config_dict(n_gpus):
-    return {"workload": WORKLOAD, "episodes_per_gpu": BATCH, "global_episodes": BATCH * n_gpus,
-            "levels": "P3-P7 100x168,50x84,25x42,13x21,7x11", "match_mode": "product", "match_dtype": "f32",
-            "post_params": PARAMS, "parallelism": f"episode-dp{n_gpus}",
+def config_dict(n_gpus, name="config2", gather=None):
+    wl = WORKLOADS[name]
+    return {"workload": wl["text"], "workload_key": name, "episodes_per_gpu": wl["batch"],
+            "global_episodes": wl["batch"] * n_gpus, "levels": LEVELS_TEXT[(wl["height"], wl["width"])],
+            "match_mode": "product", "match_dtype": "f32", "shots": wl["shots"], "post_params": wl["params"],
+            "parallelism": f"episode-dp{n_gpus}", "gather": gather,
             "streams": "2 (matching || post-processing), see stages.overlap",
-            "cache": "inputs larger than L2 (367 MB features in + 367 MB out per step vs 126 MB L2)"}
+            "cache": "inputs larger than L2 (features in + out per step >= 734 MB vs 126 MB L2)"}
 
 
 # ------------------------------------------------------------------------------------------------------
-# synthetic inputs: features ~ N(0,1); cls ~ N(-4, 2^2); ctr ~ N(0,1); reg = exp(N(log 4s, .5^2))
+# synthetic inputs: features ~ N(0,1); cls ~ N(-4, 2^2); ctr ~ N(0,1); reg = exp(N(log 4s, .5^2));
+# "clustered": reg = 4s exactly (identical box shapes per level -> heavy suppression, the early exit cannot hit)
 # ------------------------------------------------------------------------------------------------------
-def fill_inputs(pipe, seed):
-    import math
-
+def fill_inputs(pipe, seed, heads="spread"):
     import torch
 
     g = torch.Generator(device=pipe.device).manual_seed(seed)
@@ -66,15 +93,28 @@ def fill_inputs(pipe, seed):
     for t in pipe.ctr:
         t.normal_(generator=g)
     for t, s in zip(pipe.reg, pipe.strides):
-        t.normal_(mean=math.log(4.0 * s), std=0.5, generator=g).exp_()
+        if heads == "clustered":
+            t.fill_(4.0 * s)
+        else:
+            t.normal_(mean=math.log(4.0 * s), std=0.5, generator=g).exp_()
+
+
+def make_pipe(name, dev, double_buffer=False):
+    from oneshotdet_b200.pipeline import EpisodePipeline, PostParams
+
+    wl = WORKLOADS[name]
+    return EpisodePipeline(wl["batch"], wl["height"], wl["width"], [wl["image"]] * wl["batch"], channels=CHANNELS,
+                           shots=wl["shots"], params=PostParams(**wl["params"]), match_mode="product", device=dev,
+                           early_exit=wl["early_exit"], double_buffer=double_buffer)
 
 
 # ------------------------------------------------------------------------------------------------------
-# the reference's CPU path on a bounded sample: torch.mul matching (generalized_rcnn.py:306-311) + the
-# post-processing restated with the same ATen ops (oracle) + the reference's own nms_cpu when it was compiled
+# the reference's CPU path on a bounded sample: torch.mul matching (generalized_rcnn.py:100-104, 306-311) + the
+# reference's own FCOSPostProcessor.forward (modeling/rpn/fcos/inference.py:251-323, unmodified, vendored next to its
+# compiled nms_cpu in oracle/_ref by oracle/build_ref.py).  Without the vendored copy: the oracle restatement.
 # ------------------------------------------------------------------------------------------------------
 class CpuReference:
-    def __init__(self, episodes=1, seed=7, threads=None):
+    def __init__(self, name="config2", episodes=1, seed=7, threads=None, inputs=None):
         import torch
 
         from oracle import build_ref
@@ -83,46 +123,89 @@ class CpuReference:
         self.orc, self.torch = orc, torch
         torch.set_num_threads(threads or os.cpu_count() or 1)
         self.cores = torch.get_num_threads()
-        ref = None
-        try:
-            ref = build_ref.load_ref()
-        except Exception:  # noqa: BLE001
-            ref = None
-        self.kind = "reference" if ref is not None else "port"
-        if ref is not None:
-            self.nms_fn = lambda b, s, thr: ref.nms(torch.from_numpy(b), torch.from_numpy(s), float(thr)).numpy()
+        wl = WORKLOADS[name]
+        self.wl, self.episodes = wl, episodes
+        self.params = orc.PostParams(**wl["params"])
+        self.sizes = [wl["image"]] * episodes
+        if inputs is None:
+            feats, supp = orc.synth_features(episodes, wl["shots"], CHANNELS, wl["height"], wl["width"], seed)
+            cls, reg, ctr = orc.synth_head_outputs(episodes, wl["height"], wl["width"], seed, distinct=False)
+            if wl["heads"] == "clustered":
+                reg = [r * 0 + float(4 * s) for r, s in zip(reg, orc.FPN_STRIDES)]
         else:
-            self.nms_fn = None
-        self.episodes = episodes
-        self.feats, self.supp = orc.synth_features(episodes, SHOTS, CHANNELS, HEIGHT, WIDTH, seed)
-        self.cls, self.reg, self.ctr = orc.synth_head_outputs(episodes, HEIGHT, WIDTH, seed, distinct=False)
-        self.params = orc.PostParams(**PARAMS)
-        self.sizes = [IMAGE_SIZE] * episodes
+            feats, supp, cls, reg, ctr = inputs
+        self.feats, self.supp, self.cls, self.reg, self.ctr = feats, supp, cls, reg, ctr
+        self.post = None
+        self.kind = "port"
+        self.nms_fn = None
+        try:
+            ref_c = build_ref.load_reference_python()
+            if ref_c is not None:
+                from maskrcnn_benchmark.modeling.rpn.fcos.fcos import FCOSModule  # noqa: PLC0415
+                from maskrcnn_benchmark.modeling.rpn.fcos.inference import FCOSPostProcessor  # noqa: PLC0415
 
-    def step(self):
-        orc = self.orc
+                cfg = types.SimpleNamespace(MODEL=types.SimpleNamespace(RPN_ONLY=False),
+                                            FEW_SHOT=types.SimpleNamespace(ADD_ARTIFICIAL_PROPOSALS=False))
+                p = self.params
+                self.post = FCOSPostProcessor(cfg, p.pre_nms_thresh, p.pre_nms_top_n, p.nms_thresh, p.fpn_post_nms_top_n,
+                                              p.min_size, num_classes=2, dense_points=1, score_calculator="BINARY").eval()
+                fake = types.SimpleNamespace(dense_points=1)
+                fake.get_dense_locations = lambda loc, stride, device: loc
+                self.locations = [FCOSModule.compute_locations_per_level(fake, c.shape[-2], c.shape[-1], s, torch.device("cpu"))
+                                  for c, s in zip(cls, orc.FPN_STRIDES)]
+                self.kind = "reference"
+        except Exception as exc:  # noqa: BLE001  (fall back to the restatement, and say so in `kind`)
+            print(f"[bench] reference python unavailable ({exc}); timing the oracle restatement", file=sys.stderr)
+            self.post = None
+        if self.post is None:
+            try:
+                ref = build_ref.load_ref()
+            except Exception:  # noqa: BLE001
+                ref = None
+            if ref is not None:
+                self.kind = "port+reference-nms"
+                self.nms_fn = lambda b, s, thr: ref.nms(torch.from_numpy(b), torch.from_numpy(s), float(thr)).numpy()
+
+    def step(self, keep_result=False):
+        orc, torch = self.orc, self.torch
         t0 = time.perf_counter()
-        out = orc.match_product(self.feats, self.supp, self.episodes)
+        out = orc.match_product(self.feats, self.supp, self.episodes)   # the reference expression itself
         t1 = time.perf_counter()
-        res = orc.fcos_postprocess(self.cls, self.reg, self.ctr, orc.FPN_STRIDES, self.sizes, self.params,
-                                   nms_fn=self.nms_fn)
+        if self.post is not None:
+            with torch.no_grad():
+                res = self.post(self.locations, self.cls, self.reg, self.ctr, self.sizes)
+        else:
+            res = orc.fcos_postprocess(self.cls, self.reg, self.ctr, orc.FPN_STRIDES, self.sizes, self.params,
+                                       nms_fn=self.nms_fn)
         t2 = time.perf_counter()
         assert len(out) == 5 and len(res) == self.episodes
+        if keep_result:
+            self.last = res
         return t1 - t0, t2 - t1
 
+    def detections(self, e=0):
+        """(boxes [n,4], scores [n]) of episode e of the last kept step, as numpy."""
+        r = self.last[e]
+        if self.post is not None:
+            return r.bbox.numpy(), r.get_field("scores").numpy()
+        return r["boxes"], r["scores"]
+
     def sample_text(self):
-        nms = ("the reference's own nms_cpu (csrc/cpu/nms_cpu.cpp compiled unmodified, oracle/_ref)"
-               if self.kind == "reference" else "the C port of nms_cpu (oracle/nms_oracle.c)")
-        return (f"{self.episodes} episode(s) of the same workload per step: torch.mul matching on {self.cores} threads + "
-                f"FCOS post-processing restated with the reference's ATen ops + {nms}; nms_cpu is single-threaded by "
-                f"construction (no OpenMP)")
+        if self.kind == "reference":
+            post = ("the reference's own FCOSPostProcessor.forward (unmodified modeling/rpn/fcos/inference.py + "
+                    "structures/boxlist_ops.py, vendored by oracle/build_ref.py) with its nms_cpu compiled unmodified")
+        elif self.kind == "port+reference-nms":
+            post = "FCOS post-processing restated with the reference's ATen ops + the reference's compiled nms_cpu"
+        else:
+            post = "FCOS post-processing restated with the reference's ATen ops + the C port of nms_cpu"
+        return (f"{self.episodes} episode(s) of the workload per step: torch.mul matching on {self.cores} threads + {post}; "
+                f"nms_cpu is single-threaded by construction (no OpenMP)")
 
 
 def cpu_multi_process_throughput(processes=None, timed_steps=2):
     """The same CPU path run as `processes` independent single-threaded workers (one episode stream each) -- what the host
     cores deliver when the reference's per-image loop is data-parallelised over processes, since its nms_cpu cannot use a
-    second thread.  Every worker is this script with --ref-worker; the aggregate rate is the sum of the workers' rates
-    (they overlap for the whole timed part: all start by importing torch and running one warm-up step)."""
+    second thread.  Every worker is this script with --ref-worker; the aggregate rate is the sum of the workers' rates."""
     processes = processes or (os.cpu_count() or 1)
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
@@ -153,10 +236,13 @@ def run_ref_worker(seed, steps):
 
 
 def run_reference_arm(args):
+    """The reference's CPU path with all the host threads it can use.  Under torchrun (N > 1) rank 0 alone runs and
+    prints the line, the other ranks exit without work (the contract of this tier); the line says so in
+    `cpu_processes`, so a per-N ratio against it compares N GPUs with ONE CPU process."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    ref = CpuReference(episodes=1)
+    ref = CpuReference(args.workload, episodes=1)
     for _ in range(max(args.warmup, 1)):
         ref.step()
     times = []
@@ -166,13 +252,14 @@ def run_reference_arm(args):
         times.append(a + b)
         if sum(times) > budget_s:
             break
-    args.steps = len(times)
+    nsteps = len(times)
     total = sum(times)
-    value = ref.episodes * args.steps / total
+    value = ref.episodes * nsteps / total
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "steps": nsteps, "warmup": args.warmup, "ms_per_step": 1e3 * total / nsteps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args.gpus),
+            "config": config_dict(args.gpus, args.workload),
+            "cpu_processes": 1,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
                              "sample": ref.sample_text(),
                              "multi_process": None if args.no_multi_process else cpu_multi_process_throughput()},
@@ -233,12 +320,13 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def measured_peak_hbm():
+def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json)"
     except Exception:  # noqa: BLE001
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
 def ncu_traffic_bytes():
@@ -250,14 +338,120 @@ def ncu_traffic_bytes():
         return None
 
 
+def episode_inputs_to_host(pipe, e=0):
+    """Episode e's inputs as CPU tensors in the layout the reference consumes."""
+    s = pipe.shots
+    feats = [t[e:e + 1].cpu() for t in pipe.features]
+    supp = [t[e * s:(e + 1) * s].cpu() for t in pipe.supp]
+    return feats, supp, [t[e:e + 1].cpu() for t in pipe.cls], [t[e:e + 1].cpu() for t in pipe.reg], \
+        [t[e:e + 1].cpu() for t in pipe.ctr]
+
+
+def parity_spot_check(name, pipe, res, with_cpu_time=True):
+    """Episode 0 of the resident batch through the CPU reference path: detections must agree (boxes exactly, scores to
+    2e-6 relative: the GPU sigmoid is 1/(1+expf(-x)) with IEEE division, ATen's is vectorised) and so must the matching
+    output.  Returns the comparison and the CPU time for that episode."""
+    import numpy as np
+    import torch
+
+    ref = CpuReference(name, episodes=1, inputs=episode_inputs_to_host(pipe, 0))
+    tm, tp = ref.step(keep_result=True)
+    rb, rs = ref.detections(0)
+    n = int(res.count[0].item())
+    gb = res.boxes[0, :n].cpu().numpy()
+    gs = res.scores[0, :n].cpu().numpy()
+    same_n = n == rb.shape[0]
+    out = {"episode": 0, "checker": ref.kind, "count_gpu": n, "count_cpu": int(rb.shape[0]), "count_equal": bool(same_n)}
+    if same_n and n > 0:
+        out["boxes_equal"] = bool(np.array_equal(gb, rb))
+        out["max_score_rel_err"] = float(np.max(np.abs(gs - rs) / np.maximum(np.abs(rs), 1e-30)))
+    mref = ref.orc.match_product(ref.feats, ref.supp, 1)
+    out["matching_equal"] = bool(all(torch.equal(o[0:1].cpu(), m) for o, m in zip(pipe.combined, mref)))
+    out["ok"] = bool(same_n and out.get("boxes_equal", n == 0) and out.get("max_score_rel_err", 0.0) <= 2e-6 and
+                     out["matching_equal"])
+    cpu = {"matching_s": tm, "post_s": tp, "episodes_per_s": 1.0 / (tm + tp), "kind": ref.kind, "cores": ref.cores} \
+        if with_cpu_time else None
+    return out, cpu
+
+
+def time_steps(step_fn, steps, torch):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
+        step_fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    return ev[0].elapsed_time(ev[-1]) / steps, statistics.median(per)
+
+
+def run_extra_workload(name, dev, steps, rank, use_graph=True):
+    """One of the non-headline workloads on this GPU: overlapped/graph step time, isolated stage times, parity spot
+    check against the CPU reference path on episode 0, and that path's time on the same inputs."""
+    import torch
+
+    wl = WORKLOADS[name]
+    pipe = make_pipe(name, dev)
+    fill_inputs(pipe, seed=3000 + 17 * rank + sum(map(ord, name)), heads=wl["heads"])
+    step_fn = pipe.run_overlapped
+    launch = "eager"
+    if use_graph:
+        try:
+            step_fn = pipe.capture(overlapped=True)
+            launch = "cuda-graph"
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] {name}: CUDA-graph capture failed ({exc}); launching eagerly", file=sys.stderr)
+            torch.cuda.synchronize()
+    for _ in range(3):
+        res = step_fn()
+    torch.cuda.synchronize()
+    n = max(3, min(steps, 10))
+    avg_ms, med_ms = time_steps(step_fn, n, torch)
+    m_ms, _ = time_steps(pipe.match, n, torch)
+    p_ms, _ = time_steps(pipe.post, n, torch)
+    res = pipe.run()
+    torch.cuda.synchronize()
+    kept = res.kept_before_cut().cpu().tolist()
+    parity, cpu = parity_spot_check(name, pipe, res)
+    out = {"workload": wl["text"], "episodes_per_gpu": wl["batch"], "post_params": wl["params"], "shots": wl["shots"],
+           "early_exit": wl["early_exit"], "ms_per_step": avg_ms, "ms_per_step_median": med_ms,
+           "episodes_per_s": wl["batch"] / (avg_ms * 1e-3), "steps": n, "launch": launch,
+           "stages": {"match_ms_isolated": m_ms, "post_ms_isolated": p_ms},
+           "detections_per_episode": res.count.cpu().tolist()[:4], "kept_before_cut": kept[:4],
+           "parity": parity, "cpu_same_inputs": cpu}
+    del pipe
+    torch.cuda.empty_cache()
+    return out
+
+
+def h2d_ceiling(pipe, host_in, steps, torch, dist, world, dev):
+    """What the box delivers for this step's host->device traffic alone: the same pinned buffers copied into the same
+    device tensors back to back, all ranks at once, nothing else running."""
+    s = torch.cuda.Stream(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(s):
+        for _ in range(steps):
+            for dst, src in zip(pipe.input_tensors(), host_in):
+                dst.copy_(src, non_blocking=True)
+    s.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return pipe.h2d_bytes * steps / float(t.item()) / 1e9
+
+
 # ------------------------------------------------------------------------------------------------------
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
 
     from oneshotdet_b200 import ops
-    from oneshotdet_b200.distributed import BlockGatherer, DetectionGatherer
-    from oneshotdet_b200.pipeline import EpisodePipeline, PostParams
+    from oneshotdet_b200.distributed import BlockGatherer, DetectionGatherer, PeerBlockGatherer
+    from oneshotdet_b200.pipeline import HostStreamer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -268,18 +462,18 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL is left at its defaults: fewer channels / the LL protocol help the 643 KB gather at 2 GPUs (0.174 vs
-        # 0.182 ms per step) but starve it at 8 (0.26 - 0.46 ms), see DESIGN section 7.
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     warmup = max(args.warmup, 3)
     steps = args.steps
+    name = args.workload
+    wl = WORKLOADS[name]
+    batch = wl["batch"]
 
-    pipe = EpisodePipeline(BATCH, HEIGHT, WIDTH, [IMAGE_SIZE] * BATCH, channels=CHANNELS, shots=SHOTS,
-                           params=PostParams(**PARAMS), match_mode="product", device=dev,
-                           double_buffer=(world > 1 and args.gather == "block"))
-    fill_inputs(pipe, seed=2000 + rank)
-    ep_off = rank * BATCH
+    block_mode = args.gather in ("peer", "peer-kernel", "block")
+    pipe = make_pipe(name, dev, double_buffer=(world > 1 and block_mode))
+    fill_inputs(pipe, seed=2000 + rank, heads=wl["heads"])
+    ep_off = rank * batch
 
     overlap = not args.serial
     launch = "eager"
@@ -292,21 +486,27 @@ def run_b200_arm(args):
             print(f"[bench] CUDA-graph capture failed ({exc}); launching eagerly", file=sys.stderr)
             torch.cuda.synchronize()
 
-    # N > 1: the step's detections go to every rank with one asynchronous NCCL all-gather.  "block" (default): the
-    # post-processing outputs of a step are one contiguous result block in a double-buffered pipeline and that block is
-    # gathered as is, every step, without packing kernels.  "packed": [E, K+1, 6] payloads packed by copy kernels and
-    # gathered in groups of --gather-every steps (the reference gathers once, after the whole dataset).
+    # N > 1: the step's detections go to every rank.  "peer" (default): the result block of a step (one contiguous
+    # buffer of a double-buffered pipeline) is pushed into every rank's receive buffer through CUDA-IPC-mapped peer
+    # memory on the copy engines -- no collective kernel shares the SMs with the step.  "peer-kernel": the same push as
+    # one small kernel of ours storing through the peer pointers.  "block": one asynchronous NCCL all-gather of the block
+    # per step.  "packed": [E, K+1, 6] payloads gathered in groups of --gather-every steps.
     gatherer = None
+    K = pipe.post.plan.out_capacity
     if world > 1 and args.gather != "none":
-        if args.gather == "block":
-            gatherer = BlockGatherer(BATCH, pipe.post.plan.out_capacity, dev)
+        if args.gather in ("peer", "peer-kernel"):
+            gatherer = PeerBlockGatherer(batch, K, dev, mode="copy" if args.gather == "peer" else "kernel")
+        elif args.gather == "block":
+            gatherer = BlockGatherer(batch, K, dev)
         else:
-            gatherer = DetectionGatherer(BATCH, pipe.post.plan.out_capacity, dev, ep_off, steps_per_gather=args.gather_every)
+            gatherer = DetectionGatherer(batch, K, dev, ep_off, steps_per_gather=args.gather_every)
 
     def step():
+        if gatherer is not None and block_mode:
+            gatherer.acquire()         # the exchange that still reads the block this step overwrites has finished
         res = step_fn()
-        if gatherer is not None:   # asynchronous: NCCL moves step i over NVLink while step i+1 computes
-            if args.gather == "block":
+        if gatherer is not None:       # asynchronous: step i crosses NVLink while step i+1 computes
+            if block_mode:
                 gatherer.submit(res.block)
             else:
                 gatherer.submit(res.boxes, res.scores, res.count)
@@ -339,57 +539,77 @@ def run_b200_arm(args):
     counts = res.count.cpu().tolist()
 
     # ---- timed region: exactly `steps` steps, CUDA events on the launching stream, barrier + sync both sides
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 2)]
     sampler = ClockSampler(local_rank)
+    final_gather = None
+    if world > 1 and block_mode:
+        final_gather = torch.empty((world, gatherer.block_bytes), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(final_gather.view(-1), res.block)     # NCCL communicator set up before the timing
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ops.reset_launch_count()
     sampler.start()
     t_host0 = time.perf_counter()
+    ev[0].record()
     for i in range(steps):
-        ev[i][0].record()
-        step()
-        ev[i][1].record()
+        res = step()
+        ev[i + 1].record()
     if gatherer is not None:
-        gatherer.finish()     # the last gathers are inside the timed region
-        ev[-1][1].record()
+        gatherer.finish()     # the last exchanges are inside the timed region
+        if final_gather is not None:
+            # north_star's "final NCCL all-gather of detections": the last step's block, once, through NCCL
+            dist.all_gather_into_tensor(final_gather.view(-1), res.block)
+    ev[steps + 1].record()
     torch.cuda.synchronize()
     t_host1 = time.perf_counter()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
     launches = launches_per_step * steps
-    total_ms = ev[0][0].elapsed_time(ev[-1][1])
-    match_ms, post_ms = iso_match, iso_post
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    total_ms = ev[0].elapsed_time(ev[steps + 1])
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    t = torch.tensor([total_ms, statistics.median(per_step)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    value = BATCH * n_gpus * steps / (total_ms_max * 1e-3)
+    total_ms_max, median_ms_max = float(t[0].item()), float(t[1].item())
+    value = batch * n_gpus * steps / (total_ms_max * 1e-3)
+
+    # ---- the exchange delivered every rank's block: pushed copy == NCCL copy == (for this rank) the local block
+    exchange = None
+    if world > 1 and block_mode:
+        slot = (gatherer.i - 1) % 2
+        if args.gather == "block":
+            got = gatherer.out[slot].view(world, gatherer.block_bytes)
+        else:
+            got = gatherer.recv[slot]
+        ok_nccl = bool(torch.equal(got, final_gather))
+        ok_local = bool(torch.equal(got[rank], res.block))
+        flag = torch.tensor([int(ok_nccl and ok_local)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exchange = {"mode": args.gather, "block_bytes": gatherer.block_bytes, "ranks": world,
+                    "equals_nccl_all_gather": ok_nccl, "own_block_round_trip": ok_local, "all_ranks_ok": bool(flag.item())}
 
     # ---- roofline of the dominant streaming kernel (match_product_bulk_kernel: one launch per step)
     locs = sum(h * w for h, w in pipe.shapes)
-    match_bytes = 2 * 4 * CHANNELS * locs * BATCH                     # fp32 in + out, SURVEY section 8(d)
-    match_avg_ms = statistics.mean(match_ms)
-    peak, peak_src = measured_peak_hbm()
+    match_bytes = 2 * 4 * CHANNELS * locs * batch                     # fp32 in + out, SURVEY section 8(d)
+    match_avg_ms = statistics.mean(iso_match)
+    peak, tpeak, peak_src = measured_peaks()
     achieved = match_bytes / (match_avg_ms * 1e-3) / 1e9
     roofline = {"kernel": "match_product_bulk_kernel<float>", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
                 "algorithmic_bytes_per_launch": match_bytes, "avg_launch_ms": match_avg_ms, "peak_source": peak_src,
                 "timing": "CUDA events around the kernel on its launching stream, kernel running alone (serial loop "
                           "right before the timed region); inside the timed region it overlaps the post-processing chain",
-                "share_of_serial_step": match_avg_ms / (match_avg_ms + statistics.mean(post_ms))}
-    post_read = 6 * 4 * locs * BATCH
-    stages = {"match_ms_isolated": match_avg_ms, "post_ms_isolated": statistics.mean(post_ms),
-              "serial_ms_per_step": match_avg_ms + statistics.mean(post_ms),
+                "share_of_serial_step": match_avg_ms / (match_avg_ms + statistics.mean(iso_post))}
+    stages = {"match_ms_isolated": match_avg_ms, "post_ms_isolated": statistics.mean(iso_post),
+              "serial_ms_per_step": match_avg_ms + statistics.mean(iso_post),
               "overlap": "match || post-processing on two streams (software pipelining)" if overlap else "none (one stream)",
-              "launch": launch,
-              "post_algorithmic_read_bytes": post_read,
+              "launch": launch, "post_algorithmic_read_bytes": 6 * 4 * locs * batch,
               "host_ms_per_step": 1e3 * (t_host1 - t_host0) / steps}
 
     # ---- the 1x1 fusion-conv matching mode (BASELINE configs[1]: "fp32 matching + bf16 1x1 fusion conv"), timed as
-    #      its own stage on the same resident features: bias fold + conv1 (tcgen05) + conv2 (tcgen05) + GN/LeakyReLU
+    #      its own stage on the same resident features
     fusion = None
     if not args.no_fusion:
         from oneshotdet_b200 import MatchingModule
@@ -397,42 +617,36 @@ def run_b200_arm(args):
 
         torch.manual_seed(1234 + rank)
         mm = MatchingModule("fusion", channels=CHANNELS).to(dev)
-        pf = PreparedFusion(pipe.features, pipe.supp, BATCH, mm.compress_dim_conv, "full")
+        pf = PreparedFusion(pipe.features, pipe.supp, batch, mm.compress_dim_conv, "full")
         for _ in range(3):
             pf()
         torch.cuda.synchronize()
         fsteps = max(3, min(steps, 20))
-        fe = [torch.cuda.Event(enable_timing=True) for _ in range(fsteps + 1)]
-        fe[0].record()
-        for i in range(fsteps):
-            pf()
-            fe[i + 1].record()
-        torch.cuda.synchronize()
-        f_ms = fe[0].elapsed_time(fe[-1]) / fsteps
-        flops = 2.0 * locs * BATCH * (CHANNELS * 2 * CHANNELS + 2 * CHANNELS * CHANNELS)      # executed (support half folded)
-        flops_ref = 2.0 * locs * BATCH * ((2 * CHANNELS) ** 2 + 2 * CHANNELS * CHANNELS)       # reference form
-        hbm = 4.0 * locs * BATCH * CHANNELS * (1 + 2 + 2 + 1 + 2)                               # x, y1 w+r, y2 w, GN pass r+w
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                tpeak = float(json.load(f)["bf16_tflops_sustained"])
-            tsrc = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
-        except Exception:  # noqa: BLE001
-            tpeak, tsrc = 1400.0, "fallback (B200_PROFILING.md sustained)"
-        fusion = {"ms_per_step": f_ms, "episodes_per_s": BATCH / (f_ms * 1e-3), "steps": fsteps,
-                  "executed_tflops": flops / (f_ms * 1e-3) / 1e12, "reference_form_tflops": flops_ref / (f_ms * 1e-3) / 1e12,
-                  "tensor_peak_tflops": tpeak, "tensor_frac_executed": flops / (f_ms * 1e-3) / 1e12 / tpeak,
-                  "tensor_peak_source": tsrc, "hbm_algorithmic_bytes": hbm,
-                  "hbm_gbs": hbm / (f_ms * 1e-3) / 1e9, "hbm_frac": hbm / (f_ms * 1e-3) / 1e9 / peak,
-                  "what": "compress_dim_conv on P3-P7 for 16 episodes: folded-bias kernel + 2 tcgen05 GEMM launches "
-                          "(bf16 operands, fp32 accumulate, fp32 intermediates) + GroupNorm/LeakyReLU pass"}
+        f_ms, f_med = time_steps(pf, fsteps, torch)
+        flops = 2.0 * locs * batch * (CHANNELS * 2 * CHANNELS + 2 * CHANNELS * CHANNELS)      # executed once (support half folded)
+        flops_exec = flops * 1.5                                                                # conv1 runs in both passes
+        flops_ref = 2.0 * locs * batch * ((2 * CHANNELS) ** 2 + 2 * CHANNELS * CHANNELS)       # reference form
+        hbm_alg = 4.0 * locs * batch * CHANNELS * 2                                             # read x, write out
+        hbm_design = 2.0 * locs * batch * CHANNELS * 10                                         # 20C bytes per pixel over the 3 passes
+        fusion = {"ms_per_step": f_ms, "ms_per_step_median": f_med, "episodes_per_s": batch / (f_ms * 1e-3), "steps": fsteps,
+                  "useful_tflops": flops / (f_ms * 1e-3) / 1e12, "executed_tflops": flops_exec / (f_ms * 1e-3) / 1e12,
+                  "reference_form_tflops": flops_ref / (f_ms * 1e-3) / 1e12,
+                  "tensor_peak_tflops": tpeak, "tensor_frac_executed": flops_exec / (f_ms * 1e-3) / 1e12 / tpeak,
+                  "tensor_peak_source": peak_src, "hbm_algorithmic_bytes": hbm_alg, "hbm_design_bytes": hbm_design,
+                  "hbm_gbs_design": hbm_design / (f_ms * 1e-3) / 1e9, "hbm_frac_design": hbm_design / (f_ms * 1e-3) / 1e9 / peak,
+                  "what": "compress_dim_conv on P3-P7 for the batch: folded-bias kernel; pass A = conv1 statistics (tcgen05) + "
+                          "bf16 copy of x; pass B = conv1 -> GN1 -> LeakyReLU -> conv2 back to back on tcgen05 with the 2C "
+                          "intermediate in TMEM; pass C = GroupNorm-2/LeakyReLU in place"}
 
-    # ---- end-to-end through the public API with pinned host buffers
+    # ---- end-to-end through the public API with pinned host buffers: pipelined HostStreamer (H2D of batch i+1 on a copy
+    #      stream while batch i replays, D2H on a third stream) and the plain serial run_host, against the measured
+    #      host->device ceiling of the same buffers
     e2e = None
     if rank == 0 or world > 1:
         host_in = pipe.make_host_inputs(pinned=True)
         for h, d in zip(host_in, pipe.input_tensors()):
             h.copy_(d)
-        e2e_steps = max(3, min(steps, 10))
+        e2e_steps = max(4, min(steps, 10))
         pipe.run_host(host_in)
         if world > 1:
             dist.barrier()
@@ -441,36 +655,84 @@ def run_b200_arm(args):
         for _ in range(e2e_steps):
             out = pipe.run_host(host_in)
         torch.cuda.synchronize()
+        dt_serial = time.perf_counter() - t0
+        ceiling = h2d_ceiling(pipe, host_in, e2e_steps, torch, dist, world, dev)
+        pipe2 = make_pipe(name, dev)
+        streamer = HostStreamer([pipe, pipe2], use_graph=not args.no_graph)
+        for _ in range(2):
+            streamer.submit(host_in)
+        streamer.drain()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            streamer.submit(host_in)
+        out = streamer.drain()
+        torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        tt = torch.tensor([dt, dt_serial], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": BATCH * n_gpus * e2e_steps / float(tt.item()), "unit": UNIT,
+        dt, dt_serial = float(tt[0].item()), float(tt[1].item())
+        gbs = pipe.h2d_bytes * e2e_steps / dt / 1e9
+        e2e = {"value": batch * n_gpus * e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes, "steps": e2e_steps,
-               "api": "EpisodePipeline.run_host (pinned host inputs -> H2D -> match + post-process -> D2H detections)",
+               "api": "HostStreamer.submit (pinned host inputs -> H2D on a copy stream || graph replay of match + "
+                      "post-process || D2H of the detections; one event sync per returned result)",
+               "h2d_gbs_per_gpu": gbs, "h2d_ceiling_gbs_per_gpu": ceiling, "frac_of_h2d_ceiling": gbs / ceiling,
+               "serial_run_host_value": batch * n_gpus * e2e_steps / dt_serial,
                "check_count0": int(out[2][0])}
+        del streamer, pipe2
 
-    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload
-    cpu = None
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload, same inputs as the parity spot check
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ref = CpuReference(episodes=1)
+        res = pipe.run()
+        torch.cuda.synchronize()
+        parity, _ = parity_spot_check(name, pipe, res, with_cpu_time=False)
+        ref = CpuReference(name, episodes=1)
         ref.step()
         ts = [sum(ref.step()) for _ in range(4)]
         cpu = {"value": ref.episodes / statistics.median(ts), "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
                "sample": ref.sample_text() + f"; median of 4 steps, {statistics.median(ts):.3f} s/episode",
                "multi_process": None if args.no_multi_process else cpu_multi_process_throughput()}
 
+    # ---- the other BASELINE configs and the NMS worst cases (N = 1: parity-test cases, reported beside the headline)
+    extra = None
+    if rank == 0 and world == 1 and not args.no_workloads:
+        extra = {}
+        del pipe
+        torch.cuda.empty_cache()
+        for wname in WORKLOADS:
+            if wname == name:
+                continue
+            try:
+                extra[wname] = run_extra_workload(wname, dev, steps, rank, use_graph=not args.no_graph)
+            except Exception as exc:  # noqa: BLE001  (report, do not lose the headline line)
+                extra[wname] = {"error": repr(exc)}
+
     if rank == 0:
+        gather_text = None
+        if world > 1:
+            gather_text = {"none": "none (DIAGNOSIS RUN: not a multi-GPU measurement)",
+                           "peer": "result block pushed to every rank's receive buffer over peer memory (copy engines), "
+                                   "every step, asynchronous; one final NCCL all-gather",
+                           "peer-kernel": "result block pushed to every rank by one store kernel over peer memory, every "
+                                          "step, asynchronous; one final NCCL all-gather",
+                           "block": "result block, NCCL all-gather every step, asynchronous",
+                           "packed": f"packed payloads, NCCL all-gather every {args.gather_every} steps, asynchronous"}[args.gather]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
-                "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak",
-                "gather": (("none (DIAGNOSIS RUN: not a multi-GPU measurement)" if args.gather == "none" else
-                            "result block, every step, async" if args.gather == "block" else
-                            f"packed payloads, every {args.gather_every} steps, async") if world > 1 else None),
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(n_gpus),
+                "ms_per_step": total_ms_max / steps, "ms_per_step_median": median_ms_max, "higher_is_better": True,
+                "scaling": "weak", "gather": gather_text, "exchange_check": exchange,
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(n_gpus, name, gather_text),
                 "roofline": roofline, "stages": stages, "fusion_mode": fusion, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks,
-                "check": {"detections_per_episode": counts[:4], "kept_before_cut": kept[:4]}}
+                "check": {"detections_per_episode": counts[:4], "kept_before_cut": kept[:4], "parity": parity},
+                "workloads": extra}
         print(json.dumps(line), flush=True)
+    if gatherer is not None and hasattr(gatherer, "close"):
+        gatherer.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -482,17 +744,20 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS),
+                    help="headline workload of the line (default: BASELINE configs[1]); the others are reported under "
+                         "`workloads` of the default N=1 run")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the extra workloads of the N=1 run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-multi-process", action="store_true",
                     help="skip the multi-process variant of the CPU baseline (cpu_baseline.multi_process)")
     ap.add_argument("--ref-worker", type=int, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--no-fusion", action="store_true")
     ap.add_argument("--serial", action="store_true", help="one stream: matching then post-processing, no overlap")
-    ap.add_argument("--gather", choices=["block", "packed", "none"], default="block",
-                    help="N>1: gather the step's result block as is (default), pack [E,K+1,6] payloads, or (diagnosis "
-                         "only: not a valid multi-GPU measurement) no gather at all")
+    ap.add_argument("--gather", choices=["peer", "peer-kernel", "block", "packed", "none"], default="peer",
+                    help="N>1: how a step's detections reach every rank (see run_b200_arm); 'none' is a diagnosis run")
     ap.add_argument("--gather-every", type=int, default=10,
-                    help="N>1: steps per NCCL all-gather of the detections (1 = every step)")
+                    help="N>1, --gather packed: steps per NCCL all-gather of the detections (1 = every step)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.ref_worker is not None:

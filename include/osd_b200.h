@@ -365,6 +365,31 @@ int osd_coco_write_json(const float* records, const int32_t* record_episode, int
                         const int64_t* image_ids, const int64_t* category_ids, int32_t num_episodes,
                         const char* path);
 
+/* ------------------------------------------------------------------------------------------------
+ * Detection exchange over peer memory -- SURVEY section 8(e).
+ *
+ * Replaces  all_gather / scatter_gather of maskrcnn_benchmark/utils/comm.py:48-88 (pickle -> ByteTensor -> two
+ *           dist.all_gather -> unpickle) as used by engine/inference.py:133-152 (_accumulate_predictions_from_multiple_gpus)
+ *           for the fixed-shape result block of this path.
+ *
+ * Every rank (one process per GPU of one NVLink/NVSwitch box) owns a receive buffer allocated by osd_comm_alloc and
+ * exports it as a 64-byte CUDA IPC handle; the handles travel through the host-side process group once, at set-up,
+ * and osd_comm_import maps each peer's buffer into this process.  A step's result block is then PUSHED into every
+ * rank's buffer -- an all-gather with no rendezvous and no collective kernel: osd_comm_push issues one peer copy per
+ * destination on the copy engines (no SM is taken from the step's own kernels); osd_comm_push_kernel is the same
+ * exchange as ONE small kernel of ours storing through the mapped peer pointers (st.global over NVLink), for when the
+ * copy engines are busy with host traffic.  Both enqueue on `stream` and do not synchronise.  Ordering between ranks
+ * (when a receive slot may be overwritten, when it is complete) is the caller's: see PeerBlockGatherer.
+ * ---------------------------------------------------------------------------------------------- */
+#define OSD_IPC_HANDLE_BYTES 64
+int osd_comm_alloc(size_t bytes, void** ptr);   /* zero-filled device buffer outside any caching allocator (IPC-exportable) */
+int osd_comm_free(void* ptr);
+int osd_comm_export(void* ptr, unsigned char handle[OSD_IPC_HANDLE_BYTES]);
+int osd_comm_import(const unsigned char handle[OSD_IPC_HANDLE_BYTES], void** ptr);   /* peer access is enabled lazily */
+int osd_comm_close(void* ptr);                  /* unmaps an imported buffer */
+int osd_comm_push(void* const* dst, int32_t num_dst, const void* src, size_t bytes, void* stream);
+int osd_comm_push_kernel(void* const* dst, int32_t num_dst, const void* src, size_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

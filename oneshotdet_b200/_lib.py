@@ -117,6 +117,13 @@ SYMBOLS = {
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "osd_coco_write_json": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, ctypes.c_int32,
                                            ctypes.c_char_p]),
+    "osd_comm_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(c_void_p)]),
+    "osd_comm_free": (ctypes.c_int, [c_void_p]),
+    "osd_comm_export": (ctypes.c_int, [c_void_p, ctypes.c_char_p]),
+    "osd_comm_import": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(c_void_p)]),
+    "osd_comm_close": (ctypes.c_int, [c_void_p]),
+    "osd_comm_push": (ctypes.c_int, [ctypes.POINTER(c_void_p), ctypes.c_int32, c_void_p, ctypes.c_size_t, c_void_p]),
+    "osd_comm_push_kernel": (ctypes.c_int, [ctypes.POINTER(c_void_p), ctypes.c_int32, c_void_p, ctypes.c_size_t, c_void_p]),
     "osd_box_postprocess_plan": (ctypes.c_int, [ctypes.POINTER(BoxPostConfig), ctypes.POINTER(BoxPostPlan)]),
     "osd_box_postprocess": (ctypes.c_int, [ctypes.POINTER(BoxPostConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, ctypes.c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -178,7 +185,9 @@ def current_stream_ptr(device) -> int:
 
 
 class Workspace:
-    """Grow-only per-device scratch buffer from PyTorch's caching allocator (stream-ordered reuse)."""
+    """Grow-only scratch buffer per (device, stream) from PyTorch's caching allocator.  Reuse is stream-ordered, which is
+    only sound within ONE stream: calls issued on different streams get different buffers, and a buffer that is replaced by
+    a larger one goes back to the allocator on the stream that used it."""
 
     def __init__(self):
         self._buf = {}
@@ -186,7 +195,8 @@ class Workspace:
     def get(self, device, nbytes: int):
         import torch
 
-        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = (device.type, idx, torch.cuda.current_stream(idx).cuda_stream)
         buf = self._buf.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

@@ -114,7 +114,7 @@ class BlockGatherer:
     stage writes boxes | scores | index | count of a step into ONE result block (``FcosResult.block``), and that block is
     what goes over NVLink -- no packing kernels.  ``submit(block)`` issues one asynchronous ``all_gather_into_tensor`` of
     the block; before issuing it makes the current stream wait for the gather two steps back, whose source block the next
-    step will overwrite.  ``result(slot)`` returns the (boxes, scores, index, count) views of every rank's block."""
+    step will overwrite -- call ``acquire()`` before launching a step and ``submit(block)`` after it.  ``result(slot)`` returns the (boxes, scores, index, count) views of every rank's block."""
 
     def __init__(self, e_local: int, k: int, device, group=None):
         from . import ops
@@ -127,11 +127,20 @@ class BlockGatherer:
         self.work = [None, None]
         self.i = 0
 
+    def acquire(self):
+        """Call BEFORE launching (or replaying) the step whose result block ``submit`` will ship next: makes the current
+        stream wait for the gather issued two steps ago, which reads the block that step is about to overwrite.  (The
+        wait inside ``submit`` alone comes too late -- by then the step's kernels are already enqueued.)"""
+        slot = self.i & 1
+        if self.work[slot] is not None:
+            self.work[slot].wait()
+            self.work[slot] = None
+
     def submit(self, block):
         slot = self.i & 1
         self.i += 1
-        if self.work[slot] is not None:
-            self.work[slot].wait()          # stream-side wait: the block written two steps ago has been shipped
+        if self.work[slot] is not None:     # acquire() was not called: still order the collective itself
+            self.work[slot].wait()
             self.work[slot] = None
         if block.numel() != self.block_bytes:
             raise ValueError(f"result block of {block.numel()} bytes, expected {self.block_bytes}")
@@ -153,3 +162,130 @@ class BlockGatherer:
 
         blocks = self.out[slot].view(self.world, self.block_bytes)
         return [ops.result_block(self.e, self.k, blocks.device, blocks[r])[1] for r in range(self.world)]
+
+
+class PeerBlockGatherer:
+    """The same exchange without a collective kernel: every rank owns a receive buffer [slots][world][block] that its
+    peers map through CUDA IPC (handles travel once through the host-side process group); ``submit(block)`` PUSHES the
+    step's result block into slot ``i % slots``, row ``rank`` of every rank's buffer -- one peer copy per destination on
+    the copy engines, issued on a side stream behind an event of the compute stream (``mode='kernel'``: one small
+    kernel of ours storing through the mapped peer pointers instead).  No SM is taken from the step's kernels and no
+    rendezvous sits between the ranks, which is what NCCL's per-step all-gather kernel cost at 2-8 GPUs (DESIGN section
+    7).  ``acquire()`` before a step makes the compute stream wait until the pushes that still read the block it
+    overwrites have been issued to completion; ``finish()`` drains the pushes and runs a process-group barrier, after
+    which ``result(slot)`` holds every rank's block of the last ``slots`` steps.  Between two ``finish`` (or ``fence``)
+    calls at most ``slots`` steps may be submitted if a consumer reads the results on other ranks."""
+
+    def __init__(self, e_local: int, k: int, device, group=None, slots: int = 2, mode: str = "copy"):
+        import ctypes
+
+        from . import _lib, ops
+
+        if mode not in ("copy", "kernel"):
+            raise ValueError("mode must be 'copy' or 'kernel'")
+        self.group, self.mode, self.slots = group, mode, slots
+        self.device = torch.device(device)
+        ok = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if ok else 1
+        self.rank = dist.get_rank(group) if ok else 0
+        self.e, self.k = e_local, k
+        _, self.block_bytes = ops.result_block_layout(e_local, k)
+        self.lib = _lib.load()
+        _lib.require_device(self.device)
+        nbytes = slots * self.world * self.block_bytes
+        with torch.cuda.device(self.device):
+            p = ctypes.c_void_p()
+            _lib.check(self.lib.osd_comm_alloc(nbytes, ctypes.byref(p)), "osd_comm_alloc")
+            self._own = p.value
+            h = ctypes.create_string_buffer(64)
+            _lib.check(self.lib.osd_comm_export(self._own, h), "osd_comm_export")
+            handles = [None] * self.world
+            if self.world > 1:
+                dist.all_gather_object(handles, h.raw, group=group)
+            else:
+                handles[0] = h.raw
+            self._peer = []
+            for r, raw in enumerate(handles):
+                if r == self.rank:
+                    self._peer.append(self._own)
+                    continue
+                q = ctypes.c_void_p()
+                _lib.check(self.lib.osd_comm_import(ctypes.create_string_buffer(raw, 64), ctypes.byref(q)), "osd_comm_import")
+                self._peer.append(q.value)
+        self._ptrs = (ctypes.c_void_p * self.world)()
+        # receive buffer as a tensor view (no copy): [slots, world, block_bytes] uint8
+        self.recv = _wrap_device_memory(self._own, nbytes, self.device).view(slots, self.world, self.block_bytes)
+        self.side = torch.cuda.Stream(self.device)
+        self.ready = [torch.cuda.Event() for _ in range(slots)]     # compute -> side: block written
+        self.pushed = [None] * slots                                # side -> compute: block has been read by the pushes
+        self.i = 0
+
+    def acquire(self):
+        """Before launching the step that overwrites the block submitted ``slots`` steps ago (with a double-buffered
+        pipeline and slots = 2: two steps ago)."""
+        ev = self.pushed[self.i % self.slots]
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def submit(self, block):
+        import ctypes
+
+        from . import _lib
+
+        if block.numel() != self.block_bytes:
+            raise ValueError(f"result block of {block.numel()} bytes, expected {self.block_bytes}")
+        slot = self.i % self.slots
+        self.i += 1
+        off = (slot * self.world + self.rank) * self.block_bytes
+        for r in range(self.world):
+            self._ptrs[r] = self._peer[r] + off
+        self.ready[slot].record(torch.cuda.current_stream(self.device))
+        self.side.wait_event(self.ready[slot])
+        fn = self.lib.osd_comm_push if self.mode == "copy" else self.lib.osd_comm_push_kernel
+        with torch.cuda.device(self.device):
+            _lib.check(fn(self._ptrs, self.world, block.data_ptr(), self.block_bytes, self.side.cuda_stream), "osd_comm_push")
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        self.pushed[slot] = ev
+        return slot
+
+    def fence(self):
+        """All pushes issued so far by every rank have landed (process-group barrier behind a drained side stream)."""
+        self.side.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    finish = fence
+
+    def result(self, slot):
+        """List over ranks of (boxes [E,K,4], scores [E,K], index [E,K], count [E]) views of the received blocks."""
+        from . import ops
+
+        return [ops.result_block(self.e, self.k, self.device, self.recv[slot, r])[1] for r in range(self.world)]
+
+    def close(self):
+        from . import _lib
+
+        if getattr(self, "_own", None) is None:
+            return
+        with torch.cuda.device(self.device):
+            self.side.synchronize()
+            if self.world > 1:
+                dist.barrier(group=self.group)       # nobody pushes into a buffer that is about to be unmapped
+            for r, p in enumerate(self._peer):
+                if r != self.rank:
+                    _lib.check(self.lib.osd_comm_close(p), "osd_comm_close")
+            self.recv = None
+            _lib.check(self.lib.osd_comm_free(self._own), "osd_comm_free")
+        self._own = None
+
+
+def _wrap_device_memory(ptr: int, nbytes: int, device):
+    """uint8 tensor view of raw device memory (``__cuda_array_interface__``); the caller keeps the memory alive."""
+
+    class _Raw:
+        pass
+
+    raw = _Raw()
+    raw.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+    return torch.as_tensor(raw, device=device)

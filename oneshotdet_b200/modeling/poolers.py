@@ -104,14 +104,19 @@ class Pooler(nn.Module):
         return out.view(rois.size(0), rois.size(1), out.size(1), out.size(2), out.size(3))
 
     def forward(self, x, boxes):
-        """poolers.py:93-125: ``boxes`` is a list of BoxList with equal lengths (:79); returns [bs, R, C, P, P]."""
+        """poolers.py:93-125: ``boxes`` is a list of BoxList with equal lengths (:79); returns [bs, R, C, P, P] for several
+        levels (:123) and, as the reference does (:104-106), the 4-D [bs*R, C, P, P] output of the only ROIAlign when
+        there is a single level."""
         if len(x) != len(self.scales):
             raise ValueError(f"{len(self.scales)} poolers but {len(x)} feature levels")  # poolers.py:101-102
         counts = {len(b) for b in boxes}
         if len(counts) != 1:
             raise ValueError(f"all images must carry the same number of boxes, got {sorted(counts)}")  # :79
         rois = torch.stack([b.convert("xyxy").bbox for b in boxes], dim=0).to(torch.float32)
-        return self.forward_fixed(x, rois)
+        out = self.forward_fixed(x, rois)
+        if len(self.scales) == 1:
+            return out.reshape(out.size(0) * out.size(1), out.size(2), out.size(3), out.size(4))
+        return out
 
 
 def make_pooler(cfg, head_name):

@@ -169,3 +169,71 @@ class EpisodePipeline:
         b, k = res.scores.shape
         eid = torch.arange(episode_offset, episode_offset + b, device=res.scores.device, dtype=torch.float32)
         return torch.cat((res.boxes, res.scores.unsqueeze(-1), eid.view(b, 1, 1).expand(b, k, 1)), dim=-1), res.count
+
+
+class HostStreamer:
+    """End-to-end serving loop over HOST batches, software-pipelined across steps: two EpisodePipelines (two sets of
+    device inputs and outputs) alternate; batch i+1 crosses PCIe on a copy stream while batch i computes (CUDA-graph
+    replay on the compute stream) and the detections of batch i-1 return on a third stream.  ``submit(host_inputs)``
+    enqueues one batch and returns the host detections of the PREVIOUS batch (``None`` for the first call) -- one host
+    synchronisation per returned result, on an event, never on the device; ``drain()`` returns the last one.  The
+    per-step cost is max(H2D, compute, D2H) instead of their sum (``run_host``)."""
+
+    def __init__(self, pipes, use_graph: bool = True):
+        assert len(pipes) >= 2, "HostStreamer alternates between at least two pipelines"
+        self.pipes = list(pipes)
+        dev = self.pipes[0].device
+        self.device = dev
+        self.s_h2d, self.s_run, self.s_d2h = (torch.cuda.Stream(dev) for _ in range(3))
+        n = len(self.pipes)
+        self.ev_in = [torch.cuda.Event() for _ in range(n)]      # inputs of slot landed
+        self.ev_run = [torch.cuda.Event() for _ in range(n)]     # compute of slot finished (inputs may be overwritten)
+        self.ev_out = [torch.cuda.Event() for _ in range(n)]     # detections of slot are on the host
+        self.host_out = [None] * n
+        self.steps = []
+        for p in self.pipes:
+            if use_graph:
+                with torch.cuda.stream(self.s_run):
+                    self.steps.append(p.capture(overlapped=False))
+            else:
+                self.steps.append(p.run)
+        torch.cuda.synchronize(dev)
+        self.i = 0
+        self._pending = None
+
+    def submit(self, host_inputs):
+        slot = self.i % len(self.pipes)
+        pipe = self.pipes[slot]
+        if self.i >= len(self.pipes):
+            self.s_h2d.wait_event(self.ev_run[slot])     # the step that last read these device inputs has finished
+        with torch.cuda.stream(self.s_h2d):
+            for dst, src in zip(pipe.input_tensors(), host_inputs):
+                dst.copy_(src, non_blocking=True)
+            self.ev_in[slot].record(self.s_h2d)
+        self.s_run.wait_event(self.ev_in[slot])
+        if self.i >= len(self.pipes):
+            self.s_run.wait_event(self.ev_out[slot])     # its previous detections have left the device
+        with torch.cuda.stream(self.s_run):
+            res = self.steps[slot]()
+            self.ev_run[slot].record(self.s_run)
+        self.s_d2h.wait_event(self.ev_run[slot])
+        with torch.cuda.stream(self.s_d2h):
+            if self.host_out[slot] is None:
+                self.host_out[slot] = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                                            for t in (res.boxes, res.scores, res.count))
+            for dst, src in zip(self.host_out[slot], (res.boxes, res.scores, res.count)):
+                dst.copy_(src, non_blocking=True)
+            self.ev_out[slot].record(self.s_d2h)
+        prev, self._pending = self._pending, slot
+        self.i += 1
+        if prev is None:
+            return None
+        self.ev_out[prev].synchronize()
+        return self.host_out[prev]
+
+    def drain(self):
+        if self._pending is None:
+            return None
+        slot, self._pending = self._pending, None
+        self.ev_out[slot].synchronize()
+        return self.host_out[slot]

@@ -100,6 +100,53 @@ def build_ref(force: bool = False, verbose: bool = False) -> str | None:
     return REF_SO
 
 
+PYREF_DIR = os.path.join(REF_OUT_DIR, "pyref")
+
+
+def vendor_reference_python(force: bool = False) -> str | None:
+    """Copy the reference's Python package (maskrcnn_benchmark/**/*.py, unmodified, no csrc) next to the compiled ops,
+    into oracle/_ref/pyref -- git-ignored build output that gpurun ships to the GPU box, so that `bench.py --impl
+    reference` can run the reference's own FCOSPostProcessor there.  Needs /root/reference; returns the directory, or
+    None when neither the reference tree nor a previous copy exists."""
+    import shutil
+
+    src_pkg = os.path.join(REF_ROOT, "maskrcnn_benchmark")
+    dst_pkg = os.path.join(PYREF_DIR, "maskrcnn_benchmark")
+    marker = os.path.join(dst_pkg, "modeling", "rpn", "fcos", "inference.py")
+    if not os.path.isdir(src_pkg):
+        return PYREF_DIR if os.path.exists(marker) else None
+    if os.path.exists(marker) and not force:
+        return PYREF_DIR
+    if os.path.isdir(dst_pkg):
+        shutil.rmtree(dst_pkg)
+    for root, dirs, files in os.walk(src_pkg):
+        rel = os.path.relpath(root, src_pkg)
+        if rel.split(os.sep)[0] == "csrc":
+            dirs[:] = []
+            continue
+        os.makedirs(os.path.join(dst_pkg, rel), exist_ok=True)
+        for f in files:
+            if f.endswith(".py"):
+                shutil.copyfile(os.path.join(root, f), os.path.join(dst_pkg, rel, f))
+    return PYREF_DIR
+
+
+def load_reference_python():
+    """Make the vendored, unmodified reference package importable with the compiled CPU ops injected as
+    ``maskrcnn_benchmark._C``.  Returns the ``_C`` module, or None if unavailable."""
+    ref_c = load_ref()
+    pyref = vendor_reference_python()
+    if ref_c is None or pyref is None:
+        return None
+    if pyref not in sys.path:
+        sys.path.insert(0, pyref)
+    import maskrcnn_benchmark  # noqa: PLC0415
+
+    maskrcnn_benchmark._C = ref_c
+    sys.modules["maskrcnn_benchmark._C"] = ref_c
+    return ref_c
+
+
 def load_ref():
     """Import oracle/_ref/osd_ref_C.so as a module exposing nms / roi_align_forward.
     Returns None when it has not been built (and cannot be)."""
@@ -119,3 +166,4 @@ if __name__ == "__main__":
     v = "-v" in sys.argv
     print("C oracle  :", build_c_oracle(force="-f" in sys.argv, verbose=v))
     print("reference :", build_ref(force="-f" in sys.argv, verbose=v))
+    print("ref python:", vendor_reference_python(force="-f" in sys.argv))

@@ -25,7 +25,8 @@ def test_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None
     assert "workload" in line["config"] and "model" not in line["config"]
     cb = line["cpu_baseline"]
-    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert cb["kind"] in ("reference", "port", "port+reference-nms") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["cpu_processes"] == 1
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -154,9 +154,12 @@ def _block_gatherer_worker(rank, world, port, q):
         ok = True
         for step in range(5):
             block, views = blocks[step & 1]
+            # the documented order: acquire() BEFORE the step overwrites the block the gather two steps back still reads
+            g.acquire()
+            assert g.work[step & 1] is None, "acquire() must have drained the gather that reads this block"
             fill(views, step, rank)
             slot = g.submit(block)
-            assert slot == step & 1
+            assert slot == step & 1 and g.work[slot] is not None
         g.finish()
         for step in (3, 4):                                   # the two groups still resident
             per_rank = g.result(step & 1)
