@@ -36,6 +36,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 
 #include "fusion_internal.cuh"
 #include "osd_common.cuh"
@@ -48,8 +49,13 @@ using namespace tc;
 constexpr int kTileM = 128;             // pixels per tile (UMMA M, TMEM lanes)
 constexpr int kChunk = 128;             // conv1 output channels per chunk (UMMA N of conv1, K of one conv2 block)
 constexpr int kStageK = 64;             // K elements per weight stage (one 128-byte swizzle row of bf16)
-constexpr int kStageBytes = 128 * 128;  // 16 KB: 128 rows x 64 K
-constexpr int kStages = 5;
+// weight ring: 80 KB per CTA.  One CTA per tile: 5 stages of 16 KB (128 rows x 64 K).  CTA pairs (cta_group::2): every
+// CTA holds HALF the rows of a stage (8 KB) -- 10 stages, and half the L2 -> SM weight stream per CTA.
+template <bool TWO> struct Ring {
+  static constexpr int kStages = TWO ? 10 : 5;
+  static constexpr int kStageBytes = TWO ? 64 * 128 : 128 * 128;   // bytes of a stage in THIS CTA's shared memory
+};
+constexpr int kRingBytes = 5 * 128 * 128;
 constexpr int kUmmaK = 16;
 constexpr uint32_t kD2Col = 256;        // TMEM columns: D1/y1 chunk buffers at 0 and 128, D2 at 256..511
 
@@ -90,6 +96,11 @@ struct TileInfo {
 };
 
 __device__ __forceinline__ TileInfo decode_tile(const FArgs& A, int tile) {
+  if (tile >= A.total_tiles) {   // the odd tile out of the last CTA pair: no valid pixel, coordinates past level 0's rows
+    TileInfo g;
+    g.level = 0; g.img = 0; g.px0 = A.lv[0].tiles_per_img * kTileM; g.nvalid = 0;
+    return g;
+  }
   int li = 0;
 #pragma unroll
   for (int k = 1; k < OSD_MAX_LEVELS; ++k)
@@ -110,15 +121,16 @@ struct Smem {
   static constexpr uint32_t x_bytes = C * 256;                 // one activation tile: [C rows][128 px] bf16
   static constexpr uint32_t x_off = 0;
   static constexpr uint32_t w_off = 2 * x_bytes;
-  static constexpr uint32_t aux_off = w_off + kStages * kStageBytes;
+  static constexpr uint32_t aux_off = w_off + kRingBytes;
   // aux: pass A: bias1 [2][2C] floats; pass B: coef1 [2][2C] float2, b2 [C] floats, coef2 [2][C] float2
   static constexpr uint32_t aux_bytes = 2 * 2 * C * 8 + C * 4 + 2 * C * 8;
   static constexpr uint32_t bar_off = aux_off + aux_bytes;
   static constexpr uint32_t total = bar_off + 256 + 1024;       // barriers + alignment slack
 };
 
+constexpr int kMaxRingStages = 10;
 struct Bars {
-  uint32_t w_full, w_empty;      // [kStages] each
+  uint32_t w_full, w_empty;      // [ring stages] each
   uint32_t x_full, x_empty;      // [2]
   uint32_t d1_full, d1_done;     // [2]: conv1 chunk accumulated / chunk epilogue finished (y1 written or D1 drained)
   uint32_t d2_full, d2_empty;    // [1]
@@ -127,8 +139,8 @@ struct Bars {
 __device__ __forceinline__ Bars make_bars(uint32_t base) {
   Bars b;
   b.w_full = base;
-  b.w_empty = base + 8u * kStages;
-  b.x_full = base + 16u * kStages;
+  b.w_empty = base + 8u * kMaxRingStages;
+  b.x_full = base + 16u * kMaxRingStages;
   b.x_empty = b.x_full + 16u;
   b.d1_full = b.x_full + 32u;
   b.d1_done = b.x_full + 48u;
@@ -161,10 +173,11 @@ __device__ __forceinline__ bool elect_one() {
 // than the 64 clk the tensor core needs for it.
 
 // conv1 block for one chunk: D1[buf] = x_tile . W1x[chunk rows]^T, K = C in stages of 64
-template <int C>
+template <int C, bool TWO>
 __device__ __forceinline__ void issue_conv1(const Bars& bar, uint32_t sX, uint32_t sW, uint32_t tmem_d, uint32_t& wc,
                                             long long* tw = nullptr) {
-  constexpr uint32_t idesc = make_idesc_ex(kTileM, kChunk, /*a_mn=*/1, /*b_mn=*/0);
+  constexpr int kStages = Ring<TWO>::kStages, kStageBytes = Ring<TWO>::kStageBytes;
+  constexpr uint32_t idesc = make_idesc_ex(TWO ? 2 * kTileM : kTileM, kChunk, /*a_mn=*/1, /*b_mn=*/0);
   // A: MN-major SW128: 64-pixel atoms are x_bytes/2 apart (LBO), 8-channel groups 1024 B apart (SBO)
   const uint64_t adesc0 = make_smem_desc(sX, (uint32_t)C * 128u, 1024u);
   // B: K-major SW128: 8-row groups 1024 B apart (SBO), K advances by 32 B inside the swizzle row
@@ -179,20 +192,23 @@ __device__ __forceinline__ void issue_conv1(const Bars& bar, uint32_t sX, uint32
 #pragma unroll
       for (int k16 = 0; k16 < kStageK / kUmmaK; ++k16) {
         const uint32_t kgrp = (uint32_t)(kc * kStageK + k16 * kUmmaK) >> 3;
-        umma_bf16(tmem_d, adesc0 + (uint64_t)(kgrp * 64u), bs + (uint64_t)(k16 * 2), idesc, (kc | k16) != 0 ? 1u : 0u);
+        if (TWO) umma_bf16_2sm(tmem_d, adesc0 + (uint64_t)(kgrp * 64u), bs + (uint64_t)(k16 * 2), idesc, (kc | k16) != 0 ? 1u : 0u);
+        else umma_bf16(tmem_d, adesc0 + (uint64_t)(kgrp * 64u), bs + (uint64_t)(k16 * 2), idesc, (kc | k16) != 0 ? 1u : 0u);
       }
-      umma_commit(bar.w_empty + 8u * s);
+      if (TWO) umma_commit_2sm(bar.w_empty + 8u * s);
+      else umma_commit(bar.w_empty + 8u * s);
     }
     __syncwarp();
   }
 }
 
 // conv2 block for one chunk: D2 (+)= y1[buf] (TMEM, 128 px x 128 ch bf16) . W2[:, chunk]^T
-template <int C>
+template <int C, bool TWO>
 __device__ __forceinline__ void issue_conv2(const Bars& bar, uint32_t sW, uint32_t tmem_base, uint32_t buf, bool first_chunk,
                                             uint32_t& wc, long long* tw = nullptr) {
+  constexpr int kStages = Ring<TWO>::kStages, kStageBytes = Ring<TWO>::kStageBytes;
   constexpr int N2 = C < 128 ? C : 128;
-  constexpr uint32_t idesc = make_idesc_ex(kTileM, N2, /*a_mn=*/0, /*b_mn=*/0);
+  constexpr uint32_t idesc = make_idesc_ex(TWO ? 2 * kTileM : kTileM, N2, /*a_mn=*/0, /*b_mn=*/0);
   const uint64_t bdesc0 = make_smem_desc(sW, 16u, 1024u);
   const uint32_t acc0 = first_chunk ? 0u : 1u;
 #pragma unroll
@@ -209,10 +225,13 @@ __device__ __forceinline__ void issue_conv2(const Bars& bar, uint32_t sW, uint32
           // y1 channels [64 kc2, 64 kc2 + 64) of the chunk sit at columns [64 kc2, 64 kc2 + 32): each half was written in
           // place by the epilogue warp that read it; 16 bf16 = 8 columns per K step
           const uint32_t a_taddr = tmem_base + buf * (uint32_t)kChunk + (uint32_t)kc2 * 64u + (uint32_t)k16 * 8u;
-          umma_bf16_ts(tmem_base + kD2Col + (uint32_t)h * 128u, a_taddr, bs + (uint64_t)(k16 * 2), idesc,
-                       (kc2 | k16) != 0 ? 1u : acc0);
+          const uint32_t d_taddr = tmem_base + kD2Col + (uint32_t)h * 128u;
+          const uint32_t acc = (kc2 | k16) != 0 ? 1u : acc0;
+          if (TWO) umma_bf16_ts_2sm(d_taddr, a_taddr, bs + (uint64_t)(k16 * 2), idesc, acc);
+          else umma_bf16_ts(d_taddr, a_taddr, bs + (uint64_t)(k16 * 2), idesc, acc);
         }
-        umma_commit(bar.w_empty + 8u * s);
+        if (TWO) umma_commit_2sm(bar.w_empty + 8u * s);
+        else umma_commit(bar.w_empty + 8u * s);
       }
       __syncwarp();
     }
@@ -229,18 +248,58 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
   }
 }
 
+template <bool TWO>
 __device__ __forceinline__ void commit_elect(uint32_t bar) {
-  if (elect_one()) umma_commit(bar);
+  if (elect_one()) {
+    if (TWO) umma_commit_2sm(bar);
+    else umma_commit(bar);
+  }
   __syncwarp();
 }
 
+// arrival of a consumer role on a barrier that gates the MMA issue: in a CTA pair that barrier is the leader's
+template <bool TWO>
+__device__ __forceinline__ void arrive_gate(uint32_t bar) {
+  if (TWO) mbar_arrive_leader(bar);
+  else mbar_arrive(bar);
+}
+
+// One weight stage.  Pairs: this CTA loads ITS half of the rows (rows_half each) into its own ring; the bytes of both
+// halves are counted on the leader's full barrier (leader: arrive + expect_tx of both halves, follower: plain arrive).
+template <bool TWO>
 __device__ __forceinline__ void load_weight_stage(const Bars& bar, uint32_t sW, const CUtensorMap* map, int col, int row,
-                                                  uint32_t& wc) {
+                                                  uint32_t stage_tx_bytes, int rows_half, uint32_t rank, uint32_t& wc) {
+  constexpr int kStages = Ring<TWO>::kStages, kStageBytes = Ring<TWO>::kStageBytes;
   const uint32_t s = wc % kStages, ph = (wc / kStages) & 1u;
   mbar_wait(bar.w_empty + 8u * s, ph ^ 1u);
-  mbar_expect_tx(bar.w_full + 8u * s, kStageBytes);
-  tma_load_2d(sW + s * kStageBytes, map, col, row, bar.w_full + 8u * s);
+  if (TWO) {
+    if (rank == 0) mbar_expect_tx(bar.w_full + 8u * s, stage_tx_bytes);
+    else mbar_arrive_leader(bar.w_full + 8u * s);
+    tma_load_2d_2sm(sW + s * kStageBytes, map, col, row + (int)rank * rows_half, bar.w_full + 8u * s);
+  } else {
+    mbar_expect_tx(bar.w_full + 8u * s, stage_tx_bytes);
+    tma_load_2d(sW + s * kStageBytes, map, col, row, bar.w_full + 8u * s);
+  }
   ++wc;
+}
+
+// pairs: before a CTA exits, every multicast completion addressed to its barriers must have landed -- wait for the last
+// phase of each weight-stage "empty" barrier (wc = stages loaded) / activation "empty" barrier (it = tiles processed)
+template <bool TWO>
+__device__ __forceinline__ void drain_ring(const Bars& bar, uint32_t wc) {
+  constexpr int kStages = Ring<TWO>::kStages;
+  for (uint32_t s = 0; s < (uint32_t)kStages; ++s) {
+    if (wc <= s) continue;
+    const uint32_t uses = (wc - s + kStages - 1) / kStages;
+    mbar_wait(bar.w_empty + 8u * s, (uses - 1) & 1u);
+  }
+}
+__device__ __forceinline__ void drain_x(const Bars& bar, uint32_t it) {
+  for (uint32_t b = 0; b < 2; ++b) {
+    if (it <= b) continue;
+    const uint32_t uses = (it - b + 1) / 2;
+    mbar_wait(bar.x_empty + 8u * b, (uses - 1) & 1u);
+  }
 }
 
 // Sum 32 per-lane values over the warp's lanes: afterwards v[0] of lane L holds the total of value L (31 shuffles
@@ -261,10 +320,13 @@ __device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane
 // ------------------------------------------------------------------------------------------------
 // pass A: conv1 statistics (+ bf16 copy of x)
 // ------------------------------------------------------------------------------------------------
-template <int C>
+template <int C, bool TWO>
 __global__ void __launch_bounds__(kThreadsA, 1)
 fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A) {
   using S = Smem<C>;
+  constexpr int kStages = Ring<TWO>::kStages;
+  const uint32_t rank = TWO ? (blockIdx.x & 1u) : 0u;          // cluster dims (2,1,1): rank in the pair
+  const int tile0 = TWO ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x;
   constexpr int C2 = 2 * C;
   constexpr int NCH = C2 / kChunk;          // conv1 chunks per tile
   constexpr int GS = C2 / 32;               // channels per GroupNorm-1 group
@@ -279,23 +341,29 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
   const Bars bar = make_bars(smem_base + S::bar_off);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  constexpr uint32_t kPair = TWO ? 2u : 1u;   // arrivals on the leader's gate barriers come from both CTAs of a pair
+  if (TWO) cluster_sync_all();                 // both CTAs are resident before TMEM is allocated for the pair
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_w1);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(bar.w_full + 8u * s, 1);
+      mbar_init(bar.w_full + 8u * s, kPair);
       mbar_init(bar.w_empty + 8u * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar.x_full + 8u * s, 8);    // producer warps
+      mbar_init(bar.x_full + 8u * s, 8 * kPair);    // producer warps
       mbar_init(bar.x_empty + 8u * s, 1);
       mbar_init(bar.d1_full + 8u * s, 1);
-      mbar_init(bar.d1_done + 8u * s, 8);   // statistics warps
+      mbar_init(bar.d1_done + 8u * s, 8 * kPair);   // statistics warps
     }
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(bar.tmem_slot, 512);
+  if (warp == kMmaWarp) {
+    if (TWO) tmem_alloc_2sm(bar.tmem_slot, 512);
+    else tmem_alloc(bar.tmem_slot, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (bar.tmem_slot - smem_base));
 
@@ -303,18 +371,20 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
     // ===================== TMA: weight stages, in the order the MMA warp consumes them =====================
     if (lane == 0) {
       uint32_t wc = 0;
-      for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x)
+      for (int base = tile0; base < A.total_tiles; base += gridDim.x)
         for (int j = 0; j < NCH; ++j)
-          for (int kc = 0; kc < C / kStageK; ++kc) load_weight_stage(bar, sW, &tmap_w1, kc * kStageK, j * kChunk, wc);
+          for (int kc = 0; kc < C / kStageK; ++kc)
+            load_weight_stage<TWO>(bar, sW, &tmap_w1, kc * kStageK, j * kChunk, 128 * 128, 64, rank, wc);
+      if (TWO) drain_ring<TWO>(bar, wc);
     }
   } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer =====================
-    {
+    // ===================== MMA issuer (pairs: the leader CTA issues for both) =====================
+    if (rank == 0) {
       uint32_t wc = 0, g = 0, it = 0;
       long long pr[4] = {0, 0, 0, 0};   // x_full, w_full, d1_done, total
       long long* P = A.prof ? pr : nullptr;
       const long long tstart = clock64();
-      for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
+      for (int base = tile0; base < A.total_tiles; base += gridDim.x, ++it) {
         const uint32_t xb = it & 1u;
         mbar_wait_timed(bar.x_full + 8u * xb, (it >> 1) & 1u, P);
         tc_fence_after();
@@ -322,10 +392,10 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
           const uint32_t b = g & 1u, u = g >> 1;
           mbar_wait_timed(bar.d1_done + 8u * b, (u & 1u) ^ 1u, P ? P + 2 : nullptr);   // statistics warps drained the chunk two back
           tc_fence_after();
-          issue_conv1<C>(bar, sX + xb * S::x_bytes, sW, tmem_base + b * (uint32_t)kChunk, wc, P ? P + 1 : nullptr);
-          commit_elect(bar.d1_full + 8u * b);
+          issue_conv1<C, TWO>(bar, sX + xb * S::x_bytes, sW, tmem_base + b * (uint32_t)kChunk, wc, P ? P + 1 : nullptr);
+          commit_elect<TWO>(bar.d1_full + 8u * b);
         }
-        commit_elect(bar.x_empty + 8u * xb);
+        commit_elect<TWO>(bar.x_empty + 8u * xb);
       }
       if (P && lane == 0) {
         pr[3] = clock64() - tstart;
@@ -338,9 +408,9 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
     const int chunk = lane & 15;       // 16-byte bf16 chunk = 8 pixels; 16 chunks = 128 pixels
     const int rsub = lane >> 4;        // row inside the pair this warp handles per round
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
+    for (int base = tile0; base < A.total_tiles; base += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
-      const TileInfo t = decode_tile(A, tile);
+      const TileInfo t = decode_tile(A, base + (int)rank);
       const FLevel& L = A.lv[t.level];
       const int px = t.px0 + chunk * 8;
       const float* src = L.in + (size_t)t.img * C * L.hw + px;
@@ -382,8 +452,9 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
       }
       fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async proxy
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar.x_full + 8u * buf);
+      if (lane == 0) arrive_gate<TWO>(bar.x_full + 8u * buf);
     }
+    if (TWO && warp == 0 && lane == 0) drain_x(bar, it);
   } else {
     // ===================== GroupNorm-1 statistics (warps 8-15; thread = pixel) =====================
     // warp = (lane quadrant q, column half hh): reads columns [64 hh, 64 hh + 64) of every chunk.  The per-pixel sums
@@ -391,8 +462,8 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
     const int q = warp & 3, hh = (warp - 8) >> 2;
     const int tid = threadIdx.x - 256;
     uint32_t it = 0, g = 0;
-    for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
-      const TileInfo t = decode_tile(A, tile);
+    for (int base = tile0; base < A.total_tiles; base += gridDim.x, ++it) {
+      const TileInfo t = decode_tile(A, base + (int)rank);
       const bool valid = (q * 32 + lane) < t.nvalid;
       const size_t plane = (size_t)t.level * A.B + t.img;
       float* sb = sBias + (it & 1u) * C2;
@@ -414,7 +485,7 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
           if (cb == 32) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar.d1_done + 8u * b);   // the chunk buffer may be overwritten
+            if (lane == 0) arrive_gate<TWO>(bar.d1_done + 8u * b);   // the chunk buffer may be overwritten
           }
           const float4* bp = reinterpret_cast<const float4*>(sb + j * kChunk + hh * 64 + cb);
 #pragma unroll
@@ -448,10 +519,12 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all();
+  else __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (TWO) tmem_dealloc_2sm(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -467,11 +540,15 @@ __device__ __forceinline__ float lrelu(float y, float slope) {
   return y > 0.f ? y : y * slope;
 }
 
-template <int C, bool FINAL, bool SLOPE01>
+template <int C, bool FINAL, bool SLOPE01, bool TWO>
 __global__ void __launch_bounds__(kThreadsB, 1)
 fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
                   const __grid_constant__ XMaps xmaps, const FArgs A) {
   using S = Smem<C>;
+  constexpr int kStages = Ring<TWO>::kStages;
+  constexpr int N2 = C < 128 ? C : 128;
+  const uint32_t rank = TWO ? (blockIdx.x & 1u) : 0u;
+  const int tile0 = TWO ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x;
   constexpr int C2 = 2 * C;
   constexpr int NCH = C2 / kChunk;
   constexpr int GS2 = C / 32;               // channels per GroupNorm-2 group
@@ -487,26 +564,32 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
   const Bars bar = make_bars(smem_base + S::bar_off);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  constexpr uint32_t kPair = TWO ? 2u : 1u;
+  if (TWO) cluster_sync_all();
   if (warp == kTmaW && lane == 0) {
     tma_prefetch_desc(&tmap_w1);
     tma_prefetch_desc(&tmap_w2);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(bar.w_full + 8u * s, 1);
+      mbar_init(bar.w_full + 8u * s, kPair);
       mbar_init(bar.w_empty + 8u * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar.x_full + 8u * s, 1);    // expect_tx arrival of the TMA warp
+      mbar_init(bar.x_full + 8u * s, kPair);        // (expect_tx) arrival of the TMA warp of each CTA
       mbar_init(bar.x_empty + 8u * s, 1);
       mbar_init(bar.d1_full + 8u * s, 1);
-      mbar_init(bar.d1_done + 8u * s, 8);   // chunk epilogue warps
+      mbar_init(bar.d1_done + 8u * s, 8 * kPair);   // chunk epilogue warps
     }
     mbar_init(bar.d2_full, 1);
-    mbar_init(bar.d2_empty, 8);             // output epilogue warps
+    mbar_init(bar.d2_empty, 8 * kPair);             // output epilogue warps
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(bar.tmem_slot, 512);
+  if (warp == kMmaWarp) {
+    if (TWO) tmem_alloc_2sm(bar.tmem_slot, 512);
+    else tmem_alloc(bar.tmem_slot, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (bar.tmem_slot - smem_base));
 
@@ -516,14 +599,17 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
     // ===================== TMA: weight stages in consumption order =====================
     if (lane == 0) {
       uint32_t wc = 0;
-      for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x) {
+      for (int base = tile0; base < A.total_tiles; base += gridDim.x) {
         auto w1 = [&](int j) {
-          for (int kc = 0; kc < C / kStageK; ++kc) load_weight_stage(bar, sW, &tmap_w1, kc * kStageK, j * kChunk, wc);
+          for (int kc = 0; kc < C / kStageK; ++kc)
+            load_weight_stage<TWO>(bar, sW, &tmap_w1, kc * kStageK, j * kChunk, 128 * 128, 64, rank, wc);
         };
+        // one CTA: the box is always 128 rows (rows past C read as zero); pairs: N2/2 rows per CTA
         auto w2 = [&](int j) {
           for (int h = 0; h < (C + 127) / 128; ++h)
             for (int kc2 = 0; kc2 < kChunk / kStageK; ++kc2)
-              load_weight_stage(bar, sW, &tmap_w2, j * kChunk + kc2 * kStageK, h * 128, wc);
+              load_weight_stage<TWO>(bar, sW, &tmap_w2, j * kChunk + kc2 * kStageK, h * 128, (TWO ? N2 : 128) * 128, N2 / 2,
+                                     rank, wc);
         };
         w1(0);
         if (NCH > 1) w1(1);
@@ -532,30 +618,40 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
           if (j + 2 < NCH) w1(j + 2);
         }
       }
+      if (TWO) drain_ring<TWO>(bar, wc);
     }
   } else if (warp == kTmaX) {
     // ===================== TMA: activation tiles (bf16 copy written by pass A) =====================
     if (lane == 0) {
       for (int l = 0; l < A.nl; ++l) tma_prefetch_desc(&xmaps.m[l]);
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
+      for (int base = tile0; base < A.total_tiles; base += gridDim.x, ++it) {
         const uint32_t buf = it & 1u;
-        const TileInfo t = decode_tile(A, tile);
+        const TileInfo t = decode_tile(A, base + (int)rank);
         mbar_wait_relaxed(bar.x_empty + 8u * buf, ((it >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(bar.x_full + 8u * buf, S::x_bytes);
         // two boxes of 64 pixels x C rows: exactly the two MN-major swizzle atoms of the A operand
-        tma_load_2d(sX + buf * S::x_bytes, &xmaps.m[t.level], t.px0, t.img * C, bar.x_full + 8u * buf);
-        tma_load_2d(sX + buf * S::x_bytes + S::x_bytes / 2, &xmaps.m[t.level], t.px0 + 64, t.img * C, bar.x_full + 8u * buf);
+        const uint32_t dst = sX + buf * S::x_bytes;
+        if (TWO) {
+          if (rank == 0) mbar_expect_tx(bar.x_full + 8u * buf, 2 * S::x_bytes);   // this CTA's tile and the peer's
+          else mbar_arrive_leader(bar.x_full + 8u * buf);
+          tma_load_2d_2sm(dst, &xmaps.m[t.level], t.px0, t.img * C, bar.x_full + 8u * buf);
+          tma_load_2d_2sm(dst + S::x_bytes / 2, &xmaps.m[t.level], t.px0 + 64, t.img * C, bar.x_full + 8u * buf);
+        } else {
+          mbar_expect_tx(bar.x_full + 8u * buf, S::x_bytes);
+          tma_load_2d(dst, &xmaps.m[t.level], t.px0, t.img * C, bar.x_full + 8u * buf);
+          tma_load_2d(dst + S::x_bytes / 2, &xmaps.m[t.level], t.px0 + 64, t.img * C, bar.x_full + 8u * buf);
+        }
       }
+      if (TWO) drain_x(bar, it);
     }
   } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer =====================
-    {
+    // ===================== MMA issuer (pairs: the leader CTA issues for both) =====================
+    if (rank == 0) {
       uint32_t wc = 0, g0 = 0, it = 0;
       long long pr[6] = {0, 0, 0, 0, 0, 0};   // x_full, w_full (conv1), d1_done, d2_empty, w_full (conv2), total
       long long* P = A.prof ? pr : nullptr;
       const long long tstart = clock64();
-      for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it, g0 += NCH) {
+      for (int base = tile0; base < A.total_tiles; base += gridDim.x, ++it, g0 += NCH) {
         const uint32_t xb = it & 1u;
         const uint32_t sXt = sX + xb * S::x_bytes;
         mbar_wait_timed(bar.x_full + 8u * xb, (it >> 1) & 1u, P);
@@ -565,9 +661,9 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
         // before issuing it, so no further wait is needed here.
         auto c1 = [&](int j) {
           const uint32_t b = (g0 + j) & 1u;
-          issue_conv1<C>(bar, sXt, sW, tmem_base + b * (uint32_t)kChunk, wc, P ? P + 1 : nullptr);
-          commit_elect(bar.d1_full + 8u * b);
-          if (j == NCH - 1) commit_elect(bar.x_empty + 8u * xb);   // the activation tile may be refilled
+          issue_conv1<C, TWO>(bar, sXt, sW, tmem_base + b * (uint32_t)kChunk, wc, P ? P + 1 : nullptr);
+          commit_elect<TWO>(bar.d1_full + 8u * b);
+          if (j == NCH - 1) commit_elect<TWO>(bar.x_empty + 8u * xb);   // the activation tile may be refilled
         };
         c1(0);
         if (NCH > 1) c1(1);
@@ -576,8 +672,8 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
           mbar_wait_timed(bar.d1_done + 8u * b, (g >> 1) & 1u, P ? P + 2 : nullptr);          // y1 chunk written to TMEM
           if (j == 0) mbar_wait_timed(bar.d2_empty, (it & 1u) ^ 1u, P ? P + 3 : nullptr);     // previous tile's output drained
           tc_fence_after();
-          issue_conv2<C>(bar, sW, tmem_base, b, j == 0, wc, P ? P + 4 : nullptr);
-          if (j == NCH - 1) commit_elect(bar.d2_full);
+          issue_conv2<C, TWO>(bar, sW, tmem_base, b, j == 0, wc, P ? P + 4 : nullptr);
+          if (j == NCH - 1) commit_elect<TWO>(bar.d2_full);
           if (j + 2 < NCH) c1(j + 2);
         }
       }
@@ -597,8 +693,8 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
     long long e1wait = 0;
     long long* PE = (A.prof && warp == 8) ? &e1wait : nullptr;
     const long long e1start = clock64();
-    for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
-      const TileInfo t = decode_tile(A, tile);
+    for (int base = tile0; base < A.total_tiles; base += gridDim.x, ++it) {
+      const TileInfo t = decode_tile(A, base + (int)rank);
       const size_t plane = (size_t)t.level * A.B + t.img;
       float2* sc = sCoef1 + (it & 1u) * C2;
       for (int c = tid; c < C2; c += 256) sc[c] = __ldg(A.coef1 + plane * C2 + c);
@@ -628,7 +724,7 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar.d1_done + 8u * b);
+        if (lane == 0) arrive_gate<TWO>(bar.d1_done + 8u * b);
       }
     }
     if (PE && lane == 0) {
@@ -645,8 +741,8 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
     long long e2wait = 0;
     long long* PE2 = (A.prof && warp == 0) ? &e2wait : nullptr;
     const long long e2start = clock64();
-    for (int tile = blockIdx.x; tile < A.total_tiles; tile += gridDim.x, ++it) {
-      const TileInfo t = decode_tile(A, tile);
+    for (int base = tile0; base < A.total_tiles; base += gridDim.x, ++it) {
+      const TileInfo t = decode_tile(A, base + (int)rank);
       const FLevel& L = A.lv[t.level];
       const int pl = q * 32 + lane;
       const bool valid = pl < t.nvalid;
@@ -673,7 +769,7 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
         if (cb == kColsPerWarp - 32) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar.d2_empty);   // D2 may be overwritten by the next tile's conv2
+          if (lane == 0) arrive_gate<TWO>(bar.d2_empty);   // D2 may be overwritten by the next tile's conv2
         }
         const float4* bp = reinterpret_cast<const float4*>(sB2 + c0);
 #pragma unroll
@@ -714,32 +810,55 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all();
+  else __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (TWO) tmem_dealloc_2sm(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int C>
+// launch with an optional cluster of 2 CTAs along x
+template <typename... KArgs, typename... Args>
+int launch_fused(void (*kernel)(KArgs...), int grid, int threads, size_t smem, bool pairs, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pairs ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OSD_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+  return OSD_OK;
+}
+
+template <int C, bool TWO>
 int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t stream) {
   using S = Smem<C>;
   static_assert(S::total <= 227 * 1024, "shared-memory plan exceeds 227 KB");
+  constexpr int N2 = C < 128 ? C : 128;
   const int C2 = 2 * C, B = d->batch, nl = d->num_levels;
   const size_t per = (size_t)nl * B;
   OSD_CUDA(cudaMemsetAsync(ws.stats1, 0, sizeof(double) * per * 64, stream));
   OSD_CUDA(cudaMemsetAsync(ws.stats2, 0, sizeof(double) * per * 64, stream));
   timeline_mark("fusion_begin", stream);
 
+  // weight boxes: one CTA per tile loads whole 128-row stages; a CTA of a pair loads its half of the rows
   CUtensorMap map1, map2;
   XMaps xm;
   memset(&xm, 0, sizeof(xm));
-  int rc = make_bf16_map(d->w1x_bf16, C2, C, C, kStageK, 128, &map1);
+  int rc = make_bf16_map(d->w1x_bf16, C2, C, C, kStageK, TWO ? 64 : 128, &map1);
   if (rc != OSD_OK) return rc;
-  rc = make_bf16_map(d->w2_bf16, C, C2, C2, kStageK, 128, &map2);
+  rc = make_bf16_map(d->w2_bf16, C, C2, C2, kStageK, TWO ? N2 / 2 : 128, &map2);
   if (rc != OSD_OK) return rc;
 
   FArgs A{};
@@ -769,7 +888,9 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
   }
   A.total_tiles = tiles;
   if (tiles <= 0) return OSD_OK;
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  // one CTA (or one CTA pair) per SM (pair of SMs), persistent over tiles (pairs of tiles)
+  int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  if (TWO) grid = 2 * std::min((tiles + 1) / 2, kNumSMs / 2);
   static const bool prof_on = [] { const char* e = getenv("OSD_FUSION_PROF"); return e && e[0] == '1'; }();
   static long long* prof_dev = nullptr;
   if (prof_on) {
@@ -778,16 +899,18 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
     A.prof = prof_dev;
   }
 
-  rc = ensure_dynamic_smem(reinterpret_cast<const void*>(fusion_stats1_kernel<C>), S::total);
+  auto kA = fusion_stats1_kernel<C, TWO>;
+  rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kA), S::total);
   if (rc != OSD_OK) return rc;
   const bool s01 = d->lrelu_slope >= 0.f && d->lrelu_slope <= 1.f;
-  auto kB = s01 ? fusion_b2b_kernel<C, false, true> : fusion_b2b_kernel<C, false, false>;
-  auto kBfinal = s01 ? fusion_b2b_kernel<C, true, true> : fusion_b2b_kernel<C, true, false>;
+  auto kB = s01 ? fusion_b2b_kernel<C, false, true, TWO> : fusion_b2b_kernel<C, false, false, TWO>;
+  auto kBfinal = s01 ? fusion_b2b_kernel<C, true, true, TWO> : fusion_b2b_kernel<C, true, false, TWO>;
   rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kB), S::total);
   if (rc != OSD_OK) return rc;
 
   // ---- pass A: GroupNorm-1 statistics (+ bf16 copy of the features)
-  fusion_stats1_kernel<C><<<grid, kThreadsA, S::total, stream>>>(map1, A);
+  rc = launch_fused(kA, grid, kThreadsA, S::total, TWO, stream, map1, A);
+  if (rc != OSD_OK) return rc;
   OSD_LAUNCH_CHECK("fusion_stats1_kernel");
   timeline_mark("fusion_stats1_kernel", stream);
   rc = fusion_launch_gn_coef(nl, B, C2, d->gn_eps, ws.stats1, d->gn1_w, d->gn1_b, ws.bias_eff, ws.coef1, hw, stream);
@@ -797,7 +920,8 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
   static const bool recompute = [] { const char* e = getenv("OSD_FUSION_RECOMPUTE"); return e && e[0] == '1'; }();
   A.store = recompute ? 0 : 1;
   A.final_xform = 0;
-  kB<<<grid, kThreadsB, S::total, stream>>>(map1, map2, xm, A);
+  rc = launch_fused(kB, grid, kThreadsB, S::total, TWO, stream, map1, map2, xm, A);
+  if (rc != OSD_OK) return rc;
   OSD_LAUNCH_CHECK("fusion_b2b_kernel");
   timeline_mark("fusion_b2b_kernel", stream);
   rc = fusion_launch_gn_coef(nl, B, C, d->gn_eps, ws.stats2, d->gn2_w, d->gn2_b, nullptr, ws.coef2, hw, stream);
@@ -810,7 +934,8 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
     A.stats2 = nullptr;
     rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kBfinal), S::total);
     if (rc != OSD_OK) return rc;
-    kBfinal<<<grid, kThreadsB, S::total, stream>>>(map1, map2, xm, A);
+    rc = launch_fused(kBfinal, grid, kThreadsB, S::total, TWO, stream, map1, map2, xm, A);
+    if (rc != OSD_OK) return rc;
     OSD_LAUNCH_CHECK("fusion_b2b_kernel");
     timeline_mark("fusion_b2b_kernel(final)", stream);
     return OSD_OK;
@@ -825,10 +950,13 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
     const char* names[14] = {"B.mma x_full", "B.mma w_full(c1)", "B.mma d1_done", "B.mma d2_empty", "B.mma w_full(c2)", "B.mma total",
                              "B.e1 wait", "B.e1 total", "B.e2 wait", "B.e2 total", "A.mma x_full", "A.mma w_full", "A.mma d1_done",
                              "A.mma total"};
+    const int step = TWO ? 2 : 1;   // pairs: only the leader CTAs issue MMAs
     for (int i = 0; i < 14; ++i) {
       double sum = 0, mx = 0;
-      for (int c = 0; c < grid; ++c) { sum += (double)host[c * 16 + i]; mx = std::max(mx, (double)host[c * 16 + i]); }
-      fprintf(stderr, "[fusion prof] %-18s mean %10.0f clk  max %10.0f clk\n", names[i], sum / grid, mx);
+      int n = 0;
+      const bool mma_row = i < 6 || i >= 10;
+      for (int c = 0; c < grid; c += (mma_row ? step : 1), ++n) { sum += (double)host[c * 16 + i]; mx = std::max(mx, (double)host[c * 16 + i]); }
+      fprintf(stderr, "[fusion prof] %-18s mean %10.0f clk  max %10.0f clk\n", names[i], sum / n, mx);
     }
   }
   return rc;
@@ -837,10 +965,12 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
 }  // namespace
 
 int fusion_full_forward(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t stream) {
+  // OSD_FUSION_2CTA=1: CTA pairs (tcgen05 cta_group::2, M = 256 across two SMs); default: one CTA per tile
+  static const bool pairs = [] { const char* e = getenv("OSD_FUSION_2CTA"); return e && e[0] == '1'; }();
   switch (d->channels) {
-    case 64: return run_full<64>(d, ws, stream);
-    case 128: return run_full<128>(d, ws, stream);
-    case 256: return run_full<256>(d, ws, stream);
+    case 64: return pairs ? run_full<64, true>(d, ws, stream) : run_full<64, false>(d, ws, stream);
+    case 128: return pairs ? run_full<128, true>(d, ws, stream) : run_full<128, false>(d, ws, stream);
+    case 256: return pairs ? run_full<256, true>(d, ws, stream) : run_full<256, false>(d, ws, stream);
   }
   set_error("osd_fusion: channels must be 64, 128 or 256 (got %d)", d->channels);
   return OSD_ERR_INVALID;
