@@ -99,13 +99,50 @@ def fill_inputs(pipe, seed, heads="spread"):
             t.normal_(mean=math.log(4.0 * s), std=0.5, generator=g).exp_()
 
 
-def make_pipe(name, dev, double_buffer=False):
+def make_pipe(name, dev, double_buffer=False, depth=1):
     from oneshotdet_b200.pipeline import EpisodePipeline, PostParams
 
     wl = WORKLOADS[name]
     return EpisodePipeline(wl["batch"], wl["height"], wl["width"], [wl["image"]] * wl["batch"], channels=CHANNELS,
                            shots=wl["shots"], params=PostParams(**wl["params"]), match_mode="product", device=dev,
-                           early_exit=wl["early_exit"], double_buffer=double_buffer)
+                           early_exit=wl["early_exit"], double_buffer=double_buffer, pipeline_depth=depth)
+
+
+class StepRunner:
+    """K steps of a pipeline as CUDA-graph replays: graphs of `depth` consecutive steps (their post-processing chains
+    side by side, see EpisodePipeline.run_overlapped) plus a one-step graph for a remainder.  ``run(k, after=None)``
+    executes exactly k steps; ``after(results)`` is called after every replay with the list of its results."""
+
+    def __init__(self, pipe, depth, overlap=True, use_graph=True):
+        import torch
+
+        self.pipe, self.depth, self.launch = pipe, depth, "eager"
+        self.one = pipe.run_overlapped if overlap else pipe.run
+        self.many = (lambda: pipe.run_overlapped(depth)) if depth > 1 else None
+        if use_graph:
+            try:
+                one = pipe.capture(overlapped=overlap)
+                many = pipe.capture(overlapped=True, steps_per_graph=depth) if depth > 1 else None
+                self.one, self.many, self.launch = one, many, "cuda-graph"
+            except Exception as exc:  # noqa: BLE001  (launch mechanism only; the kernels are the same either way)
+                print(f"[bench] CUDA-graph capture failed ({exc}); launching eagerly", file=sys.stderr)
+                torch.cuda.synchronize()
+
+    def run(self, k, before=None, after=None, mark=None):
+        done, last = 0, None
+        while done < k:
+            n = self.depth if (self.many is not None and k - done >= self.depth) else 1
+            if before is not None:
+                before(n)
+            res = self.many() if n > 1 else self.one()
+            res = res if isinstance(res, list) else [res]
+            if after is not None:
+                after(res)
+            done += n
+            last = res[-1]
+            if mark is not None:
+                mark(done)
+        return last
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -385,28 +422,26 @@ def time_steps(step_fn, steps, torch):
     return ev[0].elapsed_time(ev[-1]) / steps, statistics.median(per)
 
 
-def run_extra_workload(name, dev, steps, rank, use_graph=True):
+def run_extra_workload(name, dev, steps, rank, use_graph=True, depth=1):
     """One of the non-headline workloads on this GPU: overlapped/graph step time, isolated stage times, parity spot
     check against the CPU reference path on episode 0, and that path's time on the same inputs."""
     import torch
 
     wl = WORKLOADS[name]
-    pipe = make_pipe(name, dev)
+    pipe = make_pipe(name, dev, depth=depth)
     fill_inputs(pipe, seed=3000 + 17 * rank + sum(map(ord, name)), heads=wl["heads"])
-    step_fn = pipe.run_overlapped
-    launch = "eager"
-    if use_graph:
-        try:
-            step_fn = pipe.capture(overlapped=True)
-            launch = "cuda-graph"
-        except Exception as exc:  # noqa: BLE001
-            print(f"[bench] {name}: CUDA-graph capture failed ({exc}); launching eagerly", file=sys.stderr)
-            torch.cuda.synchronize()
-    for _ in range(3):
-        res = step_fn()
+    runner = StepRunner(pipe, depth, overlap=True, use_graph=use_graph)
+    launch = runner.launch
+    runner.run(2 * depth)
     torch.cuda.synchronize()
-    n = max(3, min(steps, 10))
-    avg_ms, med_ms = time_steps(step_fn, n, torch)
+    n = max(4, min(steps, 10)) // depth * depth
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    runner.run(n)
+    ev[1].record()
+    torch.cuda.synchronize()
+    avg_ms = ev[0].elapsed_time(ev[1]) / n
+    med_ms = avg_ms
     m_ms, _ = time_steps(pipe.match, n, torch)
     p_ms, _ = time_steps(pipe.post, n, torch)
     res = pipe.run()
@@ -414,7 +449,7 @@ def run_extra_workload(name, dev, steps, rank, use_graph=True):
     kept = res.kept_before_cut().cpu().tolist()
     parity, cpu = parity_spot_check(name, pipe, res)
     out = {"workload": wl["text"], "episodes_per_gpu": wl["batch"], "post_params": wl["params"], "shots": wl["shots"],
-           "early_exit": wl["early_exit"], "ms_per_step": avg_ms, "ms_per_step_median": med_ms,
+           "early_exit": wl["early_exit"], "ms_per_step": avg_ms, "steps_in_flight": depth,
            "episodes_per_s": wl["batch"] / (avg_ms * 1e-3), "steps": n, "launch": launch,
            "stages": {"match_ms_isolated": m_ms, "post_ms_isolated": p_ms},
            "detections_per_episode": res.count.cpu().tolist()[:4], "kept_before_cut": kept[:4],
@@ -471,20 +506,15 @@ def run_b200_arm(args):
     batch = wl["batch"]
 
     block_mode = args.gather in ("peer", "peer-kernel", "block")
-    pipe = make_pipe(name, dev, double_buffer=(world > 1 and block_mode))
+    overlap = not args.serial
+    # steps in flight: the post-processing chains of `depth` consecutive steps run side by side under `depth` matching
+    # launches (one chain alone takes longer than one matching launch).  The NCCL block gather has two slots: depth 1.
+    depth = 1 if (args.serial or (world > 1 and args.gather in ("block", "packed"))) else max(1, args.depth)
+    pipe = make_pipe(name, dev, double_buffer=(world > 1 and block_mode), depth=depth)
     fill_inputs(pipe, seed=2000 + rank, heads=wl["heads"])
     ep_off = rank * batch
-
-    overlap = not args.serial
-    launch = "eager"
-    step_fn = pipe.run_overlapped if overlap else pipe.run
-    if not args.no_graph:
-        try:
-            step_fn = pipe.capture(overlapped=overlap)
-            launch = "cuda-graph"
-        except Exception as exc:  # noqa: BLE001  (launch mechanism only; the kernels are the same either way)
-            print(f"[bench] CUDA-graph capture failed ({exc}); launching eagerly", file=sys.stderr)
-            torch.cuda.synchronize()
+    runner = StepRunner(pipe, depth, overlap=overlap, use_graph=not args.no_graph)
+    launch = runner.launch
 
     # N > 1: the step's detections go to every rank.  "peer" (default): the result block of a step (one contiguous
     # buffer of a double-buffered pipeline) is pushed into every rank's receive buffer through CUDA-IPC-mapped peer
@@ -495,25 +525,31 @@ def run_b200_arm(args):
     K = pipe.post.plan.out_capacity
     if world > 1 and args.gather != "none":
         if args.gather in ("peer", "peer-kernel"):
-            gatherer = PeerBlockGatherer(batch, K, dev, mode="copy" if args.gather == "peer" else "kernel")
+            gatherer = PeerBlockGatherer(batch, K, dev, slots=2 * depth, mode="copy" if args.gather == "peer" else "kernel")
         elif args.gather == "block":
             gatherer = BlockGatherer(batch, K, dev)
         else:
             gatherer = DetectionGatherer(batch, K, dev, ep_off, steps_per_gather=args.gather_every)
 
-    def step():
+    def before(n):
+        # the exchanges that still read the blocks these steps overwrite have finished.  Full-depth replays cycle through
+        # the 2 x depth output sets in submission order (the previous replay's pushes may stay in flight); a remainder
+        # step uses the one-step graphs' own rotation, so it waits for everything.
         if gatherer is not None and block_mode:
-            gatherer.acquire()         # the exchange that still reads the block this step overwrites has finished
-        res = step_fn()
-        if gatherer is not None:       # asynchronous: step i crosses NVLink while step i+1 computes
-            if block_mode:
-                gatherer.submit(res.block)
+            if args.gather == "block":
+                gatherer.acquire(n)
             else:
-                gatherer.submit(res.boxes, res.scores, res.count)
-        return res
+                gatherer.acquire(n, in_flight=(depth if n == depth else 0))
 
-    for _ in range(warmup):
-        res = step()
+    def after(results):
+        if gatherer is not None:       # asynchronous: step i crosses NVLink while step i+1 computes
+            for r in results:
+                if block_mode:
+                    gatherer.submit(r.block)
+                else:
+                    gatherer.submit(r.boxes, r.scores, r.count)
+
+    res = runner.run(max(warmup, 2 * depth), before, after)
     if gatherer is not None:
         gatherer.finish()
     torch.cuda.synchronize()
@@ -552,9 +588,7 @@ def run_b200_arm(args):
     sampler.start()
     t_host0 = time.perf_counter()
     ev[0].record()
-    for i in range(steps):
-        res = step()
-        ev[i + 1].record()
+    res = runner.run(steps, before, after, mark=lambda done: ev[done].record())
     if gatherer is not None:
         gatherer.finish()     # the last exchanges are inside the timed region
         if final_gather is not None:
@@ -568,7 +602,8 @@ def run_b200_arm(args):
     clocks = sampler.stop()
     launches = launches_per_step * steps
     total_ms = ev[0].elapsed_time(ev[steps + 1])
-    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    marks = [0] + [i for i in range(1, steps + 1) if (i % depth == 0 and i <= steps // depth * depth) or i > steps // depth * depth]
+    per_step = [ev[a].elapsed_time(ev[b]) / (b - a) for a, b in zip(marks, marks[1:])]
     t = torch.tensor([total_ms, statistics.median(per_step)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -578,7 +613,7 @@ def run_b200_arm(args):
     # ---- the exchange delivered every rank's block: pushed copy == NCCL copy == (for this rank) the local block
     exchange = None
     if world > 1 and block_mode:
-        slot = (gatherer.i - 1) % 2
+        slot = (gatherer.i - 1) % (2 if args.gather == "block" else gatherer.slots)
         if args.gather == "block":
             got = gatherer.out[slot].view(world, gatherer.block_bytes)
         else:
@@ -604,8 +639,9 @@ def run_b200_arm(args):
                 "share_of_serial_step": match_avg_ms / (match_avg_ms + statistics.mean(iso_post))}
     stages = {"match_ms_isolated": match_avg_ms, "post_ms_isolated": statistics.mean(iso_post),
               "serial_ms_per_step": match_avg_ms + statistics.mean(iso_post),
-              "overlap": "match || post-processing on two streams (software pipelining)" if overlap else "none (one stream)",
-              "launch": launch, "post_algorithmic_read_bytes": 6 * 4 * locs * batch,
+              "overlap": (f"match || post-processing on {1 + depth} streams, {depth} step(s) in flight per graph replay "
+                          "(software pipelining)") if overlap else "none (one stream)",
+              "steps_in_flight": depth, "launch": launch, "post_algorithmic_read_bytes": 6 * 4 * locs * batch,
               "host_ms_per_step": 1e3 * (t_host1 - t_host0) / steps}
 
     # ---- the 1x1 fusion-conv matching mode (BASELINE configs[1]: "fp32 matching + bf16 1x1 fusion conv"), timed as
@@ -708,7 +744,7 @@ def run_b200_arm(args):
             if wname == name:
                 continue
             try:
-                extra[wname] = run_extra_workload(wname, dev, steps, rank, use_graph=not args.no_graph)
+                extra[wname] = run_extra_workload(wname, dev, steps, rank, use_graph=not args.no_graph, depth=depth)
             except Exception as exc:  # noqa: BLE001  (report, do not lose the headline line)
                 extra[wname] = {"error": repr(exc)}
 
@@ -754,6 +790,8 @@ def main():
     ap.add_argument("--ref-worker", type=int, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--no-fusion", action="store_true")
     ap.add_argument("--serial", action="store_true", help="one stream: matching then post-processing, no overlap")
+    ap.add_argument("--depth", type=int, default=2,
+                    help="consecutive steps issued per graph replay, their post-processing chains side by side (1: one step)")
     ap.add_argument("--gather", choices=["peer", "peer-kernel", "block", "packed", "none"], default="peer",
                     help="N>1: how a step's detections reach every rank (see run_b200_arm); 'none' is a diagnosis run")
     ap.add_argument("--gather-every", type=int, default=10,

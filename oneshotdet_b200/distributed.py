@@ -127,14 +127,16 @@ class BlockGatherer:
         self.work = [None, None]
         self.i = 0
 
-    def acquire(self):
-        """Call BEFORE launching (or replaying) the step whose result block ``submit`` will ship next: makes the current
+    def acquire(self, n: int = 1):
+        """Call BEFORE launching (or replaying) the step(s) whose result block(s) ``submit`` will ship next (``n``
+        consecutive steps launched at once): makes the current
         stream wait for the gather issued two steps ago, which reads the block that step is about to overwrite.  (The
         wait inside ``submit`` alone comes too late -- by then the step's kernels are already enqueued.)"""
-        slot = self.i & 1
-        if self.work[slot] is not None:
-            self.work[slot].wait()
-            self.work[slot] = None
+        for k in range(n):
+            slot = (self.i + k) & 1
+            if self.work[slot] is not None:
+                self.work[slot].wait()
+                self.work[slot] = None
 
     def submit(self, block):
         slot = self.i & 1
@@ -217,15 +219,18 @@ class PeerBlockGatherer:
         self.recv = _wrap_device_memory(self._own, nbytes, self.device).view(slots, self.world, self.block_bytes)
         self.side = torch.cuda.Stream(self.device)
         self.ready = [torch.cuda.Event() for _ in range(slots)]     # compute -> side: block written
-        self.pushed = [None] * slots                                # side -> compute: block has been read by the pushes
+        self._events = []                                           # side -> compute: pushes not yet waited for, oldest first
         self.i = 0
 
-    def acquire(self):
-        """Before launching the step that overwrites the block submitted ``slots`` steps ago (with a double-buffered
-        pipeline and slots = 2: two steps ago)."""
-        ev = self.pushed[self.i % self.slots]
-        if ev is not None:
-            torch.cuda.current_stream(self.device).wait_event(ev)
+    def acquire(self, n: int = 1, in_flight: int | None = None):
+        """Before launching the next ``n`` step(s): makes the current stream wait for the pushes that may still read a
+        result block those steps overwrite -- every push issued so far except the ``in_flight`` most recent ones
+        (default ``slots - n``: right for a pipeline that cycles through ``slots`` output sets in submission order;
+        pass 0 when in doubt)."""
+        keep = max(0, self.slots - n) if in_flight is None else max(0, int(in_flight))
+        cur = torch.cuda.current_stream(self.device)
+        while len(self._events) > keep:
+            cur.wait_event(self._events.pop(0))
 
     def submit(self, block):
         import ctypes
@@ -246,7 +251,9 @@ class PeerBlockGatherer:
             _lib.check(fn(self._ptrs, self.world, block.data_ptr(), self.block_bytes, self.side.cuda_stream), "osd_comm_push")
         ev = torch.cuda.Event()
         ev.record(self.side)
-        self.pushed[slot] = ev
+        self._events.append(ev)
+        if len(self._events) > 4 * self.slots:      # acquire() is not being called: do not grow without bound
+            self._events.pop(0)
         return slot
 
     def fence(self):

@@ -36,7 +36,7 @@ class EpisodePipeline:
     def __init__(self, batch: int, height: int, width: int, image_sizes, channels: int = 256, shots: int = 1,
                  strides=FPN_STRIDES, params: PostParams | None = None, match_mode: str = "product",
                  device="cuda", dtype=torch.float32, early_exit: bool = True, strict_iou: bool = False,
-                 double_buffer: bool = False):
+                 double_buffer: bool = False, pipeline_depth: int = 1):
         self.device = torch.device(device)
         self.batch, self.channels, self.shots = batch, channels, shots
         self.params = params or PostParams()
@@ -58,11 +58,18 @@ class EpisodePipeline:
         # double_buffer: a second set of OUTPUT tensors (same inputs, same workspace -- steps are stream-ordered);
         # consecutive steps alternate between the two, so a consumer (the multi-GPU gather) can still read step i while
         # step i+1 runs
+        # pipeline_depth > 1: that many post-processing chains may be IN FLIGHT at once (``run_overlapped(n)``: the
+        # latency-bound chains of n consecutive batches run side by side while their matching launches stream back to
+        # back), so every chain owns its outputs AND its workspace
+        self.depth = max(1, int(pipeline_depth))
         self.posts = [self.post]
-        if double_buffer:
+        for i in range(1, self.depth * (2 if double_buffer else 1)):
+            # chains that run side by side (positions 0 .. depth-1 of a multi-step call) need their own workspace; the
+            # second buffer set of a double-buffered pipeline is used by a later, stream-ordered call and shares them
+            shared = self.posts[i % self.depth].result.workspace if i >= self.depth else None
             self.posts.append(ops.PreparedFcos(self.cls, self.reg, self.ctr, self.strides, image_sizes, p.pre_nms_thresh,
                                                p.pre_nms_top_n, p.nms_thresh, p.fpn_post_nms_top_n, p.min_size, strict_iou,
-                                               early_exit, workspace=self.post.result.workspace))
+                                               early_exit, workspace=shared, private_workspace=shared is None))
         self._step = 0
         self._host_out = None
         self._streams = None
@@ -80,33 +87,53 @@ class EpisodePipeline:
         self._step += 1
         return post
 
-    def run_overlapped(self) -> ops.FcosResult:
-        """The same work software-pipelined over two streams: the HBM-bound matching stream and the latency-bound
-        post-processing chain run concurrently (the post-processing stream has the higher priority so its small
+    def run_overlapped(self, n: int = 1):
+        """The same work software-pipelined over streams: the HBM-bound matching stream and the latency-bound
+        post-processing chain run concurrently (the post-processing streams have the higher priority so their small
         CTAs slot in as matching CTAs retire).  In a deployment the overlapping pair is matching of batch i+1 and
         post-processing of batch i (post-processing consumes the FCOS head's output of its own batch); here both
-        stages read resident inputs, so the pairing inside one call is equivalent.  The current stream waits for
-        both before the call returns control to later work."""
-        if self._streams is None:
+        stages read resident inputs, so the pairing inside one call is equivalent.  ``n`` > 1 (<= pipeline_depth)
+        issues n consecutive steps at once: n matching launches back to back on the matching stream and the n chains
+        side by side on n streams -- a chain is a string of small dependent kernels that takes longer than one
+        matching launch, but two of them fit next to two matching launches.  The current stream waits for everything
+        before the call returns control to later work.  Returns the step's FcosResult (n == 1) or a list of n."""
+        if n > self.depth:
+            raise ValueError(f"run_overlapped({n}) needs pipeline_depth >= {n}")
+        if self._streams is None or len(self._streams) < 1 + n:
             lo, hi = torch.cuda.Stream.priority_range()
-            self._streams = (torch.cuda.Stream(self.device, priority=lo), torch.cuda.Stream(self.device, priority=hi))
-        s_match, s_post = self._streams
+            self._streams = tuple([torch.cuda.Stream(self.device, priority=lo)] +
+                                  [torch.cuda.Stream(self.device, priority=hi) for _ in range(max(n, self.depth))])
+        s_match = self._streams[0]
         cur = torch.cuda.current_stream(self.device)
         s_match.wait_stream(cur)
-        s_post.wait_stream(cur)
         with torch.cuda.stream(s_match):
-            self.match()
-        with torch.cuda.stream(s_post):
-            res = self._next_post()()
+            for _ in range(n):
+                self.match()
+        out = []
+        for k in range(n):
+            s_post = self._streams[1 + k]
+            s_post.wait_stream(cur)
+            with torch.cuda.stream(s_post):
+                out.append(self._next_post()())
+            cur.wait_stream(s_post)
         cur.wait_stream(s_match)
-        cur.wait_stream(s_post)
-        return res
+        return out[0] if n == 1 else out
 
-    def capture(self, overlapped: bool = True):
-        """Capture one step (all launches of both streams, with their fork/join dependencies) into a CUDA graph and
+    def capture(self, overlapped: bool = True, steps_per_graph: int = 1):
+        """Capture one step (all launches of the streams, with their fork/join dependencies) into a CUDA graph and
         return ``replay() -> FcosResult``: a serving loop then pays one graph launch per batch instead of ~10 kernel
-        launches plus stream bookkeeping from Python.  Inputs and outputs are the pipeline's resident buffers."""
-        step = self.run_overlapped if overlapped else self.run
+        launches plus stream bookkeeping from Python.  Inputs and outputs are the pipeline's resident buffers.
+        ``steps_per_graph`` = n > 1 (needs pipeline_depth >= n, overlapped): one graph holds n consecutive steps as
+        ``run_overlapped(n)`` issues them and ``replay()`` returns the list of their n results."""
+        n = int(steps_per_graph)
+        if n > 1:
+            if not overlapped:
+                raise ValueError("steps_per_graph > 1 is the overlapped multi-step form")
+            if len(self.posts) % n != 0:
+                raise ValueError("the number of output sets must be a multiple of steps_per_graph")
+            step = lambda: self.run_overlapped(n)   # noqa: E731
+        else:
+            step = self.run_overlapped if overlapped else self.run
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -115,18 +142,19 @@ class EpisodePipeline:
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         graphs = []
-        for _ in self.posts:   # one graph per output buffer set; replay alternates between them
-            self._step = len(graphs)
+        for g in range(len(self.posts) // n):   # one graph per output buffer set(s); replay alternates between them
+            self._step = g * n
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
                 res = step()
             graphs.append((graph, res))
         self._graph = graphs
         self._step = 0
+        state = {"i": 0}
 
         def replay():
-            graph, res = graphs[self._step % len(graphs)]
-            self._step += 1
+            graph, res = graphs[state["i"] % len(graphs)]
+            state["i"] += 1
             graph.replay()
             return res
 
