@@ -402,10 +402,36 @@ def parity_spot_check(name, pipe, res, with_cpu_time=True):
     if same_n and n > 0:
         out["boxes_equal"] = bool(np.array_equal(gb, rb))
         out["max_score_rel_err"] = float(np.max(np.abs(gs - rs) / np.maximum(np.abs(rs), 1e-30)))
+        if not out["boxes_equal"]:
+            # say what differs: rows, whether the two results hold the same boxes in another order, and the score gap
+            # between the rows that trade places (a swap of two candidates whose scores differ by less than the stated
+            # score tolerance is the sigmoid's rounding, not a different selection)
+            rows = np.nonzero(np.any(gb != rb, axis=1))[0]
+            order = lambda a: a[np.lexsort(a.T[::-1])]  # noqa: E731
+            out["rows_differ"] = int(rows.size)
+            out["first_rows_differ"] = rows[:8].tolist()
+            out["same_boxes_other_order"] = bool(np.array_equal(order(gb), order(rb)))
+            r0 = int(rows[0])
+            out["first_diff"] = {"row": r0, "gpu_box": gb[r0].tolist(), "cpu_box": rb[r0].tolist(),
+                                 "gpu_score": float(gs[r0]), "cpu_score": float(rs[r0]),
+                                 "cpu_score_next": float(rs[min(r0 + 1, n - 1)])}
+            # Exactly tied scores: the reference's order among them is whatever ATen's topk(sorted=False)
+            # (fcos/inference.py:96-98) handed to its stable sorts -- unspecified; ours is "lower location first".  Rows that
+            # differ only by a permutation inside a run of bit-identical CPU scores are the same result.
+            runs_ok = True
+            for r in rows.tolist():
+                a = r
+                while a > 0 and rs[a - 1] == rs[r]:
+                    a -= 1
+                b = r
+                while b + 1 < n and rs[b + 1] == rs[r]:
+                    b += 1
+                runs_ok = runs_ok and b > a and np.array_equal(order(gb[a:b + 1]), order(rb[a:b + 1]))
+            out["differ_only_inside_exact_score_ties"] = bool(runs_ok and out["same_boxes_other_order"])
     mref = ref.orc.match_product(ref.feats, ref.supp, 1)
     out["matching_equal"] = bool(all(torch.equal(o[0:1].cpu(), m) for o, m in zip(pipe.combined, mref)))
-    out["ok"] = bool(same_n and out.get("boxes_equal", n == 0) and out.get("max_score_rel_err", 0.0) <= 2e-6 and
-                     out["matching_equal"])
+    boxes_ok = out.get("boxes_equal", n == 0) or out.get("differ_only_inside_exact_score_ties", False)
+    out["ok"] = bool(same_n and boxes_ok and out.get("max_score_rel_err", 0.0) <= 2e-6 and out["matching_equal"])
     cpu = {"matching_s": tm, "post_s": tp, "episodes_per_s": 1.0 / (tm + tp), "kind": ref.kind, "cores": ref.cores} \
         if with_cpu_time else None
     return out, cpu
