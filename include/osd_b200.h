@@ -344,6 +344,49 @@ int osd_roi_pool_workspace_bytes(const osd_roi_pool_desc* desc, size_t* bytes);
 int osd_roi_pool(const osd_roi_pool_desc* desc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Second-stage dense head -- SURVEY section 8(f) row 2, the part between the pooler and the post-processor.
+ *
+ * Replaces  ROIBoxHead.forward for comparison_method 'concat', one support, no negative support, LINEAR_FUSION off
+ *           (maskrcnn_benchmark/modeling/roi_heads/box_head/box_head.py:118-157): cat((x, support.expand_as(x)), 1)
+ *           -> compress_dim_conv (:43-54) -> feature_aggreg (:62-67) -> relu(fc6) -> relu(fc7) (:75-76, :152-154) and
+ *           FPNPredictor.forward (modeling/roi_heads/box_head/roi_box_predictors.py:80-84).
+ * pooled [B*R, C, 7, 7] fp32 is the Pooler's output (osd_roi_pool), supp [B, C, 7, 7] the ROI-pooled support of each
+ * episode.  Six GEMM launches per chunk of ROIs on tcgen05 (bf16 operands, fp32 accumulation in tensor memory), each
+ * with its bias / per-ROI GroupNorm / LeakyReLU / ReLU in the epilogue; activations between layers are bf16.
+ * Weights are prepared by the host once (bf16, K-major; see oneshotdet_b200/box_head.py for the permutations):
+ *   w1 [2C, 2C]  compress_dim_conv.0.weight            w2 [C, 2C]  compress_dim_conv.3.weight
+ *   w3 [C/2, 9C] feature_aggreg.0.weight as (out, ky, kx, in)
+ *   w6 [mlp, 49*C/2] fc6.weight as (out, pixel, channel)  w7 [mlp, mlp]  fc7.weight
+ *   wp [num_classes + num_box_out, mlp]  cls_score.weight rows, then bbox_pred.weight rows; bp likewise
+ * Outputs fp32: class_logits [B*R, num_classes], box_regression [B*R, num_box_out].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch;            /* B episodes */
+  int32_t rois_per_image;   /* R */
+  int32_t channels;         /* C: 64, 128 or 256 */
+  int32_t pooled_size;      /* 7 (MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION) */
+  int32_t mlp_dim;          /* MODEL.ROI_BOX_HEAD.MLP_HEAD_DIM, a multiple of 8 */
+  int32_t num_classes;      /* rows of cls_score (2) */
+  int32_t num_box_out;      /* rows of bbox_pred (8) */
+  int32_t roi_chunk;        /* ROIs per pass over the six layers; <= 0: sized so a chunk's activations stay in L2 */
+  float gn_eps;             /* 1e-5 */
+  float lrelu_slope;        /* 0.2 */
+  const float* pooled;      /* device [B*R, C, 7, 7] */
+  const float* supp;        /* device [B, C, 7, 7] */
+  const void* w1; const float* b1; const float* gn1_w; const float* gn1_b;
+  const void* w2; const float* b2; const float* gn2_w; const float* gn2_b;
+  const void* w3; const float* b3; const float* gn3_w; const float* gn3_b;
+  const void* w6; const float* b6;
+  const void* w7; const float* b7;
+  const void* wp; const float* bp;
+  float* class_logits;      /* device [B*R, num_classes] */
+  float* box_regression;    /* device [B*R, num_box_out] */
+} osd_box_head_desc;
+
+int osd_box_head_workspace_bytes(const osd_box_head_desc* desc, size_t* bytes);
+int osd_box_head_forward(const osd_box_head_desc* desc, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Result hand-off: detections -> COCO detection records -> the reference's JSON file.  SURVEY section 8(f) row 4.
  *
  * Replaces  the per-image body of prepare_for_coco_detection

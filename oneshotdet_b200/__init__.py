@@ -9,6 +9,7 @@ from .layers import nms  # noqa: F401
 from .modeling.matching import MatchingModule  # noqa: F401
 from .modeling.rpn.fcos.inference import FCOSPostProcessor, make_fcos_postprocessor  # noqa: F401
 from .modeling.poolers import LevelMapper, Pooler, make_pooler, roi_pool  # noqa: F401
+from .modeling.roi_heads.box_head.box_head import BoxHeadDense  # noqa: F401
 from .modeling.roi_heads.box_head.inference import BoxCoder, PostProcessor, make_roi_box_post_processor  # noqa: F401
 from .modeling.support_pooling import SuppAlignLayer, SuppAvgPool, support_pool  # noqa: F401
 from .ops import batched_nms, box_postprocess, fcos_postprocess, match_forward  # noqa: F401

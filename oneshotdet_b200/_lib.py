@@ -91,6 +91,19 @@ class RoiPoolDesc(ctypes.Structure):
                 ("workspace_bytes", ctypes.c_size_t)]
 
 
+class BoxHeadDesc(ctypes.Structure):
+    _fields_ = [("batch", ctypes.c_int32), ("rois_per_image", ctypes.c_int32), ("channels", ctypes.c_int32),
+                ("pooled_size", ctypes.c_int32), ("mlp_dim", ctypes.c_int32), ("num_classes", ctypes.c_int32),
+                ("num_box_out", ctypes.c_int32), ("roi_chunk", ctypes.c_int32), ("gn_eps", ctypes.c_float),
+                ("lrelu_slope", ctypes.c_float), ("pooled", ctypes.c_void_p), ("supp", ctypes.c_void_p),
+                ("w1", ctypes.c_void_p), ("b1", ctypes.c_void_p), ("gn1_w", ctypes.c_void_p), ("gn1_b", ctypes.c_void_p),
+                ("w2", ctypes.c_void_p), ("b2", ctypes.c_void_p), ("gn2_w", ctypes.c_void_p), ("gn2_b", ctypes.c_void_p),
+                ("w3", ctypes.c_void_p), ("b3", ctypes.c_void_p), ("gn3_w", ctypes.c_void_p), ("gn3_b", ctypes.c_void_p),
+                ("w6", ctypes.c_void_p), ("b6", ctypes.c_void_p), ("w7", ctypes.c_void_p), ("b7", ctypes.c_void_p),
+                ("wp", ctypes.c_void_p), ("bp", ctypes.c_void_p),
+                ("class_logits", ctypes.c_void_p), ("box_regression", ctypes.c_void_p)]
+
+
 # every symbol include/osd_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "osd_version": (ctypes.c_int, []),
@@ -113,6 +126,8 @@ SYMBOLS = {
     "osd_support_pool": (ctypes.c_int, [ctypes.POINTER(SupportPoolDesc), c_void_p]),
     "osd_roi_pool": (ctypes.c_int, [ctypes.POINTER(RoiPoolDesc), c_void_p]),
     "osd_roi_pool_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(RoiPoolDesc), ctypes.POINTER(ctypes.c_size_t)]),
+    "osd_box_head_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(BoxHeadDesc), ctypes.POINTER(ctypes.c_size_t)]),
+    "osd_box_head_forward": (ctypes.c_int, [ctypes.POINTER(BoxHeadDesc), c_void_p, ctypes.c_size_t, c_void_p]),
     "osd_coco_records": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int32, ctypes.c_int32,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "osd_coco_write_json": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, ctypes.c_int32,

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "lib", "obj")
 LIB = os.path.join(PKG, "lib", "libosd_b200.so")
-SOURCES = ["common.cu", "nms.cu", "fcos_post.cu", "match.cu", "fusion_conv.cu", "fusion_fused.cu", "support_pool.cu", "box_post.cu", "roi_pool.cu", "coco_writer.cu", "peer_comm.cu"]
+SOURCES = ["common.cu", "nms.cu", "fcos_post.cu", "match.cu", "fusion_conv.cu", "fusion_fused.cu", "support_pool.cu", "box_post.cu", "roi_pool.cu", "coco_writer.cu", "peer_comm.cu", "box_head.cu"]
 HEADERS = ["osd_common.cuh", "osd_device_utils.cuh", os.path.join(ROOT, "include", "osd_b200.h")]
 
 NVCC_FLAGS = [

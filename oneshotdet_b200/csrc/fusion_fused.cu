@@ -59,6 +59,7 @@ constexpr int kRingBytes = 5 * 128 * 128;
 constexpr int kUmmaK = 16;
 constexpr uint32_t kD2Col = 256;        // TMEM columns: D1/y1 chunk buffers at 0 and 128, D2 at 256..511
 
+constexpr int kDefaultFusionMode = 0;    // see fusion_full_forward
 constexpr int kThreadsA = 32 * 18;
 constexpr int kThreadsB = 32 * 19;
 
@@ -172,8 +173,18 @@ __device__ __forceinline__ bool elect_one() {
 // A single-lane loop (if (lane == 0) {...}) spent ~130 clk per MMA on address arithmetic and register moves -- more
 // than the 64 clk the tensor core needs for it.
 
+// a weight stage has been consumed by every MMA issued so far.  Pairs: one multicast commit of the leader reaches both
+// CTAs' barriers.  Multicast weights (MC): each CTA's own MMAs read its copy of the stage, and the stage is refilled in
+// BOTH CTAs by both TMA threads -- so each commit arrives on the "empty" barrier of both CTAs (count 2).
+template <bool TWO, bool MC>
+__device__ __forceinline__ void release_stage(uint32_t bar) {
+  if (TWO) umma_commit_2sm(bar);
+  else if (MC) umma_commit_mc(bar, (uint16_t)3);
+  else umma_commit(bar);
+}
+
 // conv1 block for one chunk: D1[buf] = x_tile . W1x[chunk rows]^T, K = C in stages of 64
-template <int C, bool TWO>
+template <int C, bool TWO, bool MC>
 __device__ __forceinline__ void issue_conv1(const Bars& bar, uint32_t sX, uint32_t sW, uint32_t tmem_d, uint32_t& wc,
                                             long long* tw = nullptr) {
   constexpr int kStages = Ring<TWO>::kStages, kStageBytes = Ring<TWO>::kStageBytes;
@@ -195,15 +206,14 @@ __device__ __forceinline__ void issue_conv1(const Bars& bar, uint32_t sX, uint32
         if (TWO) umma_bf16_2sm(tmem_d, adesc0 + (uint64_t)(kgrp * 64u), bs + (uint64_t)(k16 * 2), idesc, (kc | k16) != 0 ? 1u : 0u);
         else umma_bf16(tmem_d, adesc0 + (uint64_t)(kgrp * 64u), bs + (uint64_t)(k16 * 2), idesc, (kc | k16) != 0 ? 1u : 0u);
       }
-      if (TWO) umma_commit_2sm(bar.w_empty + 8u * s);
-      else umma_commit(bar.w_empty + 8u * s);
+      release_stage<TWO, MC>(bar.w_empty + 8u * s);
     }
     __syncwarp();
   }
 }
 
 // conv2 block for one chunk: D2 (+)= y1[buf] (TMEM, 128 px x 128 ch bf16) . W2[:, chunk]^T
-template <int C, bool TWO>
+template <int C, bool TWO, bool MC>
 __device__ __forceinline__ void issue_conv2(const Bars& bar, uint32_t sW, uint32_t tmem_base, uint32_t buf, bool first_chunk,
                                             uint32_t& wc, long long* tw = nullptr) {
   constexpr int kStages = Ring<TWO>::kStages, kStageBytes = Ring<TWO>::kStageBytes;
@@ -230,8 +240,7 @@ __device__ __forceinline__ void issue_conv2(const Bars& bar, uint32_t sW, uint32
           if (TWO) umma_bf16_ts_2sm(d_taddr, a_taddr, bs + (uint64_t)(k16 * 2), idesc, acc);
           else umma_bf16_ts(d_taddr, a_taddr, bs + (uint64_t)(k16 * 2), idesc, acc);
         }
-        if (TWO) umma_commit_2sm(bar.w_empty + 8u * s);
-        else umma_commit(bar.w_empty + 8u * s);
+        release_stage<TWO, MC>(bar.w_empty + 8u * s);
       }
       __syncwarp();
     }
@@ -266,13 +275,19 @@ __device__ __forceinline__ void arrive_gate(uint32_t bar) {
 
 // One weight stage.  Pairs: this CTA loads ITS half of the rows (rows_half each) into its own ring; the bytes of both
 // halves are counted on the leader's full barrier (leader: arrive + expect_tx of both halves, follower: plain arrive).
-template <bool TWO>
+template <bool TWO, bool MC>
 __device__ __forceinline__ void load_weight_stage(const Bars& bar, uint32_t sW, const CUtensorMap* map, int col, int row,
                                                   uint32_t stage_tx_bytes, int rows_half, uint32_t rank, uint32_t& wc) {
   constexpr int kStages = Ring<TWO>::kStages, kStageBytes = Ring<TWO>::kStageBytes;
   const uint32_t s = wc % kStages, ph = (wc / kStages) & 1u;
   mbar_wait(bar.w_empty + 8u * s, ph ^ 1u);
-  if (TWO) {
+  if (MC) {
+    // both CTAs of the cluster hold the WHOLE stage; this CTA fetches its half of the rows once from L2 and the TMA unit
+    // writes it into both CTAs' rings (same offset), signalling each CTA's own "full" barrier: half the L2 -> SM bytes
+    mbar_expect_tx(bar.w_full + 8u * s, stage_tx_bytes);
+    tma_load_2d_mc(sW + s * kStageBytes + rank * (uint32_t)(rows_half * 128), map, col, row + (int)rank * rows_half,
+                   bar.w_full + 8u * s, (uint16_t)3);
+  } else if (TWO) {
     if (rank == 0) mbar_expect_tx(bar.w_full + 8u * s, stage_tx_bytes);
     else mbar_arrive_leader(bar.w_full + 8u * s);
     tma_load_2d_2sm(sW + s * kStageBytes, map, col, row + (int)rank * rows_half, bar.w_full + 8u * s);
@@ -320,13 +335,15 @@ __device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane
 // ------------------------------------------------------------------------------------------------
 // pass A: conv1 statistics (+ bf16 copy of x)
 // ------------------------------------------------------------------------------------------------
-template <int C, bool TWO>
+template <int C, bool TWO, bool MC>
 __global__ void __launch_bounds__(kThreadsA, 1)
 fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A) {
   using S = Smem<C>;
+  static_assert(!(TWO && MC), "pairs (cta_group::2) and multicast weights are alternatives");
+  constexpr bool CL = TWO || MC;                               // launched as clusters of 2 CTAs
   constexpr int kStages = Ring<TWO>::kStages;
-  const uint32_t rank = TWO ? (blockIdx.x & 1u) : 0u;          // cluster dims (2,1,1): rank in the pair
-  const int tile0 = TWO ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x;
+  const uint32_t rank = CL ? (blockIdx.x & 1u) : 0u;           // cluster dims (2,1,1): rank in the pair
+  const int tile0 = CL ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x;
   constexpr int C2 = 2 * C;
   constexpr int NCH = C2 / kChunk;          // conv1 chunks per tile
   constexpr int GS = C2 / 32;               // channels per GroupNorm-1 group
@@ -342,12 +359,12 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   constexpr uint32_t kPair = TWO ? 2u : 1u;   // arrivals on the leader's gate barriers come from both CTAs of a pair
-  if (TWO) cluster_sync_all();                 // both CTAs are resident before TMEM is allocated for the pair
+  if (CL) cluster_sync_all();                  // both CTAs are resident before TMEM is allocated for the pair
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_w1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar.w_full + 8u * s, kPair);
-      mbar_init(bar.w_empty + 8u * s, 1);
+      mbar_init(bar.w_empty + 8u * s, MC ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar.x_full + 8u * s, 8 * kPair);    // producer warps
@@ -362,7 +379,7 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
     else tmem_alloc(bar.tmem_slot, 512);
   }
   tc_fence_before();
-  if (TWO) cluster_sync_all();
+  if (CL) cluster_sync_all();
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (bar.tmem_slot - smem_base));
@@ -374,12 +391,12 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
       for (int base = tile0; base < A.total_tiles; base += gridDim.x)
         for (int j = 0; j < NCH; ++j)
           for (int kc = 0; kc < C / kStageK; ++kc)
-            load_weight_stage<TWO>(bar, sW, &tmap_w1, kc * kStageK, j * kChunk, 128 * 128, 64, rank, wc);
-      if (TWO) drain_ring<TWO>(bar, wc);
+            load_weight_stage<TWO, MC>(bar, sW, &tmap_w1, kc * kStageK, j * kChunk, 128 * 128, 64, rank, wc);
+      if (CL) drain_ring<TWO>(bar, wc);
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (pairs: the leader CTA issues for both) =====================
-    if (rank == 0) {
+    if (!TWO || rank == 0) {
       uint32_t wc = 0, g = 0, it = 0;
       long long pr[4] = {0, 0, 0, 0};   // x_full, w_full, d1_done, total
       long long* P = A.prof ? pr : nullptr;
@@ -392,7 +409,7 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
           const uint32_t b = g & 1u, u = g >> 1;
           mbar_wait_timed(bar.d1_done + 8u * b, (u & 1u) ^ 1u, P ? P + 2 : nullptr);   // statistics warps drained the chunk two back
           tc_fence_after();
-          issue_conv1<C, TWO>(bar, sX + xb * S::x_bytes, sW, tmem_base + b * (uint32_t)kChunk, wc, P ? P + 1 : nullptr);
+          issue_conv1<C, TWO, MC>(bar, sX + xb * S::x_bytes, sW, tmem_base + b * (uint32_t)kChunk, wc, P ? P + 1 : nullptr);
           commit_elect<TWO>(bar.d1_full + 8u * b);
         }
         commit_elect<TWO>(bar.x_empty + 8u * xb);
@@ -519,7 +536,7 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
   }
 
   tc_fence_before();
-  if (TWO) cluster_sync_all();
+  if (CL) cluster_sync_all();
   else __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
@@ -540,15 +557,17 @@ __device__ __forceinline__ float lrelu(float y, float slope) {
   return y > 0.f ? y : y * slope;
 }
 
-template <int C, bool FINAL, bool SLOPE01, bool TWO>
+template <int C, bool FINAL, bool SLOPE01, bool TWO, bool MC>
 __global__ void __launch_bounds__(kThreadsB, 1)
 fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
                   const __grid_constant__ XMaps xmaps, const FArgs A) {
   using S = Smem<C>;
+  static_assert(!(TWO && MC), "pairs (cta_group::2) and multicast weights are alternatives");
+  constexpr bool CL = TWO || MC;
   constexpr int kStages = Ring<TWO>::kStages;
   constexpr int N2 = C < 128 ? C : 128;
-  const uint32_t rank = TWO ? (blockIdx.x & 1u) : 0u;
-  const int tile0 = TWO ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x;
+  const uint32_t rank = CL ? (blockIdx.x & 1u) : 0u;
+  const int tile0 = CL ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x;
   constexpr int C2 = 2 * C;
   constexpr int NCH = C2 / kChunk;
   constexpr int GS2 = C / 32;               // channels per GroupNorm-2 group
@@ -565,13 +584,13 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   constexpr uint32_t kPair = TWO ? 2u : 1u;
-  if (TWO) cluster_sync_all();
+  if (CL) cluster_sync_all();
   if (warp == kTmaW && lane == 0) {
     tma_prefetch_desc(&tmap_w1);
     tma_prefetch_desc(&tmap_w2);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar.w_full + 8u * s, kPair);
-      mbar_init(bar.w_empty + 8u * s, 1);
+      mbar_init(bar.w_empty + 8u * s, MC ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar.x_full + 8u * s, kPair);        // (expect_tx) arrival of the TMA warp of each CTA
@@ -588,7 +607,7 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
     else tmem_alloc(bar.tmem_slot, 512);
   }
   tc_fence_before();
-  if (TWO) cluster_sync_all();
+  if (CL) cluster_sync_all();
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (bar.tmem_slot - smem_base));
@@ -602,14 +621,14 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
       for (int base = tile0; base < A.total_tiles; base += gridDim.x) {
         auto w1 = [&](int j) {
           for (int kc = 0; kc < C / kStageK; ++kc)
-            load_weight_stage<TWO>(bar, sW, &tmap_w1, kc * kStageK, j * kChunk, 128 * 128, 64, rank, wc);
+            load_weight_stage<TWO, MC>(bar, sW, &tmap_w1, kc * kStageK, j * kChunk, 128 * 128, 64, rank, wc);
         };
         // one CTA: the box is always 128 rows (rows past C read as zero); pairs: N2/2 rows per CTA
         auto w2 = [&](int j) {
           for (int h = 0; h < (C + 127) / 128; ++h)
             for (int kc2 = 0; kc2 < kChunk / kStageK; ++kc2)
-              load_weight_stage<TWO>(bar, sW, &tmap_w2, j * kChunk + kc2 * kStageK, h * 128, (TWO ? N2 : 128) * 128, N2 / 2,
-                                     rank, wc);
+              load_weight_stage<TWO, MC>(bar, sW, &tmap_w2, j * kChunk + kc2 * kStageK, h * 128, (CL ? N2 : 128) * 128,
+                                         N2 / 2, rank, wc);
         };
         w1(0);
         if (NCH > 1) w1(1);
@@ -618,7 +637,7 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
           if (j + 2 < NCH) w1(j + 2);
         }
       }
-      if (TWO) drain_ring<TWO>(bar, wc);
+      if (CL) drain_ring<TWO>(bar, wc);
     }
   } else if (warp == kTmaX) {
     // ===================== TMA: activation tiles (bf16 copy written by pass A) =====================
@@ -646,7 +665,7 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (pairs: the leader CTA issues for both) =====================
-    if (rank == 0) {
+    if (!TWO || rank == 0) {
       uint32_t wc = 0, g0 = 0, it = 0;
       long long pr[6] = {0, 0, 0, 0, 0, 0};   // x_full, w_full (conv1), d1_done, d2_empty, w_full (conv2), total
       long long* P = A.prof ? pr : nullptr;
@@ -661,7 +680,7 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
         // before issuing it, so no further wait is needed here.
         auto c1 = [&](int j) {
           const uint32_t b = (g0 + j) & 1u;
-          issue_conv1<C, TWO>(bar, sXt, sW, tmem_base + b * (uint32_t)kChunk, wc, P ? P + 1 : nullptr);
+          issue_conv1<C, TWO, MC>(bar, sXt, sW, tmem_base + b * (uint32_t)kChunk, wc, P ? P + 1 : nullptr);
           commit_elect<TWO>(bar.d1_full + 8u * b);
           if (j == NCH - 1) commit_elect<TWO>(bar.x_empty + 8u * xb);   // the activation tile may be refilled
         };
@@ -672,7 +691,7 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
           mbar_wait_timed(bar.d1_done + 8u * b, (g >> 1) & 1u, P ? P + 2 : nullptr);          // y1 chunk written to TMEM
           if (j == 0) mbar_wait_timed(bar.d2_empty, (it & 1u) ^ 1u, P ? P + 3 : nullptr);     // previous tile's output drained
           tc_fence_after();
-          issue_conv2<C, TWO>(bar, sW, tmem_base, b, j == 0, wc, P ? P + 4 : nullptr);
+          issue_conv2<C, TWO, MC>(bar, sW, tmem_base, b, j == 0, wc, P ? P + 4 : nullptr);
           if (j == NCH - 1) commit_elect<TWO>(bar.d2_full);
           if (j + 2 < NCH) c1(j + 2);
         }
@@ -810,7 +829,7 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
   }
 
   tc_fence_before();
-  if (TWO) cluster_sync_all();
+  if (CL) cluster_sync_all();
   else __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
@@ -841,9 +860,10 @@ int launch_fused(void (*kernel)(KArgs...), int grid, int threads, size_t smem, b
   return OSD_OK;
 }
 
-template <int C, bool TWO>
+template <int C, bool TWO, bool MC>
 int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t stream) {
   using S = Smem<C>;
+  constexpr bool CL = TWO || MC;
   static_assert(S::total <= 227 * 1024, "shared-memory plan exceeds 227 KB");
   constexpr int N2 = C < 128 ? C : 128;
   const int C2 = 2 * C, B = d->batch, nl = d->num_levels;
@@ -856,9 +876,9 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
   CUtensorMap map1, map2;
   XMaps xm;
   memset(&xm, 0, sizeof(xm));
-  int rc = make_bf16_map(d->w1x_bf16, C2, C, C, kStageK, TWO ? 64 : 128, &map1);
+  int rc = make_bf16_map(d->w1x_bf16, C2, C, C, kStageK, CL ? 64 : 128, &map1);
   if (rc != OSD_OK) return rc;
-  rc = make_bf16_map(d->w2_bf16, C, C2, C2, kStageK, TWO ? N2 / 2 : 128, &map2);
+  rc = make_bf16_map(d->w2_bf16, C, C2, C2, kStageK, CL ? N2 / 2 : 128, &map2);
   if (rc != OSD_OK) return rc;
 
   FArgs A{};
@@ -890,7 +910,28 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
   if (tiles <= 0) return OSD_OK;
   // one CTA (or one CTA pair) per SM (pair of SMs), persistent over tiles (pairs of tiles)
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  if (TWO) grid = 2 * std::min((tiles + 1) / 2, kNumSMs / 2);
+  auto kA = fusion_stats1_kernel<C, TWO, MC>;
+  rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kA), S::total);
+  if (rc != OSD_OK) return rc;
+  if (CL) {
+    // persistent clusters: every cluster of the grid must be resident at once (a cluster that has to wait for a free SM
+    // pair would run its whole share of the tiles after the others have finished)
+    int max_clusters = kNumSMs / 2;
+    cudaLaunchConfig_t q{};
+    q.gridDim = dim3((unsigned)kNumSMs);
+    q.blockDim = dim3((unsigned)kThreadsB);
+    q.dynamicSmemBytes = S::total;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    q.attrs = qa; q.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, reinterpret_cast<const void*>(kA), &q) == cudaSuccess && n > 0)
+      max_clusters = std::min(max_clusters, n);
+    else
+      (void)cudaGetLastError();
+    grid = 2 * std::min((tiles + 1) / 2, max_clusters);
+  }
   static const bool prof_on = [] { const char* e = getenv("OSD_FUSION_PROF"); return e && e[0] == '1'; }();
   static long long* prof_dev = nullptr;
   if (prof_on) {
@@ -899,17 +940,14 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
     A.prof = prof_dev;
   }
 
-  auto kA = fusion_stats1_kernel<C, TWO>;
-  rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kA), S::total);
-  if (rc != OSD_OK) return rc;
   const bool s01 = d->lrelu_slope >= 0.f && d->lrelu_slope <= 1.f;
-  auto kB = s01 ? fusion_b2b_kernel<C, false, true, TWO> : fusion_b2b_kernel<C, false, false, TWO>;
-  auto kBfinal = s01 ? fusion_b2b_kernel<C, true, true, TWO> : fusion_b2b_kernel<C, true, false, TWO>;
+  auto kB = s01 ? fusion_b2b_kernel<C, false, true, TWO, MC> : fusion_b2b_kernel<C, false, false, TWO, MC>;
+  auto kBfinal = s01 ? fusion_b2b_kernel<C, true, true, TWO, MC> : fusion_b2b_kernel<C, true, false, TWO, MC>;
   rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kB), S::total);
   if (rc != OSD_OK) return rc;
 
   // ---- pass A: GroupNorm-1 statistics (+ bf16 copy of the features)
-  rc = launch_fused(kA, grid, kThreadsA, S::total, TWO, stream, map1, A);
+  rc = launch_fused(kA, grid, kThreadsA, S::total, CL, stream, map1, A);
   if (rc != OSD_OK) return rc;
   OSD_LAUNCH_CHECK("fusion_stats1_kernel");
   timeline_mark("fusion_stats1_kernel", stream);
@@ -920,7 +958,7 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
   static const bool recompute = [] { const char* e = getenv("OSD_FUSION_RECOMPUTE"); return e && e[0] == '1'; }();
   A.store = recompute ? 0 : 1;
   A.final_xform = 0;
-  rc = launch_fused(kB, grid, kThreadsB, S::total, TWO, stream, map1, map2, xm, A);
+  rc = launch_fused(kB, grid, kThreadsB, S::total, CL, stream, map1, map2, xm, A);
   if (rc != OSD_OK) return rc;
   OSD_LAUNCH_CHECK("fusion_b2b_kernel");
   timeline_mark("fusion_b2b_kernel", stream);
@@ -934,7 +972,7 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
     A.stats2 = nullptr;
     rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kBfinal), S::total);
     if (rc != OSD_OK) return rc;
-    rc = launch_fused(kBfinal, grid, kThreadsB, S::total, TWO, stream, map1, map2, xm, A);
+    rc = launch_fused(kBfinal, grid, kThreadsB, S::total, CL, stream, map1, map2, xm, A);
     if (rc != OSD_OK) return rc;
     OSD_LAUNCH_CHECK("fusion_b2b_kernel");
     timeline_mark("fusion_b2b_kernel(final)", stream);
@@ -965,13 +1003,29 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
 }  // namespace
 
 int fusion_full_forward(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t stream) {
-  // OSD_FUSION_2CTA=1: CTA pairs (tcgen05 cta_group::2, M = 256 across two SMs); default: one CTA per tile
-  static const bool pairs = [] { const char* e = getenv("OSD_FUSION_2CTA"); return e && e[0] == '1'; }();
+  // OSD_FUSION_MODE: "single" = one CTA per tile; "mc" = clusters of 2 CTAs, one tile each, every weight stage
+  // fetched once from L2 and multicast into both CTAs' rings; "pair" (or OSD_FUSION_2CTA=1) = CTA pairs on tcgen05
+  // cta_group::2 (M = 256 across two SMs)
+  static const int mode = [] {
+    const char* e = getenv("OSD_FUSION_MODE");
+    const char* p2 = getenv("OSD_FUSION_2CTA");
+    if (e && !strcmp(e, "pair")) return 1;
+    if (e && !strcmp(e, "mc")) return 2;
+    if (e && !strcmp(e, "single")) return 0;
+    if (p2 && p2[0] == '1') return 1;
+    return kDefaultFusionMode;
+  }();
+#define OSD_FUSION_DISPATCH(CH)                                         \
+  case CH:                                                              \
+    if (mode == 1) return run_full<CH, true, false>(d, ws, stream);     \
+    if (mode == 2) return run_full<CH, false, true>(d, ws, stream);     \
+    return run_full<CH, false, false>(d, ws, stream);
   switch (d->channels) {
-    case 64: return pairs ? run_full<64, true>(d, ws, stream) : run_full<64, false>(d, ws, stream);
-    case 128: return pairs ? run_full<128, true>(d, ws, stream) : run_full<128, false>(d, ws, stream);
-    case 256: return pairs ? run_full<256, true>(d, ws, stream) : run_full<256, false>(d, ws, stream);
+    OSD_FUSION_DISPATCH(64)
+    OSD_FUSION_DISPATCH(128)
+    OSD_FUSION_DISPATCH(256)
   }
+#undef OSD_FUSION_DISPATCH
   set_error("osd_fusion: channels must be 64, 128 or 256 (got %d)", d->channels);
   return OSD_ERR_INVALID;
 }

@@ -44,3 +44,114 @@ def test_pooler_and_postprocessor_reproduce_the_reference_second_stage(golden_di
         np.testing.assert_allclose(gs, rs, rtol=2e-5, atol=0)     # expf vs ATen exp on logits that differ by a few ulp
         np.testing.assert_allclose(gb, rb, rtol=0, atol=2e-3)
         np.testing.assert_array_equal(o.get_field("labels").cpu().numpy(), z[f"out_labels{i}"][:len(gs)])
+
+
+# ------------------------------------------------------------------------------------------------------
+# the dense middle on the GPU (csrc/box_head.cu): six tcgen05 GEMM launches with GroupNorm / LeakyReLU epilogues
+# ------------------------------------------------------------------------------------------------------
+def _bf(t):
+    return t.bfloat16().float()
+
+
+def emulated_dense(pooled, supp, m):
+    """The oracle's box_head_dense on bf16-ROUNDED operands and bf16 activations between layers, fp32 accumulation --
+    what the tensor-core path computes (differences left: summation order, one-pass GroupNorm variance)."""
+    import torch.nn.functional as F
+
+    b, r, c, p, _ = pooled.shape
+    cdc, agg = m["compress_dim_conv"], m["feature_aggreg"]
+    with torch.no_grad():
+        x = torch.cat((_bf(pooled).reshape(-1, c, p, p), _bf(supp).expand_as(pooled).reshape(-1, c, p, p)), 1)
+        y = F.conv2d(x, _bf(cdc[0].weight), cdc[0].bias)
+        a1 = _bf(cdc[2](cdc[1](y)))
+        y = F.conv2d(a1, _bf(cdc[3].weight), cdc[3].bias)
+        a2 = _bf(cdc[5](cdc[4](y)))
+        y = F.conv2d(a2, _bf(agg[0].weight), agg[0].bias, padding=1)
+        a3 = _bf(agg[2](agg[1](y)))
+        h6 = _bf(F.relu(F.linear(a3.reshape(a3.size(0), -1), _bf(m["fc6"].weight), m["fc6"].bias)))
+        h7 = _bf(F.relu(F.linear(h6, _bf(m["fc7"].weight), m["fc7"].bias)))
+        return (F.linear(h7, _bf(m["cls_score"].weight), m["cls_score"].bias),
+                F.linear(h7, _bf(m["bbox_pred"].weight), m["bbox_pred"].bias), (a1, a2, a3, h6, h7))
+
+
+def gpu_head(mods, c, mlp, roi_chunk=0):
+    import oneshotdet_b200 as osd
+
+    head = osd.BoxHeadDense(c, mlp, roi_chunk=roi_chunk)
+    sd = {("predictor." + k if k.startswith(("cls_score", "bbox_pred")) else k): v for k, v in mods.state_dict().items()}
+    head.load_state_dict(sd)
+    return head.to(DEV).eval()
+
+
+def rel_err(got, ref):
+    return float((got - ref).abs().max()) / max(float(ref.abs().max()), 1e-12)
+
+
+def test_dense_head_kernels_against_the_executed_reference(golden_dir):
+    """class_logits / box_regression of the reference's executed ROIBoxHead.forward (fp32) from the tcgen05 path
+    (bf16 operands and activations, fp32 accumulation): within 2 % of the output range; within 0.5 % of the oracle
+    evaluated on bf16-rounded operands.  Then the whole second stage on the GPU: pooler -> dense head -> post-processor."""
+    import types
+
+    import oneshotdet_b200 as osd
+
+    z, mods = load(golden_dir)
+    c, mlp = int(z["channels"]), int(z["w_fc7.weight"].shape[0])
+    pooled, supp = torch.from_numpy(z["pooled"]), torch.from_numpy(z["supp"])
+    head = gpu_head(mods, c, mlp)
+    logits, reg = head(pooled.to(DEV), supp.to(DEV))
+    torch.cuda.synchronize()
+    logits, reg = logits.cpu(), reg.cpu()
+    el, er, _ = emulated_dense(pooled, supp, mods)
+    assert rel_err(logits, el) <= 5e-3 and rel_err(reg, er) <= 5e-3, (rel_err(logits, el), rel_err(reg, er))
+    rl, rr = torch.from_numpy(z["class_logits"]), torch.from_numpy(z["box_regression"])
+    assert rel_err(logits, rl) <= 2e-2 and rel_err(reg, rr) <= 2e-2, (rel_err(logits, rl), rel_err(reg, rr))
+
+    # the whole second stage on the GPU
+    b, h, w = int(z["batch"]), int(z["height"]), int(z["width"])
+    feats, _ = orc.synth_features(b, 1, c, h, w, int(z["seed"]))
+    sizes = [tuple(int(v) for v in hw) for hw in z["image_sizes"]]
+    boxes = torch.from_numpy(z["boxes"])
+    pooler = osd.Pooler((7, 7), [1 / s for s in orc.FPN_STRIDES], 2)
+    bl = [osd.BoxList(boxes[i].to(DEV), (sizes[i][1], sizes[i][0]), mode="xyxy") for i in range(b)]
+    lg, rg = head(pooler([f.to(DEV) for f in feats], bl), supp.to(DEV))
+    st, nt, dpi = z["params"]
+    cfg = types.SimpleNamespace(FEW_SHOT=types.SimpleNamespace(SECOND_STAGE_CLS_LOSS="ce_loss"))
+    post = osd.PostProcessor(cfg, float(st), float(nt), int(dpi), osd.BoxCoder(tuple(float(v) for v in z["weights"])), False).eval()
+    out = post((lg, rg), bl, target_ids=z["target_ids"].tolist())
+    for i, o in enumerate(out):
+        rb, rs = z[f"out_boxes{i}"], z[f"out_scores{i}"]
+        gb, gs = o.bbox.cpu().numpy(), o.get_field("scores").cpu().numpy()
+        # scores are softmax probabilities of logits that differ by bf16 rounding: the detections above the score
+        # threshold are the same set unless a score sits within that error of the threshold
+        assert abs(gb.shape[0] - rb.shape[0]) <= 1
+        if gb.shape == rb.shape:
+            gb, gs = canon(gb, gs); rb, rs = canon(rb, rs)
+            np.testing.assert_allclose(gs, rs, rtol=0, atol=5e-3)
+
+
+@pytest.mark.parametrize("c,mlp,b,r,chunk", [(64, 64, 2, 5, 0), (128, 256, 1, 9, 4), (256, 1024, 2, 37, 16), (256, 1024, 3, 64, 0)])
+def test_dense_head_layers_against_bf16_emulation(c, mlp, b, r, chunk):
+    """Random weights and inputs at the reference's widths, odd ROI counts and several chunks: every layer's output
+    (read back from the workspace when one chunk holds all ROIs) and the final outputs against the bf16-emulated oracle."""
+    torch.manual_seed(100 + c + r)
+    mods = orc.make_box_head_modules(c, mlp)
+    with torch.no_grad():
+        for p_ in mods.parameters():            # default inits give near-zero logits: use O(1)-signal weights
+            if p_.dim() > 1:
+                p_.normal_(std=1.0 / (p_[0].numel() ** 0.5))
+            else:
+                p_.uniform_(-0.5, 0.5)
+        for k in ("compress_dim_conv.1", "compress_dim_conv.4", "feature_aggreg.1"):
+            mods.get_submodule(k).weight.uniform_(0.5, 1.5)
+    pooled = torch.randn(b, r, c, 7, 7)
+    supp = torch.randn(b, 1, c, 7, 7)
+    head = gpu_head(mods, c, mlp, roi_chunk=chunk)
+    logits, reg = head(pooled.to(DEV), supp.to(DEV))
+    torch.cuda.synchronize()
+    el, er, _ = emulated_dense(pooled, supp, mods)
+    # a bf16 rounding boundary crossed in one activation moves later layers by up to one bf16 ulp of that value
+    assert rel_err(logits.cpu(), el) <= 1e-2, rel_err(logits.cpu(), el)
+    assert rel_err(reg.cpu(), er) <= 1e-2, rel_err(reg.cpu(), er)
+    fl, fr = orc.box_head_dense(pooled, supp, mods)
+    assert rel_err(logits.cpu(), fl) <= 3e-2 and rel_err(reg.cpu(), fr) <= 3e-2

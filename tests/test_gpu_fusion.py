@@ -128,3 +128,21 @@ def test_matching_module_fusion_mode_loads_reference_state_dict():
     ref = orc.match_fusion(feats, supp, 2, ref_module)
     for o, r in zip(out, ref):
         assert float((o.cpu() - r).abs().max()) <= 0.08
+
+
+@pytest.mark.parametrize("mode", ["single", "mc", "pair"])
+def test_cluster_modes_in_subprocess(mode):
+    """The fused kernels' other launch forms (OSD_FUSION_MODE is read once per process): clusters of two CTAs with
+    multicast weight stages ('mc'), CTA pairs on cta_group::2 ('pair') and the plain one-CTA form must all pass the
+    full-module parity tests of this file."""
+    import subprocess
+    import sys
+
+    if os.environ.get("OSD_FUSION_SUBTEST"):
+        pytest.skip("already inside the subprocess")
+    env = dict(os.environ, OSD_FUSION_MODE=mode, OSD_FUSION_SUBTEST="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                        "full_module or reference_fixtures", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=900,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
