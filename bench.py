@@ -704,7 +704,7 @@ def run_b200_arm(args):
     #      stream while batch i replays, D2H on a third stream) and the plain serial run_host, against the measured
     #      host->device ceiling of the same buffers
     e2e = None
-    if rank == 0 or world > 1:
+    if (rank == 0 or world > 1) and not args.no_e2e:
         host_in = pipe.make_host_inputs(pinned=True)
         for h, d in zip(host_in, pipe.input_tensors()):
             h.copy_(d)
@@ -815,8 +815,9 @@ def main():
                     help="skip the multi-process variant of the CPU baseline (cpu_baseline.multi_process)")
     ap.add_argument("--ref-worker", type=int, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--no-fusion", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end measurement (diagnosis runs)")
     ap.add_argument("--serial", action="store_true", help="one stream: matching then post-processing, no overlap")
-    ap.add_argument("--depth", type=int, default=2,
+    ap.add_argument("--depth", type=int, default=1,
                     help="consecutive steps issued per graph replay, their post-processing chains side by side (1: one step)")
     ap.add_argument("--gather", choices=["peer", "peer-kernel", "block", "packed", "none"], default="peer",
                     help="N>1: how a step's detections reach every rank (see run_b200_arm); 'none' is a diagnosis run")

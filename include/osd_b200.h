@@ -338,6 +338,8 @@ typedef struct {
   void* workspace;          /* device scratch of osd_roi_pool_workspace_bytes() bytes (256-byte aligned) for the
                                channels-last copy of the maps; NULL: pool straight from NCHW (slower, same result) */
   size_t workspace_bytes;
+  void* out_nhwc_bf16;      /* optional device bf16 [B*R, P*P, C] (needs `workspace`): the same values rounded to bf16 in the
+                               K-major row layout osd_box_head_forward reads (pooled_nhwc_bf16); `out` may then be NULL */
 } osd_roi_pool_desc;
 
 int osd_roi_pool_workspace_bytes(const osd_roi_pool_desc* desc, size_t* bytes);
@@ -371,7 +373,7 @@ typedef struct {
   int32_t roi_chunk;        /* ROIs per pass over the six layers; <= 0: sized so a chunk's activations stay in L2 */
   float gn_eps;             /* 1e-5 */
   float lrelu_slope;        /* 0.2 */
-  const float* pooled;      /* device [B*R, C, 7, 7] */
+  const float* pooled;      /* device [B*R, C, 7, 7], or NULL when pooled_nhwc_bf16 is given */
   const float* supp;        /* device [B, C, 7, 7] */
   const void* w1; const float* b1; const float* gn1_w; const float* gn1_b;
   const void* w2; const float* b2; const float* gn2_w; const float* gn2_b;
@@ -381,6 +383,8 @@ typedef struct {
   const void* wp; const float* bp;
   float* class_logits;      /* device [B*R, num_classes] */
   float* box_regression;    /* device [B*R, num_box_out] */
+  const void* pooled_nhwc_bf16;  /* optional device bf16 [B*R, 49, C] written by osd_roi_pool (out_nhwc_bf16): skips the
+                                    fp32 round trip and the repacking pass */
 } osd_box_head_desc;
 
 int osd_box_head_workspace_bytes(const osd_box_head_desc* desc, size_t* bytes);

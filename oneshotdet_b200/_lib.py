@@ -88,7 +88,7 @@ class RoiPoolDesc(ctypes.Structure):
                 ("canonical_level", ctypes.c_int32), ("eps", ctypes.c_float),
                 ("feat", ctypes.c_void_p * OSD_MAX_LEVELS), ("rois", ctypes.c_void_p), ("roi_count", ctypes.c_void_p),
                 ("out", ctypes.c_void_p), ("levels_out", ctypes.c_void_p), ("workspace", ctypes.c_void_p),
-                ("workspace_bytes", ctypes.c_size_t)]
+                ("workspace_bytes", ctypes.c_size_t), ("out_nhwc_bf16", ctypes.c_void_p)]
 
 
 class BoxHeadDesc(ctypes.Structure):
@@ -101,7 +101,8 @@ class BoxHeadDesc(ctypes.Structure):
                 ("w3", ctypes.c_void_p), ("b3", ctypes.c_void_p), ("gn3_w", ctypes.c_void_p), ("gn3_b", ctypes.c_void_p),
                 ("w6", ctypes.c_void_p), ("b6", ctypes.c_void_p), ("w7", ctypes.c_void_p), ("b7", ctypes.c_void_p),
                 ("wp", ctypes.c_void_p), ("bp", ctypes.c_void_p),
-                ("class_logits", ctypes.c_void_p), ("box_regression", ctypes.c_void_p)]
+                ("class_logits", ctypes.c_void_p), ("box_regression", ctypes.c_void_p),
+                ("pooled_nhwc_bf16", ctypes.c_void_p)]
 
 
 # every symbol include/osd_b200.h declares: name -> (restype, argtypes)

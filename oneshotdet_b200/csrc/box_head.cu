@@ -42,13 +42,22 @@ using namespace tc;
 constexpr int kP = 7, kPix = kP * kP;
 constexpr int kBM = 128;                       // rows per tile (UMMA M)
 constexpr int kBK = 64;                        // K elements per stage (one 128-byte swizzle row of bf16)
-constexpr int kRing = 4;
 constexpr uint32_t kABytes = kBM * kBK * 2;    // 16 KB
-constexpr uint32_t kBBytesMax = 256 * kBK * 2; // 32 KB (N tile <= 256)
-constexpr uint32_t kStage = kABytes + kBBytesMax;
+constexpr uint32_t kRingBytes = 4 * (kABytes + 256 * kBK * 2);   // 192 KB of operand stages
+constexpr int kMaxRing = 10;
+// ring depth for an N tile of BN columns: a stage is the A tile (16 KB) + BN rows of W (128 B each).  Narrow layers get a
+// deeper ring -- their stages are consumed faster (4 MMAs of BN/2 clocks each) while the TMA latency stays the same
+__host__ __device__ constexpr uint32_t stage_bytes(int bn) { return kABytes + (uint32_t)bn * 128u; }
+__host__ __device__ constexpr int ring_depth(int bn) {
+  return (int)(kRingBytes / stage_bytes(bn)) < kMaxRing ? (int)(kRingBytes / stage_bytes(bn)) : kMaxRing;
+}
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 32 * (kEpiWarps + 2);
-constexpr uint32_t kGemmSmem = kRing * kStage + 256 /* barriers */ + 2 * kEpiWarps * 32 * 4 /* exchange */ + 1024 /* align */;
+constexpr int kMaxParamCols = 2048;            // bias / gamma / beta of up to this many output columns are staged in smem
+constexpr uint32_t kXchBytes = 2 * kEpiWarps * 32 * 4;          // statistics exchange between the two warps of an ROI
+constexpr uint32_t kCoefBytes = 2 * 2 * 2 * 128 * 8;            // (scale, shift) [tile parity][ROI][column half][128]
+constexpr uint32_t kParamBytes = kMaxParamCols * 4 + 2 * 512 * 4;   // bias [2048], gamma [512], beta [512]
+constexpr uint32_t kGemmSmem = kRingBytes + 256 /* barriers */ + kXchBytes + kCoefBytes + kParamBytes + 1024 /* align */;
 
 enum { A_PLAIN = 0, A_ROI = 1, A_ROI_3X3 = 2 };
 
@@ -121,13 +130,20 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   constexpr int BN = 2 * CPW;
   constexpr int LD = CPW >= 32 ? 32 : 16;
   static_assert(BN <= 256 && BN % 16 == 0, "N tile");
+  constexpr int kRing = ring_depth(BN);
+  constexpr uint32_t kStage = stage_bytes(BN);
+  static_assert(kStage % 1024 == 0 && kRing >= 2 && 8 * (2 * kRing + 4) + 4 <= 256, "ring layout");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar0 = base + kRing * kStage;
+  const uint32_t bar0 = base + kRingBytes;
   const uint32_t b_full = bar0, b_empty = bar0 + 8u * kRing, b_accf = bar0 + 16u * kRing, b_acce = b_accf + 16u;
   const uint32_t tmem_slot = b_acce + 16u;
-  float* xch = reinterpret_cast<float*>(gen + kRing * kStage + 256);   // [2][kEpiWarps][32]
+  float* xch = reinterpret_cast<float*>(gen + kRingBytes + 256);   // [2][kEpiWarps][32]
+  float2* coef = reinterpret_cast<float2*>(gen + kRingBytes + 256 + kXchBytes);
+  float* sBias = reinterpret_cast<float*>(gen + kRingBytes + 256 + kXchBytes + kCoefBytes);
+  float* sGamma = sBias + kMaxParamCols;
+  float* sBeta = sGamma + 512;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int m_tiles = G.a_mode == A_PLAIN ? (G.M + kBM - 1) / kBM : (G.M + 1) / 2;
@@ -216,7 +232,22 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
   } else {
     // ===================== epilogue (warps 0-7; thread = tile row) =====================
+    // Per-column parameters live in shared memory (a warp reads the same column in all lanes: one broadcast wavefront,
+    // four columns per LDS.128).  The global loads they replace (four per element) were what bound the first version:
+    // 2500 instructions per thread and tile, LSU queue full.
     const int q = warp & 3, hh = warp >> 2;
+    const int etid = threadIdx.x;                       // 0 .. 255
+    const bool params_in_smem = G.N <= kMaxParamCols;
+    if (params_in_smem) {
+      for (int c = etid; c < G.N; c += 32 * kEpiWarps) {
+        sBias[c] = __ldg(G.bias + c);
+        if (EPI == 1) {
+          sGamma[c] = __ldg(G.gamma + c);
+          sBeta[c] = __ldg(G.beta + c);
+        }
+      }
+    }
+    named_bar_sync(5, 32 * kEpiWarps);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
@@ -229,8 +260,10 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         constexpr int NG = CPW / GS;
         static_assert(NG <= 16, "a warp keeps (sum, sum of squares) of at most 16 groups");
         const int row = q * 32 + lane, rl = row & 63;
-        const int roi = mt * 2 + (row >> 6);
+        const int rloc = row >> 6;                       // which of the tile's two ROIs
+        const int roi = mt * 2 + rloc;
         const bool valid = rl < kPix && roi < G.M;
+        // ---- pass 1: (sum, sum of squares) of y = d + bias per group over this thread's row
         float acc_s[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc_s[i] = 0.f;
@@ -239,12 +272,19 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           uint32_t r[32];
           tmem_ld_cols<LD>(taddr + (uint32_t)cb, r);
           tmem_ld_wait();
+          const float4* bp = reinterpret_cast<const float4*>(sBias + col0 + cb);
 #pragma unroll
-          for (int i = 0; i < LD; ++i) {
-            const int gi = (cb + i) / GS;
-            const float y = __uint_as_float(r[i]) + __ldg(G.bias + col0 + cb + i);
-            acc_s[2 * gi] += y;
-            acc_s[2 * gi + 1] = fmaf(y, y, acc_s[2 * gi + 1]);
+          for (int i4 = 0; i4 < LD / 4; ++i4) {
+            const float4 bv = bp[i4];
+            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * i4 + e;
+              const int gi = (cb + i) / GS;
+              const float y = __uint_as_float(r[i]) + bb[e];
+              acc_s[2 * gi] += y;
+              acc_s[2 * gi + 1] = fmaf(y, y, acc_s[2 * gi + 1]);
+            }
           }
         }
         if (!valid) {
@@ -264,13 +304,25 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const float mean = sum * inv_n;
         const float var = fmaxf(fmaf(-mean, mean, sq * inv_n), 0.f);
         const float rstd = 1.0f / sqrtf(var + G.eps);          // lanes 2g, 2g+1: statistics of group g
-        float gsc[NG], gsh[NG];
+        // ---- coefficient table of this (ROI, column half): y_out = d * scale + shift, computed once per column by the
+        //      64 threads of the warp pair instead of once per element by every row
+        float2* ctab = coef + (((it & 1u) * 2 + rloc) * 2 + hh) * 128;     // [parity][roi][half][128 columns]
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          gsc[g] = __shfl_sync(0xffffffffu, rstd, 2 * g);
-          gsh[g] = -__shfl_sync(0xffffffffu, mean, 2 * g) * gsc[g];
+        for (int u = 0; u < (CPW + 63) / 64; ++u) {
+          const int cl = (q & 1) * 32 + lane + 64 * u;          // column inside this warp pair's half
+          const int cc = cl < CPW ? cl : 0;
+          const int gi = cc / GS;
+          const float rs = __shfl_sync(0xffffffffu, rstd, 2 * gi);
+          const float mn = __shfl_sync(0xffffffffu, mean, 2 * gi);
+          if (cl < CPW) {
+            const float sc = rs * sGamma[col0 + cl];
+            ctab[cl] = make_float2(sc, fmaf(sBias[col0 + cl] - mn, sc, sBeta[col0 + cl]));
+          }
         }
+        named_bar_sync(1 + (warp >> 1), 64);
+        // ---- pass 2: normalise + LeakyReLU on a second read of the accumulator, bf16 rows to global memory
         __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(G.out) + ((size_t)roi * kPix + rl) * (size_t)G.ldo + col0;
+        const float slope = G.slope;
 #pragma unroll
         for (int cb = 0; cb < CPW; cb += LD) {
           uint32_t r[32];
@@ -281,19 +333,16 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(b_acce + 8u * acc);
           }
+          const float4* cp4 = reinterpret_cast<const float4*>(ctab + cb);   // (scale, shift) of two columns
           uint32_t p[16];
 #pragma unroll
           for (int i = 0; i < LD; i += 2) {
-            float y[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int c = col0 + cb + i + e;
-              const int gi = (cb + i + e) / GS;
-              float v = fmaf(__uint_as_float(r[i + e]) + __ldg(G.bias + c), gsc[gi], gsh[gi]);
-              v = fmaf(v, __ldg(G.gamma + c), __ldg(G.beta + c));
-              y[e] = v > 0.f ? v : v * G.slope;
-            }
-            p[i >> 1] = pack_bf16x2(y[0], y[1]);
+            const float4 k = cp4[i >> 1];
+            float a = fmaf(__uint_as_float(r[i]), k.x, k.y);
+            float b = fmaf(__uint_as_float(r[i + 1]), k.z, k.w);
+            a = a > 0.f ? a : a * slope;
+            b = b > 0.f ? b : b * slope;
+            p[i >> 1] = pack_bf16x2(a, b);
           }
           if (valid) store_bf16_row<LD / 2>(orow + cb, p);
         }
@@ -316,7 +365,8 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < LD; ++i) {
             const int c = c0 + i;
-            float v = __uint_as_float(r[i]) + (c < G.N ? __ldg(G.bias + c) : 0.f);
+            const float bv = c < G.N ? (params_in_smem ? sBias[c] : __ldg(G.bias + c)) : 0.f;
+            const float v = __uint_as_float(r[i]) + bv;
             y[i] = G.relu ? fmaxf(v, 0.f) : v;
           }
           if (!valid) continue;
@@ -428,28 +478,29 @@ struct HeadWorkspace {
   __nv_bfloat16* xb;   // [chunk*49, C]
   __nv_bfloat16* a1;   // [chunk*49, 2C]
   __nv_bfloat16* a2;   // [chunk*49, C]
-  __nv_bfloat16* a3;   // [chunk*49, C/2] == [chunk, 49*C/2]
-  __nv_bfloat16* h6;   // [chunk, mlp]
-  __nv_bfloat16* h7;   // [chunk, mlp]
+  __nv_bfloat16* a3;   // [B*R*49, C/2] == [B*R, 49*C/2]: all ROIs, the fully connected layers run once over everything
+  __nv_bfloat16* h6;   // [B*R, mlp]
+  __nv_bfloat16* h7;   // [B*R, mlp]
 };
 
 int head_chunk(const osd_box_head_desc* d) {
   const int64_t n = (int64_t)d->batch * d->rois_per_image;
-  // default: ~50 MB for the widest intermediate (a1) so that a chunk's activations stay in L2 from layer to layer
-  int64_t c = d->roi_chunk > 0 ? d->roi_chunk : std::max<int64_t>(2, (48ll << 20) / ((int64_t)kPix * 2 * d->channels * 2) / 2 * 2);
+  // default: 592 tiles of two ROIs = 4 full waves of the 148 SMs per layer (8 for conv1's two N tiles at C = 256); the
+  // widest intermediate (a1, 59 MB at C = 256) then stays in L2 from conv1 to conv2
+  int64_t c = d->roi_chunk > 0 ? d->roi_chunk : 8 * kNumSMs;
   c = (c + 1) / 2 * 2;
   return (int)std::min<int64_t>(c, std::max<int64_t>(n, 2));
 }
 
 size_t head_carve(const osd_box_head_desc* d, Carver& c, HeadWorkspace* ws) {
-  const size_t C = d->channels, ch = head_chunk(d), mlp = d->mlp_dim;
+  const size_t C = d->channels, ch = head_chunk(d), mlp = d->mlp_dim, n_all = (size_t)d->batch * d->rois_per_image;
   ws->sb = c.take<__nv_bfloat16>((size_t)d->batch * kPix * C);
   ws->xb = c.take<__nv_bfloat16>(ch * kPix * C);
   ws->a1 = c.take<__nv_bfloat16>(ch * kPix * 2 * C);
   ws->a2 = c.take<__nv_bfloat16>(ch * kPix * C);
-  ws->a3 = c.take<__nv_bfloat16>(ch * kPix * (C / 2));
-  ws->h6 = c.take<__nv_bfloat16>(ch * mlp);
-  ws->h7 = c.take<__nv_bfloat16>(ch * mlp);
+  ws->a3 = c.take<__nv_bfloat16>(n_all * kPix * (C / 2));
+  ws->h6 = c.take<__nv_bfloat16>(n_all * mlp);
+  ws->h7 = c.take<__nv_bfloat16>(n_all * mlp);
   return c.total();
 }
 
@@ -485,7 +536,10 @@ extern "C" int osd_box_head_forward(const osd_box_head_desc* d, void* workspace,
   if (rc != OSD_OK) return rc;
   if (d->batch == 0) return OSD_OK;
   OSD_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "osd_box_head_forward: workspace must be 256-byte aligned");
-  OSD_REQUIRE(d->pooled && d->supp && d->class_logits && d->box_regression, "osd_box_head_forward: null input / output");
+  OSD_REQUIRE((d->pooled || d->pooled_nhwc_bf16) && d->supp && d->class_logits && d->box_regression,
+              "osd_box_head_forward: null input / output");
+  OSD_REQUIRE(d->pooled_nhwc_bf16 == nullptr || (reinterpret_cast<uintptr_t>(d->pooled_nhwc_bf16) & 15) == 0,
+              "osd_box_head_forward: pooled_nhwc_bf16 must be 16-byte aligned");
   OSD_REQUIRE(d->w1 && d->b1 && d->gn1_w && d->gn1_b && d->w2 && d->b2 && d->gn2_w && d->gn2_b && d->w3 && d->b3 && d->gn3_w &&
                   d->gn3_b && d->w6 && d->b6 && d->w7 && d->b7 && d->wp && d->bp,
               "osd_box_head_forward: null parameter");
@@ -520,17 +574,19 @@ extern "C" int osd_box_head_forward(const osd_box_head_desc* d, void* workspace,
 
   for (int64_t r0 = 0; r0 < n_all; r0 += chunk) {
     const int n = (int)std::min<int64_t>(chunk, n_all - r0);
-    pack_roi_kernel<<<(unsigned)n, 256, pk_smem, stream>>>(d->pooled + (size_t)r0 * C * kPix, ws.xb, C);
-    OSD_LAUNCH_CHECK("pack_roi_kernel");
-    timeline_mark("pack_roi_kernel", stream);
+    const void* xrows = ws.xb;
+    if (d->pooled_nhwc_bf16) {
+      xrows = static_cast<const __nv_bfloat16*>(d->pooled_nhwc_bf16) + (size_t)r0 * kPix * C;
+    } else {
+      pack_roi_kernel<<<(unsigned)n, 256, pk_smem, stream>>>(d->pooled + (size_t)r0 * C * kPix, ws.xb, C);
+      OSD_LAUNCH_CHECK("pack_roi_kernel");
+      timeline_mark("pack_roi_kernel", stream);
+    }
 
-    CUtensorMap mX, mA1, mA2, mA3, mH6, mH7;
-    if ((rc = make_bf16_map(ws.xb, (int64_t)n * kPix, C, C, kBK, kPix, &mX)) != OSD_OK) return rc;
+    CUtensorMap mX, mA1, mA2;
+    if ((rc = make_bf16_map(xrows, (int64_t)n * kPix, C, C, kBK, kPix, &mX)) != OSD_OK) return rc;
     if ((rc = make_bf16_map(ws.a1, (int64_t)n * kPix, C2, C2, kBK, kPix, &mA1)) != OSD_OK) return rc;
     if ((rc = make_roi_map_4d(ws.a2, n, C, &mA2)) != OSD_OK) return rc;
-    if ((rc = make_bf16_map(ws.a3, n, (int64_t)kPix * Ch, (int64_t)kPix * Ch, kBK, kBM, &mA3)) != OSD_OK) return rc;
-    if ((rc = make_bf16_map(ws.h6, n, mlp, mlp, kBK, kBM, &mH6)) != OSD_OK) return rc;
-    if ((rc = make_bf16_map(ws.h7, n, mlp, mlp, kBK, kBM, &mH7)) != OSD_OK) return rc;
 
     GemmArgs G{};
     G.eps = d->gn_eps; G.slope = d->lrelu_slope; G.roi0 = (int)r0; G.rois_per_image = R;
@@ -544,19 +600,27 @@ extern "C" int osd_box_head_forward(const osd_box_head_desc* d, void* workspace,
     if ((rc = launch_gn_gemm(mA1, mNone, mW2, G, stream, "box_head_conv2")) != OSD_OK) return rc;
     // feature_aggreg: 3x3 conv as an implicit GEMM over 9 shifted boxes -> GN3 -> LeakyReLU
     G.N = Ch; G.K = 9 * C; G.a_mode = A_ROI_3X3; G.tap_c = C;
-    G.bias = d->b3; G.gamma = d->gn3_w; G.beta = d->gn3_b; G.out = ws.a3; G.ldo = Ch;
+    G.bias = d->b3; G.gamma = d->gn3_w; G.beta = d->gn3_b; G.out = ws.a3 + (size_t)r0 * kPix * Ch; G.ldo = Ch;
     if ((rc = launch_gn_gemm(mA2, mNone, mW3, G, stream, "box_head_aggreg")) != OSD_OK) return rc;
-    // fc6, fc7 (+ ReLU)
-    G.a_mode = A_PLAIN; G.M = n; G.N = mlp; G.K = kPix * Ch; G.relu = 1; G.out_f32 = 0;
-    G.bias = d->b6; G.out = ws.h6; G.ldo = mlp;
-    if ((rc = launch_gemm<0, 128, 1>(mA3, mNone, mW6, G, stream, "box_head_fc6")) != OSD_OK) return rc;
-    G.K = mlp; G.bias = d->b7; G.out = ws.h7;
-    if ((rc = launch_gemm<0, 128, 1>(mH6, mNone, mW7, G, stream, "box_head_fc7")) != OSD_OK) return rc;
-    // predictor: cls_score rows then bbox_pred rows of one small GEMM, fp32 outputs in the reference's two tensors
-    G.N = npred; G.relu = 0; G.out_f32 = 1; G.bias = d->bp;
-    G.out = d->class_logits + (size_t)r0 * d->num_classes; G.ldo = d->num_classes;
-    G.out2 = d->box_regression + (size_t)r0 * d->num_box_out; G.ldo2 = d->num_box_out; G.n_split = d->num_classes;
-    if ((rc = launch_gemm<0, 16, 1>(mH7, mNone, mWp, G, stream, "box_head_predictor")) != OSD_OK) return rc;
   }
-  return OSD_OK;
+
+  // ---- the fully connected layers, once over all ROIs (full waves of 128-row tiles)
+  CUtensorMap mA3, mH6, mH7;
+  const int n = (int)n_all;
+  if ((rc = make_bf16_map(ws.a3, n, (int64_t)kPix * Ch, (int64_t)kPix * Ch, kBK, kBM, &mA3)) != OSD_OK) return rc;
+  if ((rc = make_bf16_map(ws.h6, n, mlp, mlp, kBK, kBM, &mH6)) != OSD_OK) return rc;
+  if ((rc = make_bf16_map(ws.h7, n, mlp, mlp, kBK, kBM, &mH7)) != OSD_OK) return rc;
+  GemmArgs G{};
+  G.eps = d->gn_eps; G.slope = d->lrelu_slope; G.rois_per_image = R;
+  // fc6, fc7 (+ ReLU)
+  G.a_mode = A_PLAIN; G.M = n; G.N = mlp; G.K = kPix * Ch; G.relu = 1; G.out_f32 = 0;
+  G.bias = d->b6; G.out = ws.h6; G.ldo = mlp;
+  if ((rc = launch_gemm<0, 128, 1>(mA3, mNone, mW6, G, stream, "box_head_fc6")) != OSD_OK) return rc;
+  G.K = mlp; G.bias = d->b7; G.out = ws.h7;
+  if ((rc = launch_gemm<0, 128, 1>(mH6, mNone, mW7, G, stream, "box_head_fc7")) != OSD_OK) return rc;
+  // predictor: cls_score rows then bbox_pred rows of one small GEMM, fp32 outputs in the reference's two tensors
+  G.N = npred; G.relu = 0; G.out_f32 = 1; G.bias = d->bp;
+  G.out = d->class_logits; G.ldo = d->num_classes;
+  G.out2 = d->box_regression; G.ldo2 = d->num_box_out; G.n_split = d->num_classes;
+  return launch_gemm<0, 16, 1>(mH7, mNone, mWp, G, stream, "box_head_predictor");
 }

@@ -10,6 +10,8 @@
 // contiguous 128-byte run and its taps fall into a few rows of one or two channel planes.  Every arithmetic operation
 // is an explicit _rn intrinsic in the order of ROIAlign_cpu.cpp, so fp32 results are bit-identical to the reference
 // CPU operator.
+#include <cuda_bf16.h>
+
 #include "osd_common.cuh"
 
 namespace osd {
@@ -28,6 +30,7 @@ struct RoiPoolArgs {
   float k_min, k_max, s0, lvl0, eps;
   float* out;
   int32_t* levels_out;
+  __nv_bfloat16* out_bf16;   // optional [B*R, P*P, C]: the K-major rows the dense head's GEMMs read (channels-last path)
 };
 
 struct AxisTap {
@@ -162,10 +165,14 @@ __global__ void __launch_bounds__(kPoolThreads) roi_pool_nhwc_kernel(RoiPoolArgs
   const int b = roi / A.R, r = roi - b * A.R;
   const int tid = threadIdx.x;
   const int PP = A.P * A.P, per_roi = A.C * PP;
-  float* out = A.out + (size_t)roi * per_roi;
+  float* out = A.out ? A.out + (size_t)roi * per_roi : nullptr;
+  __nv_bfloat16* outb = A.out_bf16 ? A.out_bf16 + (size_t)roi * per_roi : nullptr;
   const int n_valid = A.roi_count ? min(max(A.roi_count[b], 0), A.R) : A.R;
   if (r >= n_valid) {
-    for (int e = tid; e < per_roi; e += kPoolThreads) out[e] = 0.f;
+    for (int e = tid; e < per_roi; e += kPoolThreads) {
+      if (out) out[e] = 0.f;
+      if (outb) outb[e] = __float2bfloat16_rn(0.f);
+    }
     if (tid == 0 && A.levels_out) A.levels_out[roi] = -1;
     return;
   }
@@ -217,11 +224,22 @@ __global__ void __launch_bounds__(kPoolThreads) roi_pool_nhwc_kernel(RoiPoolArgs
       }
     }
     const int c = q << 2;
-    stage[(c + 0) * PP + bin] = __fdiv_rn(acc.x, count);
-    stage[(c + 1) * PP + bin] = __fdiv_rn(acc.y, count);
-    stage[(c + 2) * PP + bin] = __fdiv_rn(acc.z, count);
-    stage[(c + 3) * PP + bin] = __fdiv_rn(acc.w, count);
+    const float r0 = __fdiv_rn(acc.x, count), r1 = __fdiv_rn(acc.y, count), r2 = __fdiv_rn(acc.z, count), r3 = __fdiv_rn(acc.w, count);
+    if (outb) {   // [bin][channel] rows: consecutive threads write consecutive 8-byte quads of one row
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(r0, r1), hi = __floats2bfloat162_rn(r2, r3);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(outb + (size_t)bin * A.C + c) = pk;
+    }
+    if (out) {
+      stage[(c + 0) * PP + bin] = r0;
+      stage[(c + 1) * PP + bin] = r1;
+      stage[(c + 2) * PP + bin] = r2;
+      stage[(c + 3) * PP + bin] = r3;
+    }
   }
+  if (!out) return;
   __syncthreads();
   if ((per_roi & 3) == 0) {   // out + roi * per_roi is then 16-byte aligned (cudaMalloc / torch allocations are)
     float4* o4 = reinterpret_cast<float4*>(out);
@@ -264,7 +282,7 @@ extern "C" int osd_roi_pool(const osd_roi_pool_desc* d, void* stream_) {
   const int64_t n = (int64_t)d->batch * d->rois_per_image;
   if (n == 0) return OSD_OK;
   OSD_REQUIRE(n < (1ll << 31), "osd_roi_pool: too many ROIs");
-  OSD_REQUIRE(d->rois != nullptr && d->out != nullptr, "osd_roi_pool: null rois / out");
+  OSD_REQUIRE(d->rois != nullptr && (d->out != nullptr || d->out_nhwc_bf16 != nullptr), "osd_roi_pool: null rois / out");
   OSD_REQUIRE((reinterpret_cast<uintptr_t>(d->rois) & 15) == 0, "osd_roi_pool: rois must be 16-byte aligned");
   RoiPoolArgs A{};
   A.nl = d->num_levels; A.B = d->batch; A.R = d->rois_per_image; A.C = d->channels; A.P = d->pooled_size;
@@ -281,11 +299,14 @@ extern "C" int osd_roi_pool(const osd_roi_pool_desc* d, void* stream_) {
   A.s0 = d->canonical_scale; A.lvl0 = (float)d->canonical_level; A.eps = d->eps;
   A.out = d->out;
   A.levels_out = d->levels_out;
+  A.out_bf16 = static_cast<__nv_bfloat16*>(d->out_nhwc_bf16);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t stage_bytes = (size_t)d->channels * d->pooled_size * d->pooled_size * sizeof(float);
   const bool channels_last = d->workspace != nullptr && (d->channels & 3) == 0 && stage_bytes <= 200 * 1024 &&
                              (reinterpret_cast<uintptr_t>(d->out) & 15) == 0;
   if (!channels_last) {  // direct NCHW taps (any C, no workspace)
+    OSD_REQUIRE(d->out_nhwc_bf16 == nullptr && d->out != nullptr,
+                "osd_roi_pool: the bf16 [roi, pixel, channel] output needs the channels-last path (workspace, C %% 4 == 0)");
     roi_pool_kernel<<<(unsigned)n, kPoolThreads, 0, stream>>>(A);
     OSD_LAUNCH_CHECK("roi_pool_kernel");
     return OSD_OK;

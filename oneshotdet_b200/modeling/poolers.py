@@ -20,11 +20,13 @@ _workspace = _lib.Workspace()
 @torch.no_grad()
 def roi_pool(features, rois, scales, output_size: int = 7, sampling_ratio: int = 2, roi_count=None,
              canonical_scale: float = 224.0, canonical_level: int = 4, eps: float = 1e-6, return_levels: bool = False,
-             channels_last: bool = True):
+             channels_last: bool = True, rows_bf16: bool = False):
     """features[l] [B,C,H_l,W_l] fp32 CUDA (NCHW); rois [B,R,4] xyxy (image coordinates; ROI (b, r) reads image b);
     scales[l] per level.  Returns [B*R, C, P, P] (and the int32 level of every ROI when ``return_levels``).
     ``channels_last`` (default, needs C % 4 == 0): the library first transposes the maps to [B, H*W, C] in a scratch
-    buffer so that every bilinear tap is one contiguous channel vector; False pools straight from NCHW.  Same bits."""
+    buffer so that every bilinear tap is one contiguous channel vector; False pools straight from NCHW.  Same bits.
+    ``rows_bf16``: return bf16 [B*R, P*P, C] instead -- the same values rounded once to bf16 in the K-major row layout
+    the dense head's GEMMs read (``BoxHeadDense``), skipping the fp32 [B*R,C,P,P] tensor altogether."""
     lib = _lib.load()
     nl = len(features)
     if nl == 0 or nl > OSD_MAX_LEVELS or len(scales) != nl:
@@ -52,14 +54,23 @@ def roi_pool(features, rois, scales, output_size: int = 7, sampling_ratio: int =
         keep.append(f)
         d.height[l], d.width[l], d.spatial_scale[l], d.feat[l] = f.shape[2], f.shape[3], float(scales[l]), f.data_ptr()
     rois = rois.contiguous()
-    out = torch.empty((b * r, c, d.pooled_size, d.pooled_size), dtype=torch.float32, device=dev)
+    if rows_bf16:
+        if not (channels_last and c % 4 == 0):
+            raise OsdError("roi_pool: rows_bf16 needs the channels-last path (C % 4 == 0)")
+        out = torch.empty((b * r, d.pooled_size * d.pooled_size, c), dtype=torch.bfloat16, device=dev)
+    else:
+        out = torch.empty((b * r, c, d.pooled_size, d.pooled_size), dtype=torch.float32, device=dev)
     levels = torch.empty((b * r,), dtype=torch.int32, device=dev) if return_levels else None
     if roi_count is not None:
         if roi_count.dtype != torch.int32 or roi_count.device != dev or roi_count.numel() != b:
             raise OsdError("roi_pool: roi_count must be an int32 vector [B] on the inputs' device")
         roi_count = roi_count.contiguous()
         d.roi_count = roi_count.data_ptr()
-    d.rois, d.out = rois.data_ptr(), out.data_ptr()
+    d.rois = rois.data_ptr()
+    if rows_bf16:
+        d.out, d.out_nhwc_bf16 = None, out.data_ptr()
+    else:
+        d.out = out.data_ptr()
     d.levels_out = levels.data_ptr() if levels is not None else None
     if channels_last and c % 4 == 0 and b * r > 0:  # pool from a channels-last copy of the maps made by the library
         need = ctypes.c_size_t(0)
@@ -96,12 +107,13 @@ class Pooler(nn.Module):
         lvl_max = -math.log2(self.scales[-1])
         self.map_levels = LevelMapper(lvl_min, lvl_max)
 
-    def forward_fixed(self, x, rois, roi_count=None):
-        """rois [B,R,4] device tensor (e.g. the FCOS stage's padded output and its counts) -> [B,R,C,P,P]; no host sync."""
+    def forward_fixed(self, x, rois, roi_count=None, rows_bf16: bool = False):
+        """rois [B,R,4] device tensor (e.g. the FCOS stage's padded output and its counts) -> [B,R,C,P,P]; no host sync.
+        ``rows_bf16``: bf16 [B,R,P*P,C] for ``BoxHeadDense`` instead (see ``roi_pool``)."""
         m = self.map_levels
         out = roi_pool(list(x), rois, self.scales[:len(x)], self.output_size[0], self.sampling_ratio, roi_count,
-                       m.s0, m.lvl0, m.eps)
-        return out.view(rois.size(0), rois.size(1), out.size(1), out.size(2), out.size(3))
+                       m.s0, m.lvl0, m.eps, rows_bf16=rows_bf16)
+        return out.view(rois.size(0), rois.size(1), out.size(1), out.size(2), *out.shape[3:])
 
     def forward(self, x, boxes):
         """poolers.py:93-125: ``boxes`` is a list of BoxList with equal lengths (:79); returns [bs, R, C, P, P] for several

@@ -92,6 +92,7 @@ class BoxHeadDense(nn.Module):
         self.fc7 = nn.Linear(mlp_dim, mlp_dim)
         self.predictor = FPNPredictor(mlp_dim, num_classes, 2)
         self._packed = None
+        self._ws = None     # grow-only scratch of the kernels (single-stream use, like PreparedFusion)
 
     def packed(self, device) -> PackedBoxHeadWeights:
         key = (str(device), tuple(p._version for p in self.parameters()), tuple(p.data_ptr() for p in self.parameters()))
@@ -101,12 +102,16 @@ class BoxHeadDense(nn.Module):
 
     @torch.no_grad()
     def forward(self, pooled, features_supp_roipooled, batch_size: int | None = None):
-        if pooled.dim() == 5:
+        """``pooled``: fp32 [B,R,C,7,7] / [B*R,C,7,7] (the reference layout), or bf16 [B,R,49,C] / [B*R,49,C] as
+        ``Pooler.forward_fixed(..., rows_bf16=True)`` writes it (no repacking pass)."""
+        rows = pooled.dtype == torch.bfloat16
+        lead = 2 if pooled.dim() == (4 if rows else 5) else 1
+        if lead == 2:
             b, r = pooled.shape[:2]
             pooled = pooled.reshape(b * r, *pooled.shape[2:])
         else:
             if batch_size is None:
-                raise OsdError("box head: a 4-D pooled tensor needs batch_size")
+                raise OsdError("box head: a pooled tensor without the [B, R] leading dimensions needs batch_size")
             b = int(batch_size)
             if pooled.size(0) % b != 0:
                 raise OsdError("box head: rows of pooled must be a multiple of the batch size")
@@ -118,8 +123,11 @@ class BoxHeadDense(nn.Module):
         supp = features_supp_roipooled
         if supp.numel() != b * c * p * p:
             raise OsdError(f"box head: one support of [C={c},{p},{p}] per episode expected (box_head.py:120), got {tuple(supp.shape)}")
-        if tuple(pooled.shape[1:]) != (c, p, p) or pooled.dtype != torch.float32 or supp.dtype != torch.float32 or supp.device != dev:
-            raise OsdError(f"box head: pooled must be [B*R,{c},{p},{p}] float32 and the support on the same device")
+        want = (p * p, c) if rows else (c, p, p)
+        if tuple(pooled.shape[1:]) != want or pooled.dtype not in (torch.float32, torch.bfloat16) or \
+                supp.dtype != torch.float32 or supp.device != dev:
+            raise OsdError(f"box head: pooled must be [B*R,{c},{p},{p}] float32 or [B*R,{p * p},{c}] bfloat16, the support float32 "
+                           "on the same device")
         pooled, supp = pooled.contiguous(), supp.reshape(b, c, p, p).contiguous()
         n = b * r
         logits = torch.empty((n, w.num_classes), dtype=torch.float32, device=dev)
@@ -128,7 +136,11 @@ class BoxHeadDense(nn.Module):
         d.batch, d.rois_per_image, d.channels, d.pooled_size = b, r, c, p
         d.mlp_dim, d.num_classes, d.num_box_out, d.roi_chunk = w.mlp, w.num_classes, w.num_box_out, int(self.roi_chunk)
         d.gn_eps, d.lrelu_slope = w.eps, w.slope
-        d.pooled, d.supp = pooled.data_ptr(), supp.data_ptr()
+        if rows:
+            d.pooled, d.pooled_nhwc_bf16 = None, pooled.data_ptr()
+        else:
+            d.pooled = pooled.data_ptr()
+        d.supp = supp.data_ptr()
         d.w1, d.b1, d.gn1_w, d.gn1_b = w.w1.data_ptr(), w.b1.data_ptr(), w.g1w.data_ptr(), w.g1b.data_ptr()
         d.w2, d.b2, d.gn2_w, d.gn2_b = w.w2.data_ptr(), w.b2.data_ptr(), w.g2w.data_ptr(), w.g2b.data_ptr()
         d.w3, d.b3, d.gn3_w, d.gn3_b = w.w3.data_ptr(), w.b3.data_ptr(), w.g3w.data_ptr(), w.g3b.data_ptr()
@@ -138,7 +150,9 @@ class BoxHeadDense(nn.Module):
         lib = _lib.load()
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.osd_box_head_workspace_bytes(ctypes.byref(d), ctypes.byref(nbytes)), "osd_box_head_workspace_bytes")
-        ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=dev)
+        ws = self._ws
+        if ws is None or ws.numel() < nbytes.value or ws.device != dev:
+            ws = self._ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = lib.osd_box_head_forward(ctypes.byref(d), ws.data_ptr(), ws.numel(), _lib.current_stream_ptr(dev))
         _lib.check(rc, "osd_box_head_forward")

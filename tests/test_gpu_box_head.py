@@ -155,3 +155,27 @@ def test_dense_head_layers_against_bf16_emulation(c, mlp, b, r, chunk):
     assert rel_err(reg.cpu(), er) <= 1e-2, rel_err(reg.cpu(), er)
     fl, fr = orc.box_head_dense(pooled, supp, mods)
     assert rel_err(logits.cpu(), fl) <= 3e-2 and rel_err(reg.cpu(), fr) <= 3e-2
+
+
+def test_pooler_bf16_rows_feed_the_dense_head(golden_dir):
+    """Pooler(rows_bf16=True) writes the pooled features once, as bf16 [B,R,49,C] rows: the fp32 result rounded to bf16
+    and transposed, bit for bit; the dense head on them equals the dense head on the fp32 tensor (same rounding, same
+    GEMMs) exactly."""
+    import oneshotdet_b200 as osd
+
+    z, mods = load(golden_dir)
+    b, c, h, w = int(z["batch"]), int(z["channels"]), int(z["height"]), int(z["width"])
+    feats, _ = orc.synth_features(b, 1, c, h, w, int(z["seed"]))
+    rois = torch.from_numpy(z["boxes"]).to(DEV)
+    pooler = osd.Pooler((7, 7), [1 / s for s in orc.FPN_STRIDES], 2)
+    fx = [f.to(DEV) for f in feats]
+    rows = pooler.forward_fixed(fx, rois, rows_bf16=True)
+    full = pooler.forward_fixed(fx, rois)
+    assert rows.dtype == torch.bfloat16 and tuple(rows.shape) == (b, rois.size(1), 49, c)
+    want = full.reshape(b, rois.size(1), c, 49).permute(0, 1, 3, 2).bfloat16()
+    assert torch.equal(rows, want)
+    head = gpu_head(mods, c, int(z["w_fc7.weight"].shape[0]))
+    supp = torch.from_numpy(z["supp"]).to(DEV)
+    l0, r0 = head(full, supp)
+    l1, r1 = head(rows, supp)
+    assert torch.equal(l0, l1) and torch.equal(r0, r1)
