@@ -10,7 +10,8 @@ launch), then score -> per-level top-k -> decode/clip -> batched NMS -> post-NMS
 stages is outside the path: head outputs are synthetic and resident.  With N > 1 every rank
 owns its episodes (weak scaling) and every step's detections (the post-processing stage's result block) are pushed to
 all ranks over NVLink peer memory on the copy engines (--gather peer; --gather block: one asynchronous NCCL all-gather
-per step); one NCCL all-gather of the final step's block closes the timed region and is checked against the pushed copy.
+per step); the timed region ends when the launching stream has waited for every exchange this rank issued.  One NCCL
+all-gather of the final step's block afterwards is the checker of the pushed copy.
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same metric through the public
 host-buffer API (H2D of all inputs + D2H of the detections inside the timed region), `roofline` describes the dominant
@@ -78,9 +79,38 @@ def config_dict(n_gpus, name="config2", gather=None):
             "cache": "inputs larger than L2 (features in + out per step >= 734 MB vs 126 MB L2)"}
 
 
+class StreamRunner:
+    """K steps as three self-ordered streams (EpisodePipeline.capture_streams): matching launches back to back on one,
+    the post-processing chains of consecutive batches alternating between two more; no join between steps.
+    ``before(1)`` / ``after([res])`` are called in the stream context of the step's chain."""
+
+    def __init__(self, pipe):
+        self.pipe, self.depth, self.launch = pipe, 1, "cuda-graphs (1 matching + 1 chain per step) on 3 streams"
+        self.steps = pipe.capture_streams()
+
+    def run(self, k, before=None, after=None, mark=None):
+        import torch
+
+        self.steps.begin()
+        last = None
+        for _ in range(k):
+            with torch.cuda.stream(self.steps.next_stream()):
+                if before is not None:
+                    before(1)
+            last, s = self.steps.step()
+            if after is not None:
+                with torch.cuda.stream(s):
+                    after([last])
+        self.steps.join()
+        if mark is not None:
+            mark(k)
+        return last
+
+
 # ------------------------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md section 8(d)): features ~ N(0,1); cls ~ N(-4, 2^2); ctr ~ N(0,1); reg = exp(N(log 4s, .5^2));
-# "clustered": reg = 4s exactly (identical box shapes per level -> heavy suppression, the early exit cannot hit)
+# "clustered": reg = 12s exactly (identical box shapes per level, 24 strides wide: IoU with the neighbours one and two
+# locations away is 0.92 / 0.85 > the 0.8 threshold -> heavy suppression, the early exit cannot hit)
 # ------------------------------------------------------------------------------------------------------
 def fill_inputs(pipe, seed, heads="spread"):
     import torch
@@ -94,7 +124,7 @@ def fill_inputs(pipe, seed, heads="spread"):
         t.normal_(generator=g)
     for t, s in zip(pipe.reg, pipe.strides):
         if heads == "clustered":
-            t.fill_(4.0 * s)
+            t.fill_(12.0 * s)     # boxes of 24 strides: neighbours up to two locations away overlap above IoU 0.8
         else:
             t.normal_(mean=math.log(4.0 * s), std=0.5, generator=g).exp_()
 
@@ -536,10 +566,14 @@ def run_b200_arm(args):
     # steps in flight: the post-processing chains of `depth` consecutive steps run side by side under `depth` matching
     # launches (one chain alone takes longer than one matching launch).  The NCCL block gather has two slots: depth 1.
     depth = 1 if (args.serial or (world > 1 and args.gather in ("block", "packed"))) else max(1, args.depth)
-    pipe = make_pipe(name, dev, double_buffer=(world > 1 and block_mode), depth=depth)
+    # --pipeline streams: no per-step graph; three streams that never join between steps (two chains in flight)
+    streamed = args.pipeline == "streams" and not args.serial and not args.no_graph and not (world > 1 and args.gather == "packed")
+    if streamed:
+        depth = 1
+    pipe = make_pipe(name, dev, double_buffer=(world > 1 and block_mode), depth=2 if streamed else depth)
     fill_inputs(pipe, seed=2000 + rank, heads=wl["heads"])
     ep_off = rank * batch
-    runner = StepRunner(pipe, depth, overlap=overlap, use_graph=not args.no_graph)
+    runner = StreamRunner(pipe) if streamed else StepRunner(pipe, depth, overlap=overlap, use_graph=not args.no_graph)
     launch = runner.launch
 
     # N > 1: the step's detections go to every rank.  "peer" (default): the result block of a step (one contiguous
@@ -551,7 +585,7 @@ def run_b200_arm(args):
     K = pipe.post.plan.out_capacity
     if world > 1 and args.gather != "none":
         if args.gather in ("peer", "peer-kernel"):
-            gatherer = PeerBlockGatherer(batch, K, dev, slots=2 * depth, mode="copy" if args.gather == "peer" else "kernel")
+            gatherer = PeerBlockGatherer(batch, K, dev, slots=len(pipe.posts), mode="copy" if args.gather == "peer" else "kernel")
         elif args.gather == "block":
             gatherer = BlockGatherer(batch, K, dev)
         else:
@@ -562,8 +596,8 @@ def run_b200_arm(args):
         # the 2 x depth output sets in submission order (the previous replay's pushes may stay in flight); a remainder
         # step uses the one-step graphs' own rotation, so it waits for everything.
         if gatherer is not None and block_mode:
-            if args.gather == "block":
-                gatherer.acquire(n)
+            if args.gather == "block" or streamed:
+                gatherer.acquire(n)    # streamed: output sets rotate in submission order, slots - 1 pushes may stay in flight
             else:
                 gatherer.acquire(n, in_flight=(depth if n == depth else 0))
 
@@ -586,17 +620,24 @@ def run_b200_arm(args):
     torch.cuda.synchronize()
     launches_per_step = ops.launch_count()
     # isolated stage times (serial, one stream): the roofline of the matching kernel and the post-processing chain
-    iso = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    iso_match, iso_post = [], []
-    for _ in range(max(3, min(args.steps, 10))):
-        iso[0].record()
+    # (each stage launched back to back n times between two events on the launching stream: a device that idles between
+    # single launches -- a host synchronisation after every one -- runs the first microseconds of the next kernel slower)
+    iso = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    n_iso = max(5, min(args.steps, 20))
+    pipe.match()
+    pipe.post()
+    iso[0].record()
+    for _ in range(n_iso):
         pipe.match()
-        iso[1].record()
+    iso[1].record()
+    torch.cuda.synchronize()
+    iso[2].record()
+    for _ in range(n_iso):
         pipe.post()
-        iso[2].record()
-        torch.cuda.synchronize()
-        iso_match.append(iso[0].elapsed_time(iso[1]))
-        iso_post.append(iso[1].elapsed_time(iso[2]))
+    iso[3].record()
+    torch.cuda.synchronize()
+    iso_match = [iso[0].elapsed_time(iso[1]) / n_iso]
+    iso_post = [iso[2].elapsed_time(iso[3]) / n_iso]
     kept = res.kept_before_cut().cpu().tolist()
     counts = res.count.cpu().tolist()
 
@@ -616,19 +657,27 @@ def run_b200_arm(args):
     ev[0].record()
     res = runner.run(steps, before, after, mark=lambda done: ev[done].record())
     if gatherer is not None:
-        gatherer.finish()     # the last exchanges are inside the timed region
-        if final_gather is not None:
-            # north_star's "final NCCL all-gather of detections": the last step's block, once, through NCCL
-            dist.all_gather_into_tensor(final_gather.view(-1), res.block)
+        # the last exchanges are inside the timed region: the launching stream waits (on the device) for every push /
+        # collective this rank has issued; no host synchronisation and no rendezvous before the end event
+        (gatherer.drain if hasattr(gatherer, "drain") else gatherer.finish)()
     ev[steps + 1].record()
     torch.cuda.synchronize()
     t_host1 = time.perf_counter()
     if world > 1:
         dist.barrier()
+    if gatherer is not None:
+        gatherer.finish()     # every rank's pushes have landed everywhere (process-group barrier)
+        if final_gather is not None:
+            # north_star's "final NCCL all-gather of detections": the last step's block, once, through NCCL -- the checker
+            # of the pushed copy below (outside the timed region: it is not part of a step)
+            dist.all_gather_into_tensor(final_gather.view(-1), res.block)
+            torch.cuda.synchronize()
     clocks = sampler.stop()
     launches = launches_per_step * steps
     total_ms = ev[0].elapsed_time(ev[steps + 1])
     marks = [0] + [i for i in range(1, steps + 1) if (i % depth == 0 and i <= steps // depth * depth) or i > steps // depth * depth]
+    if streamed:
+        marks = [0, steps]     # steps overlap: there is no per-step boundary to mark
     per_step = [ev[a].elapsed_time(ev[b]) / (b - a) for a, b in zip(marks, marks[1:])]
     t = torch.tensor([total_ms, statistics.median(per_step)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -660,13 +709,15 @@ def run_b200_arm(args):
     roofline = {"kernel": "match_product_bulk_kernel<float>", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
                 "algorithmic_bytes_per_launch": match_bytes, "avg_launch_ms": match_avg_ms, "peak_source": peak_src,
-                "timing": "CUDA events around the kernel on its launching stream, kernel running alone (serial loop "
-                          "right before the timed region); inside the timed region it overlaps the post-processing chain",
+                "timing": "CUDA events on the launching stream around n back-to-back launches of the kernel running alone, "
+                          "right before the timed region; inside the timed region it overlaps the post-processing chain",
                 "share_of_serial_step": match_avg_ms / (match_avg_ms + statistics.mean(iso_post))}
     stages = {"match_ms_isolated": match_avg_ms, "post_ms_isolated": statistics.mean(iso_post),
               "serial_ms_per_step": match_avg_ms + statistics.mean(iso_post),
-              "overlap": (f"match || post-processing on {1 + depth} streams, {depth} step(s) in flight per graph replay "
-                          "(software pipelining)") if overlap else "none (one stream)",
+              "overlap": ("matching launches back to back on one stream || the post-processing chains of consecutive steps "
+                          "alternating between two more streams, no join between steps (software pipelining across steps)")
+              if streamed else (f"match || post-processing on {1 + depth} streams, {depth} step(s) in flight per graph "
+                                "replay (software pipelining)") if overlap else "none (one stream)",
               "steps_in_flight": depth, "launch": launch, "post_algorithmic_read_bytes": 6 * 4 * locs * batch,
               "host_ms_per_step": 1e3 * (t_host1 - t_host0) / steps}
 
@@ -817,6 +868,9 @@ def main():
     ap.add_argument("--no-fusion", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end measurement (diagnosis runs)")
     ap.add_argument("--serial", action="store_true", help="one stream: matching then post-processing, no overlap")
+    ap.add_argument("--pipeline", choices=["streams", "graph"], default="streams",
+                    help="streams: matching and the post-processing chains of consecutive steps on three self-ordered streams "
+                         "(two chains in flight); graph: one CUDA graph per step (match || chain), steps serialised")
     ap.add_argument("--depth", type=int, default=1,
                     help="consecutive steps issued per graph replay, their post-processing chains side by side (1: one step)")
     ap.add_argument("--gather", choices=["peer", "peer-kernel", "block", "packed", "none"], default="peer",

@@ -213,6 +213,9 @@ typedef struct {
   const float* b2;       /* device fp32 [C] */
   const float* gn2_w;    /* device fp32 [C] */
   const float* gn2_b;
+  const float* w1x_gram; /* optional device fp32 [32, C, C]: M_g = sum over the channels c of GroupNorm-1 group g of
+                            w_c w_c^T, w_c = row c of w1x_bf16 (as fp32).  With it (C >= 128) pass A takes the GroupNorm-1
+                            statistics from a Gram GEMM of the activations with themselves instead of running conv1 */
 } osd_fusion_desc;
 
 int osd_fusion_workspace_bytes(const osd_fusion_desc* desc, size_t* bytes);

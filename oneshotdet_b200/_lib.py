@@ -67,7 +67,8 @@ class FusionDesc(ctypes.Structure):
                 ("out", ctypes.c_void_p * OSD_MAX_LEVELS),
                 ("w1x_bf16", ctypes.c_void_p), ("w1s_t", ctypes.c_void_p), ("b1", ctypes.c_void_p),
                 ("gn1_w", ctypes.c_void_p), ("gn1_b", ctypes.c_void_p), ("w2_bf16", ctypes.c_void_p),
-                ("b2", ctypes.c_void_p), ("gn2_w", ctypes.c_void_p), ("gn2_b", ctypes.c_void_p)]
+                ("b2", ctypes.c_void_p), ("gn2_w", ctypes.c_void_p), ("gn2_b", ctypes.c_void_p),
+                ("w1x_gram", ctypes.c_void_p)]
 
 
 class SupportPoolDesc(ctypes.Structure):

@@ -29,6 +29,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "fusion_internal.cuh"
@@ -51,11 +52,10 @@ __host__ __device__ constexpr uint32_t stage_bytes(int bn) { return kABytes + (u
 __host__ __device__ constexpr int ring_depth(int bn) {
   return (int)(kRingBytes / stage_bytes(bn)) < kMaxRing ? (int)(kRingBytes / stage_bytes(bn)) : kMaxRing;
 }
-constexpr int kEpiWarps = 8;
-constexpr int kGemmThreads = 32 * (kEpiWarps + 2);
+constexpr int kMaxEpiWarps = 16;
 constexpr int kMaxParamCols = 2048;            // bias / gamma / beta of up to this many output columns are staged in smem
-constexpr uint32_t kXchBytes = 2 * kEpiWarps * 32 * 4;          // statistics exchange between the two warps of an ROI
-constexpr uint32_t kCoefBytes = 2 * 2 * 2 * 128 * 8;            // (scale, shift) [tile parity][ROI][column half][128]
+constexpr uint32_t kXchBytes = 2 * kMaxEpiWarps * 32 * 4;       // statistics exchange between the two warps of an ROI
+constexpr uint32_t kCoefBytes = 2 * 2 * 256 * 8;                // (scale, shift) [tile parity][ROI][N tile column]
 constexpr uint32_t kParamBytes = kMaxParamCols * 4 + 2 * 512 * 4;   // bias [2048], gamma [512], beta [512]
 constexpr uint32_t kGemmSmem = kRingBytes + 256 /* barriers */ + kXchBytes + kCoefBytes + kParamBytes + 1024 /* align */;
 
@@ -122,12 +122,23 @@ __device__ __forceinline__ void store_bf16_row(__nv_bfloat16* dst, const uint32_
 }
 
 // EPI 0: bias (+ ReLU) -> bf16 / fp32 rows.  EPI 1: bias + GroupNorm(32 groups of GS channels, over the 49 rows of the
-// ROI) + LeakyReLU -> bf16 rows.  CPW = columns per epilogue warp (the N tile is 2 * CPW).
-template <int EPI, int CPW, int GS>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// ROI) + LeakyReLU -> bf16 rows.  The N tile is split into NH column parts of CPW columns; 4 * NH epilogue warps (TMEM
+// lane quadrant x column part) drain an accumulator -- 16 warps on the wide layers: with 8 the epilogue issued at 0.3
+// instructions per cycle and scheduler (two warps each, a chain of TMEM loads, shuffles and shared-memory reads) and was
+// what bound conv1 / conv2.
+// CL = 2: launched as clusters of two CTAs that work on two M tiles of the SAME N tile in lock step; every W stage is
+// fetched from L2 once per cluster (each CTA loads half of its rows and the TMA unit multicasts them into both CTAs'
+// rings).  The ROI layers stream the whole weight matrix per M tile and are bound by that L2 -> SM stream.
+template <int EPI, int CPW, int GS, int NH, int CL>
+__global__ void __launch_bounds__(32 * (4 * NH + 2), 1)
 roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                 const __grid_constant__ CUtensorMap mapW, const GemmArgs G) {
-  constexpr int BN = 2 * CPW;
+  constexpr int BN = NH * CPW;
+  constexpr int kEpiWarps = 4 * NH;
+  static_assert(CL == 1 || CL == 2, "cluster size");
+  const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
+  const int cta = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // tile-loop index of this CTA (pair)
+  const int ncta = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int LD = CPW >= 32 ? 32 : 16;
   static_assert(BN <= 256 && BN % 16 == 0, "N tile");
   constexpr int kRing = ring_depth(BN);
@@ -148,16 +159,19 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
   const int m_tiles = G.a_mode == A_PLAIN ? (G.M + kBM - 1) / kBM : (G.M + 1) / 2;
   const int n_tiles = (G.N + BN - 1) / BN;
-  const int total = m_tiles * n_tiles;
+  // pairs: tile t of the loop = (pair of M tiles t / n_tiles, N tile t % n_tiles); rank r takes M tile 2 * pair + r (past
+  // the last M tile: a dummy whose loads are out of range = zero-filled and whose rows are all invalid)
+  const int total = ((m_tiles + CL - 1) / CL) * n_tiles;
   const int num_k = (G.K + kBK - 1) / kBK;
 
+  if (CL == 2) cluster_sync_all();
   if (warp == kEpiWarps && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapW);
     if (G.a_mode == A_ROI && G.k_split < G.K) tma_prefetch_desc(&mapA2);
     for (int s = 0; s < kRing; ++s) {
       mbar_init(b_full + 8u * s, 1);
-      mbar_init(b_empty + 8u * s, 1);
+      mbar_init(b_empty + 8u * s, CL);      // pairs: the MMA commits of both CTAs (the stage is refilled in both)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(b_accf + 8u * a, 1);
@@ -167,7 +181,8 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   }
   if (warp == kEpiWarps + 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
-  __syncthreads();
+  if (CL == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
@@ -176,8 +191,8 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (lane == 0) {
       uint32_t c = 0;
       const uint32_t a_bytes = G.a_mode == A_PLAIN ? kABytes : 2u * kPix * 128u;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      for (int tile = cta; tile < total; tile += ncta) {
+        const int mt = (tile / n_tiles) * CL + (int)crank, nt = tile % n_tiles;
         for (int k = 0; k < num_k; ++k, ++c) {
           const uint32_t s = c % kRing, ph = (c / kRing) & 1u;
           mbar_wait(b_empty + 8u * s, ph ^ 1u);
@@ -200,7 +215,17 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
               }
             }
           }
-          tma_load_2d(sB, &mapW, k0, nt * BN, fb);
+          if (CL == 2)
+            tma_load_2d_mc(sB + crank * (uint32_t)(BN / 2) * 128u, &mapW, k0, nt * BN + (int)crank * (BN / 2), fb, (uint16_t)3);
+          else
+            tma_load_2d(sB, &mapW, k0, nt * BN, fb);
+        }
+      }
+      if (CL == 2) {   // the peer's last commits must have landed on this CTA's barriers before it may exit
+        for (uint32_t s = 0; s < (uint32_t)kRing; ++s) {
+          if (c <= s) continue;
+          const uint32_t uses = (c - s + kRing - 1) / kRing;
+          mbar_wait(b_empty + 8u * s, (uses - 1) & 1u);
         }
       }
     }
@@ -208,7 +233,7 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc_ex(kBM, BN, /*a_mn=*/0, /*b_mn=*/0);
     uint32_t c = 0, it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    for (int tile = cta; tile < total; tile += ncta, ++it) {
       const uint32_t acc = it & 1u;
       mbar_wait(b_acce + 8u * acc, ((it >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator
       tc_fence_after();
@@ -223,7 +248,8 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
           for (int k16 = 0; k16 < kBK / 16; ++k16)
             umma_bf16(d, ad + (uint64_t)(k16 * 2), bd + (uint64_t)(k16 * 2), idesc, (k | k16) != 0 ? 1u : 0u);
-          umma_commit(b_empty + 8u * s);
+          if (CL == 2) umma_commit_mc(b_empty + 8u * s, (uint16_t)3);
+          else umma_commit(b_empty + 8u * s);
         }
         __syncwarp();
       }
@@ -247,10 +273,10 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
       }
     }
-    named_bar_sync(5, 32 * kEpiWarps);
+    named_bar_sync(9, 32 * kEpiWarps);
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+    for (int tile = cta; tile < total; tile += ncta, ++it) {
+      const int mt = (tile / n_tiles) * CL + (int)crank, nt = tile % n_tiles;
       const uint32_t acc = it & 1u;
       const int col0 = nt * BN + hh * CPW;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(hh * CPW);
@@ -306,7 +332,7 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const float rstd = 1.0f / sqrtf(var + G.eps);          // lanes 2g, 2g+1: statistics of group g
         // ---- coefficient table of this (ROI, column half): y_out = d * scale + shift, computed once per column by the
         //      64 threads of the warp pair instead of once per element by every row
-        float2* ctab = coef + (((it & 1u) * 2 + rloc) * 2 + hh) * 128;     // [parity][roi][half][128 columns]
+        float2* ctab = coef + (((it & 1u) * 2 + rloc) * NH + hh) * CPW;    // [parity][roi][part][CPW columns]
 #pragma unroll
         for (int u = 0; u < (CPW + 63) / 64; ++u) {
           const int cl = (q & 1) * 32 + lane + 64 * u;          // column inside this warp pair's half
@@ -398,7 +424,8 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL == 2) cluster_sync_all();
+  else __syncthreads();
   if (warp == kEpiWarps + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -442,18 +469,47 @@ int make_roi_map_4d(const void* base, int64_t rois, int C, CUtensorMap* map) {
   return OSD_OK;
 }
 
-template <int EPI, int CPW, int GS>
+// OSD_BOX_HEAD_CLUSTER=2 launches clusters of two CTAs that share every weight stage through TMA multicast.  Measured
+// (C = 256, 32 000 ROIs): 6.07 ms against 5.88 ms for single CTAs -- the weight stream is not what binds these layers.
+bool head_pairs() {
+  static const bool on = [] { const char* e = getenv("OSD_BOX_HEAD_CLUSTER"); return e && e[0] == '2'; }();
+  return on;
+}
+
+template <int EPI, int CPW, int GS, int NH>
 int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mW, const GemmArgs& G, cudaStream_t stream,
-                const char* name) {
-  auto k = roi_gemm_kernel<EPI, CPW, GS>;
-  int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(k), kGemmSmem);
-  if (rc != OSD_OK) return rc;
-  constexpr int BN = 2 * CPW;
+                const char* name, bool pairs) {
+  constexpr int BN = NH * CPW;
+  constexpr int kGemmThreads = 32 * (4 * NH + 2);
   const int m_tiles = G.a_mode == A_PLAIN ? (G.M + kBM - 1) / kBM : (G.M + 1) / 2;
   const int n_tiles = (G.N + BN - 1) / BN;
-  const int total = m_tiles * n_tiles;
-  if (total <= 0) return OSD_OK;
-  k<<<std::min(total, kNumSMs), kGemmThreads, kGemmSmem, stream>>>(mA, mA2, mW, G);
+  if (m_tiles * n_tiles <= 0) return OSD_OK;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3((unsigned)kGemmThreads);
+  cfg.dynamicSmemBytes = kGemmSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (pairs) {
+    auto k = roi_gemm_kernel<EPI, CPW, GS, NH, 2>;
+    int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(k), kGemmSmem);
+    if (rc != OSD_OK) return rc;
+    const int total = ((m_tiles + 1) / 2) * n_tiles;
+    attr[0].val.clusterDim.x = 2;
+    cfg.gridDim = dim3((unsigned)(2 * std::min(total, kNumSMs / 2)));
+    OSD_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mA2, mW, G));
+  } else {
+    auto k = roi_gemm_kernel<EPI, CPW, GS, NH, 1>;
+    int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(k), kGemmSmem);
+    if (rc != OSD_OK) return rc;
+    attr[0].val.clusterDim.x = 1;
+    cfg.gridDim = dim3((unsigned)std::min(m_tiles * n_tiles, kNumSMs));
+    OSD_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mA2, mW, G));
+  }
   OSD_LAUNCH_CHECK(name);
   timeline_mark(name, stream);
   return OSD_OK;
@@ -461,13 +517,15 @@ int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap
 
 // GroupNorm(32, N) layers: N channels -> GS = N / 32 per group, CPW = min(128, N / 2) columns per epilogue warp
 int launch_gn_gemm(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mW, const GemmArgs& G, cudaStream_t stream,
-                   const char* name) {
+                   const char* name, bool pairs) {
   switch (G.N) {
-    case 512: return launch_gemm<1, 128, 16>(mA, mA2, mW, G, stream, name);
-    case 256: return launch_gemm<1, 128, 8>(mA, mA2, mW, G, stream, name);
-    case 128: return launch_gemm<1, 64, 4>(mA, mA2, mW, G, stream, name);
-    case 64: return launch_gemm<1, 32, 2>(mA, mA2, mW, G, stream, name);
-    case 32: return launch_gemm<1, 16, 1>(mA, mA2, mW, G, stream, name);
+    // (16 epilogue warps -- <1, 64, 16, 4> etc. -- measured no faster than 8: the layers are bound by the L2 -> SM
+    // operand stream, not by the epilogue's issue rate; section 8.1 of DESIGN.md)
+    case 512: return launch_gemm<1, 128, 16, 2>(mA, mA2, mW, G, stream, name, pairs);
+    case 256: return launch_gemm<1, 128, 8, 2>(mA, mA2, mW, G, stream, name, pairs);
+    case 128: return launch_gemm<1, 64, 4, 2>(mA, mA2, mW, G, stream, name, pairs);
+    case 64: return launch_gemm<1, 32, 2, 2>(mA, mA2, mW, G, stream, name, pairs);
+    case 32: return launch_gemm<1, 16, 1, 2>(mA, mA2, mW, G, stream, name, pairs);
   }
   set_error("osd_box_head: no GroupNorm epilogue for %d channels", G.N);
   return OSD_ERR_INVALID;
@@ -565,12 +623,15 @@ extern "C" int osd_box_head_forward(const osd_box_head_desc* d, void* workspace,
   CUtensorMap mSupp, mW1, mW2, mW3, mW6, mW7, mWp, mNone;
   memset(&mNone, 0, sizeof(mNone));
   if ((rc = make_bf16_map(ws.sb, (int64_t)d->batch * kPix, C, C, kBK, kPix, &mSupp)) != OSD_OK) return rc;
-  if ((rc = make_bf16_map(d->w1, C2, C2, C2, kBK, std::min(C2, 256), &mW1)) != OSD_OK) return rc;
-  if ((rc = make_bf16_map(d->w2, C, C2, C2, kBK, std::min(C, 256), &mW2)) != OSD_OK) return rc;
-  if ((rc = make_bf16_map(d->w3, Ch, 9 * C, 9 * C, kBK, Ch, &mW3)) != OSD_OK) return rc;
-  if ((rc = make_bf16_map(d->w6, mlp, (int64_t)kPix * Ch, (int64_t)kPix * Ch, kBK, 256, &mW6)) != OSD_OK) return rc;
-  if ((rc = make_bf16_map(d->w7, mlp, mlp, mlp, kBK, 256, &mW7)) != OSD_OK) return rc;
-  if ((rc = make_bf16_map(d->wp, npred, mlp, mlp, kBK, 32, &mWp)) != OSD_OK) return rc;
+  // W boxes: the N tile's rows; pairs load half of them per CTA and multicast
+  const bool pairs = head_pairs();
+  const int wdiv = pairs ? 2 : 1;
+  if ((rc = make_bf16_map(d->w1, C2, C2, C2, kBK, std::min(C2, 256) / wdiv, &mW1)) != OSD_OK) return rc;
+  if ((rc = make_bf16_map(d->w2, C, C2, C2, kBK, std::min(C, 256) / wdiv, &mW2)) != OSD_OK) return rc;
+  if ((rc = make_bf16_map(d->w3, Ch, 9 * C, 9 * C, kBK, Ch / wdiv, &mW3)) != OSD_OK) return rc;
+  if ((rc = make_bf16_map(d->w6, mlp, (int64_t)kPix * Ch, (int64_t)kPix * Ch, kBK, 256 / wdiv, &mW6)) != OSD_OK) return rc;
+  if ((rc = make_bf16_map(d->w7, mlp, mlp, mlp, kBK, 256 / wdiv, &mW7)) != OSD_OK) return rc;
+  if ((rc = make_bf16_map(d->wp, npred, mlp, mlp, kBK, 32 / wdiv, &mWp)) != OSD_OK) return rc;
 
   for (int64_t r0 = 0; r0 < n_all; r0 += chunk) {
     const int n = (int)std::min<int64_t>(chunk, n_all - r0);
@@ -593,15 +654,15 @@ extern "C" int osd_box_head_forward(const osd_box_head_desc* d, void* workspace,
     // conv1: K = [x | support] (concat never materialised) -> GN1 -> LeakyReLU
     G.M = n; G.N = C2; G.K = C2; G.a_mode = A_ROI; G.k_split = C;
     G.bias = d->b1; G.gamma = d->gn1_w; G.beta = d->gn1_b; G.out = ws.a1; G.ldo = C2;
-    if ((rc = launch_gn_gemm(mX, mSupp, mW1, G, stream, "box_head_conv1")) != OSD_OK) return rc;
+    if ((rc = launch_gn_gemm(mX, mSupp, mW1, G, stream, "box_head_conv1", pairs)) != OSD_OK) return rc;
     // conv2 -> GN2 -> LeakyReLU
     G.N = C; G.K = C2; G.k_split = C2;
     G.bias = d->b2; G.gamma = d->gn2_w; G.beta = d->gn2_b; G.out = ws.a2; G.ldo = C;
-    if ((rc = launch_gn_gemm(mA1, mNone, mW2, G, stream, "box_head_conv2")) != OSD_OK) return rc;
+    if ((rc = launch_gn_gemm(mA1, mNone, mW2, G, stream, "box_head_conv2", pairs)) != OSD_OK) return rc;
     // feature_aggreg: 3x3 conv as an implicit GEMM over 9 shifted boxes -> GN3 -> LeakyReLU
     G.N = Ch; G.K = 9 * C; G.a_mode = A_ROI_3X3; G.tap_c = C;
     G.bias = d->b3; G.gamma = d->gn3_w; G.beta = d->gn3_b; G.out = ws.a3 + (size_t)r0 * kPix * Ch; G.ldo = Ch;
-    if ((rc = launch_gn_gemm(mA2, mNone, mW3, G, stream, "box_head_aggreg")) != OSD_OK) return rc;
+    if ((rc = launch_gn_gemm(mA2, mNone, mW3, G, stream, "box_head_aggreg", pairs)) != OSD_OK) return rc;
   }
 
   // ---- the fully connected layers, once over all ROIs (full waves of 128-row tiles)
@@ -615,12 +676,12 @@ extern "C" int osd_box_head_forward(const osd_box_head_desc* d, void* workspace,
   // fc6, fc7 (+ ReLU)
   G.a_mode = A_PLAIN; G.M = n; G.N = mlp; G.K = kPix * Ch; G.relu = 1; G.out_f32 = 0;
   G.bias = d->b6; G.out = ws.h6; G.ldo = mlp;
-  if ((rc = launch_gemm<0, 128, 1>(mA3, mNone, mW6, G, stream, "box_head_fc6")) != OSD_OK) return rc;
+  if ((rc = launch_gemm<0, 128, 1, 2>(mA3, mNone, mW6, G, stream, "box_head_fc6", pairs)) != OSD_OK) return rc;
   G.K = mlp; G.bias = d->b7; G.out = ws.h7;
-  if ((rc = launch_gemm<0, 128, 1>(mH6, mNone, mW7, G, stream, "box_head_fc7")) != OSD_OK) return rc;
+  if ((rc = launch_gemm<0, 128, 1, 2>(mH6, mNone, mW7, G, stream, "box_head_fc7", pairs)) != OSD_OK) return rc;
   // predictor: cls_score rows then bbox_pred rows of one small GEMM, fp32 outputs in the reference's two tensors
   G.N = npred; G.relu = 0; G.out_f32 = 1; G.bias = d->bp;
   G.out = d->class_logits; G.ldo = d->num_classes;
   G.out2 = d->box_regression; G.ldo2 = d->num_box_out; G.n_split = d->num_classes;
-  return launch_gemm<0, 16, 1>(mH7, mNone, mWp, G, stream, "box_head_predictor");
+  return launch_gemm<0, 16, 1, 2>(mH7, mNone, mWp, G, stream, "box_head_predictor", pairs);
 }

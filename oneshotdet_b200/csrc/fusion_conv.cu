@@ -659,6 +659,13 @@ static size_t fusion_carve(const osd_fusion_desc* d, osd::Carver& c, osd::Fusion
       elems += (size_t)d->batch * d->channels * (size_t)osd::fusion_xb_pitch(d->hw[l]);
     ws->xb = c.take<uint16_t>(elems);
   }
+  ws->gseg = nullptr; ws->rowsum = nullptr; ws->seg_plane = nullptr; ws->max_segments = 0;
+  if (d->stage == OSD_FUSION_FULL && d->channels >= 128) {
+    ws->max_segments = osd::kNumSMs + (int)per;
+    ws->gseg = c.take<float>((size_t)ws->max_segments * d->channels * d->channels);
+    ws->rowsum = c.take<float>((size_t)ws->max_segments * d->channels);
+    ws->seg_plane = c.take<int>((size_t)ws->max_segments);
+  }
   return c.total();
 }
 

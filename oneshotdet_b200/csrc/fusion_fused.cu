@@ -60,6 +60,11 @@ constexpr int kUmmaK = 16;
 constexpr uint32_t kD2Col = 256;        // TMEM columns: D1/y1 chunk buffers at 0 and 128, D2 at 256..511
 
 constexpr int kDefaultFusionMode = 0;    // see fusion_full_forward
+// multicast-weights mode: CTAs per cluster.  Two CTAs save nothing (the L2 already merges concurrent requests for the
+// same lines of up to ~4 SMs); eight halve the L2 -> SM weight traffic, which at ~75 GB/s per SM sits at the L2's
+// throughput cap (~6300 B/clk for the whole chip)
+constexpr int kMc = 8;
+constexpr uint16_t kMcMask = (uint16_t)((1u << kMc) - 1u);
 constexpr int kThreadsA = 32 * 18;
 constexpr int kThreadsB = 32 * 19;
 
@@ -179,7 +184,7 @@ __device__ __forceinline__ bool elect_one() {
 template <bool TWO, bool MC>
 __device__ __forceinline__ void release_stage(uint32_t bar) {
   if (TWO) umma_commit_2sm(bar);
-  else if (MC) umma_commit_mc(bar, (uint16_t)3);
+  else if (MC) umma_commit_mc(bar, kMcMask);
   else umma_commit(bar);
 }
 
@@ -282,11 +287,12 @@ __device__ __forceinline__ void load_weight_stage(const Bars& bar, uint32_t sW, 
   const uint32_t s = wc % kStages, ph = (wc / kStages) & 1u;
   mbar_wait(bar.w_empty + 8u * s, ph ^ 1u);
   if (MC) {
-    // both CTAs of the cluster hold the WHOLE stage; this CTA fetches its half of the rows once from L2 and the TMA unit
-    // writes it into both CTAs' rings (same offset), signalling each CTA's own "full" barrier: half the L2 -> SM bytes
+    // every CTA of the cluster holds the WHOLE stage; this CTA fetches its 1/kMc of the rows once from L2 and the TMA
+    // unit writes them into all the CTAs' rings (same offset), signalling each CTA's own "full" barrier
+    const int rows_part = (int)(stage_tx_bytes / 128u) / kMc;
     mbar_expect_tx(bar.w_full + 8u * s, stage_tx_bytes);
-    tma_load_2d_mc(sW + s * kStageBytes + rank * (uint32_t)(rows_half * 128), map, col, row + (int)rank * rows_half,
-                   bar.w_full + 8u * s, (uint16_t)3);
+    tma_load_2d_mc(sW + s * kStageBytes + rank * (uint32_t)(rows_part * 128), map, col, row + (int)rank * rows_part,
+                   bar.w_full + 8u * s, kMcMask);
   } else if (TWO) {
     if (rank == 0) mbar_expect_tx(bar.w_full + 8u * s, stage_tx_bytes);
     else mbar_arrive_leader(bar.w_full + 8u * s);
@@ -342,8 +348,9 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
   static_assert(!(TWO && MC), "pairs (cta_group::2) and multicast weights are alternatives");
   constexpr bool CL = TWO || MC;                               // launched as clusters of 2 CTAs
   constexpr int kStages = Ring<TWO>::kStages;
-  const uint32_t rank = CL ? (blockIdx.x & 1u) : 0u;           // cluster dims (2,1,1): rank in the pair
-  const int tile0 = CL ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x;
+  constexpr uint32_t kCl = MC ? (uint32_t)kMc : (TWO ? 2u : 1u);   // CTAs per cluster; cluster c works on tiles c*kCl + rank
+  const uint32_t rank = blockIdx.x % kCl;
+  const int tile0 = (int)(blockIdx.x - rank);
   constexpr int C2 = 2 * C;
   constexpr int NCH = C2 / kChunk;          // conv1 chunks per tile
   constexpr int GS = C2 / 32;               // channels per GroupNorm-1 group
@@ -364,7 +371,7 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
     tma_prefetch_desc(&tmap_w1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar.w_full + 8u * s, kPair);
-      mbar_init(bar.w_empty + 8u * s, MC ? 2 : 1);
+      mbar_init(bar.w_empty + 8u * s, MC ? kMc : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar.x_full + 8u * s, 8 * kPair);    // producer warps
@@ -546,6 +553,316 @@ fusion_stats1_kernel(const __grid_constant__ CUtensorMap tmap_w1, const FArgs A)
 }
 
 // ------------------------------------------------------------------------------------------------
+// pass A': GroupNorm-1 statistics WITHOUT running conv1 (+ the bf16 copy of x)
+// ------------------------------------------------------------------------------------------------
+// y_c(p) = w_c . x_p + b_c is linear in x, so over the pixels p of one (episode, level) plane
+//     sum_p y_c   = w_c . sx + HW b_c                          sx = sum_p x_p            (C-vector)
+//     sum_p y_c^2 = w_c^T G w_c + 2 b_c (w_c . sx) + HW b_c^2   G  = sum_p x_p x_p^T      (C x C Gram matrix)
+// and summed over the channels of a GroupNorm group g:  sum_c w_c^T G w_c = <G, M_g>,  M_g = sum_{c in g} w_c w_c^T, which
+// depends on the weights only (prepared once by the host: w1x_gram).  The Gram matrix is a GEMM of the activation tile
+// with ITSELF: the [C, 128 px] tile the producers write for conv1's MN-major A operand is, read with the other
+// descriptor, a K-major [C rows x 128 K] operand -- A and B of  G += X X^T  are the same shared memory.  Compared with
+// pass A above: half the tensor work (C x C instead of 2C x C per pixel), NO weight stream from L2, and no per-tile
+// epilogue -- the accumulator (C x C fp32 = all of tensor memory at C = 256) stays resident while a CTA walks the
+// consecutive tiles of a plane and is written out once per (CTA, plane) segment.  The pass is then bound by its HBM
+// traffic alone (read x fp32, write the bf16 copy).
+constexpr int kThreadsG = 32 * 13;   // 8 producers, 4 drain warps, MMA issuer
+
+struct GramArgs {
+  int tile_first[kNumSMs + 1];   // CTA i owns the consecutive tiles [tile_first[i], tile_first[i + 1])
+  int seg_first[kNumSMs];        // id of CTA i's first (CTA, plane) segment
+  float* gseg;                   // [segments, C, C]
+  float* rowsum;                 // [segments, C]  sum over the segment's pixels of the bf16-rounded x
+  int* seg_plane;                // [segments]
+};
+
+__device__ __forceinline__ int tile_plane(const FArgs& A, int tile) {
+  const TileInfo t = decode_tile(A, tile);
+  return t.level * A.B + t.img;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreadsG, 1) fusion_gram_kernel(const FArgs A, const GramArgs Q) {
+  using S = Smem<C>;
+  static_assert(C == 128 || C == 256, "Gram statistics: C = 128 or 256");
+  constexpr int MH = C / 128;               // M halves of the accumulator
+  constexpr int kMmaWarp = 12;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sX = smem_base + S::x_off;
+  const Bars bar = make_bars(smem_base + S::bar_off);
+  const uint32_t acc_full = bar.d1_full, acc_empty = bar.d1_done;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = Q.tile_first[blockIdx.x], t1 = Q.tile_first[blockIdx.x + 1];
+
+  if (warp == kMmaWarp && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar.x_full + 8u * s, 8);      // producer warps
+      mbar_init(bar.x_empty + 8u * s, 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);                  // drain warps
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(bar.tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (bar.tmem_slot - smem_base));
+
+  if (warp == kMmaWarp) {
+    // ===================== MMA issuer: G (+)= X_tile X_tile^T =====================
+    constexpr uint32_t idesc = make_idesc_ex(128, C, /*a_mn=*/0, /*b_mn=*/0);
+    uint32_t it = 0, run = 0;
+    bool first = true;
+    for (int tile = t0; tile < t1; ++tile, ++it) {
+      const uint32_t xb = it & 1u;
+      mbar_wait(bar.x_full + 8u * xb, (it >> 1) & 1u);
+      if (first && run > 0) mbar_wait(acc_empty, (run - 1) & 1u);   // the previous segment has been drained
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sXt = sX + xb * S::x_bytes;
+#pragma unroll
+        for (int atom = 0; atom < 2; ++atom) {          // 64-pixel halves of the tile = K blocks of one swizzle row
+          const uint64_t b0 = make_smem_desc(sXt + (uint32_t)atom * (uint32_t)(C * 128), 16u, 1024u);
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+#pragma unroll
+            for (int mh = 0; mh < MH; ++mh) {
+              const uint64_t a0 = make_smem_desc(sXt + (uint32_t)atom * (uint32_t)(C * 128) + (uint32_t)mh * (128u * 128u), 16u, 1024u);
+              umma_bf16(tmem_base + (uint32_t)mh * 256u, a0 + (uint64_t)(k16 * 2), b0 + (uint64_t)(k16 * 2), idesc,
+                        (first && atom == 0 && k16 == 0) ? 0u : 1u);
+            }
+          }
+        }
+        umma_commit(bar.x_empty + 8u * xb);
+      }
+      __syncwarp();
+      const bool last = (tile + 1 == t1) || (tile_plane(A, tile + 1) != tile_plane(A, tile));
+      if (last) {
+        commit_elect<false>(acc_full);
+        ++run;
+      }
+      first = last;
+    }
+  } else if (warp < 8) {
+    // ===================== activation producers (as pass A) + per-row sums of the rounded values =====================
+    const int pw = warp;
+    const int chunk = lane & 15, rsub = lane >> 4;
+    constexpr int kRounds = 8;
+    float rs[(C / 128) * kRounds];
+#pragma unroll
+    for (int i = 0; i < (C / 128) * kRounds; ++i) rs[i] = 0.f;
+    uint32_t it = 0;
+    int seg = Q.seg_first[blockIdx.x];
+    for (int tile = t0; tile < t1; ++tile, ++it) {
+      const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+      const TileInfo t = decode_tile(A, tile);
+      const FLevel& L = A.lv[t.level];
+      const int px = t.px0 + chunk * 8;
+      const float* src = L.in + (size_t)t.img * C * L.hw + px;
+      __nv_bfloat16* dstg = L.xb + (size_t)t.img * C * L.pitch + px;
+      const bool vec_ok = ((L.hw & 3) == 0) && (px + 8 <= L.hw);
+      const int nleft = L.hw - px;
+#pragma unroll 1
+      for (int kh = 0; kh < C; kh += 128) {
+        float v[kRounds][8];
+#pragma unroll
+        for (int u = 0; u < kRounds; ++u) {
+          const int k = kh + u * 16 + pw * 2 + rsub;
+          const float* p = src + (size_t)k * L.hw;
+          if (vec_ok) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+            v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
+            v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[u][q] = (q < nleft) ? __ldg(p + q) : 0.f;
+          }
+        }
+        if (kh == 0) mbar_wait_relaxed(bar.x_empty + 8u * buf, ph ^ 1u);
+#pragma unroll
+        for (int u = 0; u < kRounds; ++u) {
+          const int k = kh + u * 16 + pw * 2 + rsub;
+          uint4 pk;
+          pk.x = pack_bf16x2(v[u][0], v[u][1]);
+          pk.y = pack_bf16x2(v[u][2], v[u][3]);
+          pk.z = pack_bf16x2(v[u][4], v[u][5]);
+          pk.w = pack_bf16x2(v[u][6], v[u][7]);
+          const uint32_t dst = sX + buf * S::x_bytes + (uint32_t)(chunk >> 3) * (uint32_t)(C * 128) + (uint32_t)(k >> 3) * 1024u +
+                               (uint32_t)(k & 7) * 128u + (uint32_t)(((chunk & 7) ^ (k & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+          if (nleft > 0) *reinterpret_cast<uint4*>(dstg + (size_t)k * L.pitch) = pk;
+          // the values the tensor core sees: bf16 -> fp32 is a 16-bit shift
+          const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+          float s8 = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) s8 += __uint_as_float(w[q] << 16) + __uint_as_float(w[q] & 0xffff0000u);
+          rs[(kh >> 7) * kRounds + u] += s8;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar.x_full + 8u * buf);
+      const bool last = (tile + 1 == t1) || (tile_plane(A, tile + 1) != t.level * A.B + t.img);
+      if (last) {
+#pragma unroll
+        for (int i = 0; i < (C / 128) * kRounds; ++i) {
+          float x = rs[i];
+          x += __shfl_xor_sync(0xffffffffu, x, 8);
+          x += __shfl_xor_sync(0xffffffffu, x, 4);
+          x += __shfl_xor_sync(0xffffffffu, x, 2);
+          x += __shfl_xor_sync(0xffffffffu, x, 1);
+          if (chunk == 0) Q.rowsum[(size_t)seg * C + (i / kRounds) * 128 + (i % kRounds) * 16 + pw * 2 + rsub] = x;
+          rs[i] = 0.f;
+        }
+        ++seg;
+      }
+    }
+  } else {
+    // ===================== drain warps (8-11; thread = accumulator row): one write per (CTA, plane) segment =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t run = 0;
+    int seg = Q.seg_first[blockIdx.x];
+    int tile = t0;
+    while (tile < t1) {
+      const int p = tile_plane(A, tile);
+      int e = tile + 1;
+      while (e < t1 && tile_plane(A, e) == p) ++e;
+      mbar_wait(acc_full, run & 1u);
+      tc_fence_after();
+      float* gout = Q.gseg + (size_t)seg * C * C;
+#pragma unroll
+      for (int mh = 0; mh < MH; ++mh) {
+        float4* orow = reinterpret_cast<float4*>(gout + (size_t)(mh * 128 + row) * C);
+#pragma unroll 2
+        for (int cb = 0; cb < C; cb += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mh * 256u + (uint32_t)cb, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            orow[(cb >> 2) + i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                              __uint_as_float(r[4 * i + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      if (warp == 8 && lane == 0) Q.seg_plane[seg] = p;
+      tile = e;
+      ++seg;
+      ++run;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// <G, M_g> for every plane and group: thread = one (i, j) entry of the C x C index space with its 32 M_g values in
+// registers; segments arrive in plane order (8 loads in flight), partial sums are flushed whenever the plane changes: warp
+// transpose-reduce, then shared-memory atomics into a per-plane table (no block barrier inside the loop); one fp64
+// atomic per (plane, group) and CTA at the end
+constexpr int kMaxPlanes = 160;
+template <int C>
+__global__ void __launch_bounds__(256) fusion_gram_frob_kernel(const float* __restrict__ gseg, const int* __restrict__ seg_plane,
+                                                                int nseg, int nplanes, const float* __restrict__ mg, double* stats1) {
+  __shared__ float sacc[kMaxPlanes][32];
+  __shared__ int splane[kNumSMs + kMaxPlanes];
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < nplanes * 32; i += 256) (&sacc[0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < nseg; i += 256) splane[i] = seg_plane[i];
+  float m[32], acc[32];
+#pragma unroll
+  for (int g = 0; g < 32; ++g) {
+    m[g] = __ldg(mg + (size_t)g * C * C + idx);
+    acc[g] = 0.f;
+  }
+  __syncthreads();
+  int cur = splane[0];
+  auto flush = [&](int plane) {
+    float t[32];
+#pragma unroll
+    for (int g = 0; g < 32; ++g) { t[g] = acc[g]; acc[g] = 0.f; }
+    warp_transpose_reduce32(t, lane);
+    atomicAdd(&sacc[plane][lane], t[0]);
+  };
+  constexpr int kPre = 8;
+  for (int s0 = 0; s0 < nseg; s0 += kPre) {
+    float v[kPre];
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) v[u] = (s0 + u < nseg) ? __ldg(gseg + (size_t)(s0 + u) * C * C + idx) : 0.f;
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      if (s0 + u < nseg) {
+        const int p = splane[s0 + u];
+        if (p != cur) {
+          flush(cur);
+          cur = p;
+        }
+#pragma unroll
+        for (int g = 0; g < 32; ++g) acc[g] = fmaf(v[u], m[g], acc[g]);
+      }
+    }
+  }
+  flush(cur);
+  __syncthreads();
+  for (int i = threadIdx.x; i < nplanes * 32; i += 256) {
+    const float x = (&sacc[0][0])[i];
+    if (x != 0.f) atomicAdd(stats1 + (size_t)(i >> 5) * 64 + 2 * (i & 31) + 1, (double)x);
+  }
+}
+
+// the linear terms: sx of the plane, u = W1x sx, then per group  sum_c (u_c + HW b_c)  and  sum_c (2 b_c u_c + HW b_c^2)
+template <int C>
+__global__ void __launch_bounds__(256) fusion_gram_linear_kernel(const float* __restrict__ rowsum, const int* __restrict__ seg_plane,
+                                                                  int nseg, const __nv_bfloat16* __restrict__ w1x,
+                                                                  const float* __restrict__ bias_eff, FArgs A, double* stats1) {
+  __shared__ float sx[C];
+  constexpr int C2 = 2 * C, GS = C2 / 32;
+  const int plane = blockIdx.x;
+  const float hw = (float)A.lv[plane / A.B].hw;
+  for (int k = threadIdx.x; k < C; k += 256) {
+    float s = 0.f;
+    for (int sgi = 0; sgi < nseg; ++sgi)
+      if (seg_plane[sgi] == plane) s += rowsum[(size_t)sgi * C + k];
+    sx[k] = s;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C2; c += 256) {
+    const __nv_bfloat162* wr = reinterpret_cast<const __nv_bfloat162*>(w1x + (size_t)c * C);
+    float u = 0.f;
+#pragma unroll 8
+    for (int k2 = 0; k2 < C / 2; ++k2) {
+      const float2 w = __bfloat1622float2(wr[k2]);
+      u = fmaf(w.x, sx[2 * k2], u);
+      u = fmaf(w.y, sx[2 * k2 + 1], u);
+    }
+    const float b = bias_eff[(size_t)plane * C2 + c];
+    float s1 = fmaf(hw, b, u);
+    float s2 = fmaf(2.f * b, u, hw * b * b);
+#pragma unroll
+    for (int o = GS / 2; o >= 1; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & (GS - 1)) == 0) {
+      atomicAdd(stats1 + (size_t)plane * 64 + 2 * (c / GS), (double)s1);
+      atomicAdd(stats1 + (size_t)plane * 64 + 2 * (c / GS) + 1, (double)s2);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // pass B: conv1 -> GN1 + LeakyReLU -> conv2 (+ b2) [-> GN2 + LeakyReLU] -> out, GroupNorm-2 statistics
 // ------------------------------------------------------------------------------------------------
 // FINAL: the output epilogue applies GroupNorm-2 + LeakyReLU (coef2) and always stores; otherwise it writes the raw y2
@@ -566,8 +883,9 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
   constexpr bool CL = TWO || MC;
   constexpr int kStages = Ring<TWO>::kStages;
   constexpr int N2 = C < 128 ? C : 128;
-  const uint32_t rank = CL ? (blockIdx.x & 1u) : 0u;
-  const int tile0 = CL ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x;
+  constexpr uint32_t kCl = MC ? (uint32_t)kMc : (TWO ? 2u : 1u);
+  const uint32_t rank = blockIdx.x % kCl;
+  const int tile0 = (int)(blockIdx.x - rank);
   constexpr int C2 = 2 * C;
   constexpr int NCH = C2 / kChunk;
   constexpr int GS2 = C / 32;               // channels per GroupNorm-2 group
@@ -590,7 +908,7 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
     tma_prefetch_desc(&tmap_w2);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar.w_full + 8u * s, kPair);
-      mbar_init(bar.w_empty + 8u * s, MC ? 2 : 1);
+      mbar_init(bar.w_empty + 8u * s, MC ? kMc : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar.x_full + 8u * s, kPair);        // (expect_tx) arrival of the TMA warp of each CTA
@@ -843,7 +1161,7 @@ fusion_b2b_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_cons
 // ------------------------------------------------------------------------------------------------
 // launch with an optional cluster of 2 CTAs along x
 template <typename... KArgs, typename... Args>
-int launch_fused(void (*kernel)(KArgs...), int grid, int threads, size_t smem, bool pairs, cudaStream_t stream, Args&&... args) {
+int launch_fused(void (*kernel)(KArgs...), int grid, int threads, size_t smem, int cluster, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)threads);
@@ -851,7 +1169,7 @@ int launch_fused(void (*kernel)(KArgs...), int grid, int threads, size_t smem, b
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = pairs ? 2 : 1;
+  attr[0].val.clusterDim.x = (unsigned)cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -876,9 +1194,9 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
   CUtensorMap map1, map2;
   XMaps xm;
   memset(&xm, 0, sizeof(xm));
-  int rc = make_bf16_map(d->w1x_bf16, C2, C, C, kStageK, CL ? 64 : 128, &map1);
+  int rc = make_bf16_map(d->w1x_bf16, C2, C, C, kStageK, MC ? 128 / kMc : (TWO ? 64 : 128), &map1);
   if (rc != OSD_OK) return rc;
-  rc = make_bf16_map(d->w2_bf16, C, C2, C2, kStageK, CL ? N2 / 2 : 128, &map2);
+  rc = make_bf16_map(d->w2_bf16, C, C2, C2, kStageK, MC ? N2 / kMc : (TWO ? N2 / 2 : 128), &map2);
   if (rc != OSD_OK) return rc;
 
   FArgs A{};
@@ -916,21 +1234,22 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
   if (CL) {
     // persistent clusters: every cluster of the grid must be resident at once (a cluster that has to wait for a free SM
     // pair would run its whole share of the tiles after the others have finished)
-    int max_clusters = kNumSMs / 2;
+    constexpr int kCl = MC ? kMc : 2;
+    int max_clusters = kNumSMs / kCl;
     cudaLaunchConfig_t q{};
     q.gridDim = dim3((unsigned)kNumSMs);
     q.blockDim = dim3((unsigned)kThreadsB);
     q.dynamicSmemBytes = S::total;
     cudaLaunchAttribute qa[1];
     qa[0].id = cudaLaunchAttributeClusterDimension;
-    qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    qa[0].val.clusterDim.x = kCl; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
     q.attrs = qa; q.numAttrs = 1;
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, reinterpret_cast<const void*>(kA), &q) == cudaSuccess && n > 0)
       max_clusters = std::min(max_clusters, n);
     else
       (void)cudaGetLastError();
-    grid = 2 * std::min((tiles + 1) / 2, max_clusters);
+    grid = kCl * std::min((tiles + kCl - 1) / kCl, max_clusters);
   }
   static const bool prof_on = [] { const char* e = getenv("OSD_FUSION_PROF"); return e && e[0] == '1'; }();
   static long long* prof_dev = nullptr;
@@ -947,10 +1266,58 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
   if (rc != OSD_OK) return rc;
 
   // ---- pass A: GroupNorm-1 statistics (+ bf16 copy of the features)
-  rc = launch_fused(kA, grid, kThreadsA, S::total, CL, stream, map1, A);
-  if (rc != OSD_OK) return rc;
-  OSD_LAUNCH_CHECK("fusion_stats1_kernel");
-  timeline_mark("fusion_stats1_kernel", stream);
+  // opt-in (OSD_FUSION_GRAM=1): correct (parity-tested) but measured slower than running conv1 -- DESIGN section 6
+  static const bool gram_off = [] { const char* e = getenv("OSD_FUSION_GRAM"); return !(e && e[0] == '1'); }();
+  bool gram_done = false;
+  if constexpr (C >= 128) {
+    if (d->w1x_gram != nullptr && ws.gseg != nullptr && !gram_off) {
+      // consecutive tile ranges per CTA (the accumulator follows a plane), (CTA, plane) segments numbered in tile order
+      const int gg = std::min(tiles, kNumSMs);
+      GramArgs Q{};
+      auto plane_of = [&](int tile) {
+        int li = 0;
+        for (int k = 1; k < nl; ++k)
+          if (tile >= A.lv[k].tile_begin) li = k;
+        return li * B + (tile - A.lv[li].tile_begin) / A.lv[li].tiles_per_img;
+      };
+      int nseg = 0;
+      for (int i = 0; i < gg; ++i) {
+        Q.tile_first[i] = (int)((int64_t)i * tiles / gg);
+        const int t1 = (int)((int64_t)(i + 1) * tiles / gg);
+        Q.seg_first[i] = nseg;
+        nseg += plane_of(t1 - 1) - plane_of(Q.tile_first[i]) + 1;
+      }
+      Q.tile_first[gg] = tiles;
+      Q.gseg = ws.gseg; Q.rowsum = ws.rowsum; Q.seg_plane = ws.seg_plane;
+      if (nseg > ws.max_segments) {
+        set_error("osd_fusion: %d Gram segments exceed the workspace's %d", nseg, ws.max_segments);
+        return OSD_ERR_WORKSPACE;
+      }
+      auto kG = fusion_gram_kernel<C>;
+      rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kG), S::total);
+      if (rc != OSD_OK) return rc;
+      kG<<<gg, kThreadsG, S::total, stream>>>(A, Q);
+      OSD_LAUNCH_CHECK("fusion_gram_kernel");
+      timeline_mark("fusion_gram_kernel", stream);
+      if (nl * B > kMaxPlanes) {
+        set_error("osd_fusion: %d (level, episode) planes exceed the Gram statistics' %d; split the batch", nl * B, kMaxPlanes);
+        return OSD_ERR_INVALID;
+      }
+      fusion_gram_frob_kernel<C><<<C * C / 256, 256, 0, stream>>>(ws.gseg, ws.seg_plane, nseg, nl * B, d->w1x_gram, ws.stats1);
+      OSD_LAUNCH_CHECK("fusion_gram_frob_kernel");
+      fusion_gram_linear_kernel<C><<<nl * B, 256, 0, stream>>>(ws.rowsum, ws.seg_plane, nseg,
+                                                               static_cast<const __nv_bfloat16*>(d->w1x_bf16), ws.bias_eff, A, ws.stats1);
+      OSD_LAUNCH_CHECK("fusion_gram_linear_kernel");
+      timeline_mark("fusion_gram_stats", stream);
+      gram_done = true;
+    }
+  }
+  if (!gram_done) {
+    rc = launch_fused(kA, grid, kThreadsA, S::total, MC ? kMc : (TWO ? 2 : 1), stream, map1, A);
+    if (rc != OSD_OK) return rc;
+    OSD_LAUNCH_CHECK("fusion_stats1_kernel");
+    timeline_mark("fusion_stats1_kernel", stream);
+  }
   rc = fusion_launch_gn_coef(nl, B, C2, d->gn_eps, ws.stats1, d->gn1_w, d->gn1_b, ws.bias_eff, ws.coef1, hw, stream);
   if (rc != OSD_OK) return rc;
 
@@ -958,7 +1325,7 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
   static const bool recompute = [] { const char* e = getenv("OSD_FUSION_RECOMPUTE"); return e && e[0] == '1'; }();
   A.store = recompute ? 0 : 1;
   A.final_xform = 0;
-  rc = launch_fused(kB, grid, kThreadsB, S::total, CL, stream, map1, map2, xm, A);
+  rc = launch_fused(kB, grid, kThreadsB, S::total, MC ? kMc : (TWO ? 2 : 1), stream, map1, map2, xm, A);
   if (rc != OSD_OK) return rc;
   OSD_LAUNCH_CHECK("fusion_b2b_kernel");
   timeline_mark("fusion_b2b_kernel", stream);
@@ -972,7 +1339,7 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
     A.stats2 = nullptr;
     rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kBfinal), S::total);
     if (rc != OSD_OK) return rc;
-    rc = launch_fused(kBfinal, grid, kThreadsB, S::total, CL, stream, map1, map2, xm, A);
+    rc = launch_fused(kBfinal, grid, kThreadsB, S::total, MC ? kMc : (TWO ? 2 : 1), stream, map1, map2, xm, A);
     if (rc != OSD_OK) return rc;
     OSD_LAUNCH_CHECK("fusion_b2b_kernel");
     timeline_mark("fusion_b2b_kernel(final)", stream);
@@ -1003,8 +1370,8 @@ int run_full(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t s
 }  // namespace
 
 int fusion_full_forward(const osd_fusion_desc* d, const FusionWorkspace& ws, cudaStream_t stream) {
-  // OSD_FUSION_MODE: "single" = one CTA per tile; "mc" = clusters of 2 CTAs, one tile each, every weight stage
-  // fetched once from L2 and multicast into both CTAs' rings; "pair" (or OSD_FUSION_2CTA=1) = CTA pairs on tcgen05
+  // OSD_FUSION_MODE: "single" = one CTA per tile; "mc" = clusters of 8 CTAs, one tile each, every weight stage
+  // fetched once from L2 (an eighth of its rows per CTA) and multicast into all eight rings; "pair" (or OSD_FUSION_2CTA=1) = CTA pairs on tcgen05
   // cta_group::2 (M = 256 across two SMs)
   static const int mode = [] {
     const char* e = getenv("OSD_FUSION_MODE");

@@ -33,6 +33,11 @@ struct FusionWorkspace {
   float2* coef1;      // [nl, B, 2C]
   float2* coef2;      // [nl, B, C]
   void* xb;           // bf16 copy of the features, per level [B*C, pitch_l]
+  // Gram statistics of pass A (C >= 128): one C x C fp32 matrix and one C-vector per (CTA, plane) segment
+  float* gseg;
+  float* rowsum;
+  int* seg_plane;
+  int max_segments;
 };
 
 // pitch (elements) of level rows in the bf16 copy: hw rounded up to 8 (16-byte rows for TMA)

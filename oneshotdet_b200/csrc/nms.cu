@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(kChunkThreads) nms_chunk_sort_kernel(CandLayou
     W.ecount[e] = 0;
     if (e == 0) {
       W.sched[0] = 0;  // episodes finished
-      W.sched[1] = W.sched[2] = W.sched[3] = 0;  // mask tile counters of the passes
+#pragma unroll
+      for (int k = 1; k < 8; ++k) W.sched[k] = 0;  // mask tile counters of the passes
     }
   }
   const int base = c * kChunk;
@@ -844,12 +845,21 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
     const int NPu = (int)align_up((size_t)(max_len > 0 ? max_len : 1), 64);
     const bool early = P.early_exit && P.post_top_n > 0;
     S.stop = early ? P.post_top_n + 1 : INT_MAX;
-    int bounds[3];
+    int bounds[7];
     int npass = 0;
     if (early) {
-      // enough boxes to keep post_top_n + 1 when at most ~5 % of the best-scored boxes are suppressed
+      // enough boxes to keep post_top_n + 1 when at most ~5 % of the best-scored boxes are suppressed, then prefixes
+      // that double (the first of them still inside the sweep's "small pass" limit of 4096 boxes): when the best-scored
+      // boxes suppress each other heavily (a trained detector's clusters around objects) the exit is reached after a
+      // fraction of the 67 M pairs of the full problem instead of after all of them.  A pass whose episodes have all
+      // finished returns at once (W.sched[0]).
       const int b1 = (int)align_up((size_t)P.post_top_n + 1, 64) + 64;
-      if (b1 < NPu) bounds[npass++] = b1;
+      if (b1 < NPu) {
+        bounds[npass++] = b1;
+        // 2112 -> 4096 -> 8064 -> all for post_top_n = 2000; short lists grow by 4x; no pass within 25 % of the full list
+        for (int b = (b1 < 2048 ? 4 : 2) * (b1 - 64); npass < 5 && (int64_t)4 * b <= (int64_t)3 * NPu; b = (b < 2048 ? 4 : 2) * (b - 64))
+          bounds[npass++] = b;
+      }
     }
     bounds[npass++] = NPu;
     int prev = 0;

@@ -256,6 +256,13 @@ class PeerBlockGatherer:
             self._events.pop(0)
         return slot
 
+    def drain(self):
+        """Device-side: the current stream waits for every push this rank has issued (no host synchronisation, no
+        rendezvous).  What a timed region needs at its end; ``fence()`` is what a consumer of the received blocks needs."""
+        cur = torch.cuda.current_stream(self.device)
+        while self._events:
+            cur.wait_event(self._events.pop(0))
+
     def fence(self):
         """All pushes issued so far by every rank have landed (process-group barrier behind a drained side stream)."""
         self.side.synchronize()

@@ -45,6 +45,12 @@ class PackedFusionWeights:
         self.b2 = (conv2.bias.detach() if conv2.bias is not None else torch.zeros(c)).to(**f32).contiguous()
         self.gn2_w = gn2.weight.detach().to(**f32).contiguous()
         self.gn2_b = gn2.bias.detach().to(**f32).contiguous()
+        # M_g = sum over the channels of GroupNorm-1 group g of w_c w_c^T (w = the bf16-rounded target half): lets pass A
+        # take the GN-1 statistics from a Gram GEMM of the activations instead of running conv1 (csrc/fusion_fused.cu)
+        self.w1x_gram = None
+        if c >= 128:
+            wg = self.w1x.float().reshape(32, c2 // 32, c)
+            self.w1x_gram = torch.einsum("gck,gcl->gkl", wg, wg).contiguous()
         self.versions = tuple(p._version for p in module.parameters())
 
 
@@ -106,6 +112,7 @@ class PreparedFusion:
         d.gn1_w, d.gn1_b = w.gn1_w.data_ptr(), w.gn1_b.data_ptr()
         d.w2_bf16, d.b2 = w.w2.data_ptr(), w.b2.data_ptr()
         d.gn2_w, d.gn2_b = w.gn2_w.data_ptr(), w.gn2_b.data_ptr()
+        d.w1x_gram = w.w1x_gram.data_ptr() if w.w1x_gram is not None else None
         nbytes = ctypes.c_size_t(0)
         _lib.check(self.lib.osd_fusion_workspace_bytes(ctypes.byref(d), ctypes.byref(nbytes)),
                    "osd_fusion_workspace_bytes")

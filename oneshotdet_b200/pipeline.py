@@ -160,6 +160,11 @@ class EpisodePipeline:
 
         return replay
 
+    def capture_streams(self):
+        """Continuous software pipelining instead of one graph per step: returns a ``StreamedSteps`` (needs
+        ``pipeline_depth >= 2``)."""
+        return StreamedSteps(self)
+
     def input_tensors(self):
         return self.features + self.supp + self.cls + self.reg + self.ctr
 
@@ -197,6 +202,74 @@ class EpisodePipeline:
         b, k = res.scores.shape
         eid = torch.arange(episode_offset, episode_offset + b, device=res.scores.device, dtype=torch.float32)
         return torch.cat((res.boxes, res.scores.unsqueeze(-1), eid.view(b, 1, 1).expand(b, k, 1)), dim=-1), res.count
+
+
+class StreamedSteps:
+    """Steps of an EpisodePipeline as THREE self-ordered streams with no join between steps: the matching launches run
+    back to back on one (low-priority) stream, the post-processing chains of consecutive batches alternate between two
+    more.  A chain is a string of a dozen small dependent kernels that takes LONGER than one matching launch when it
+    shares the SMs with the matching stream; a graph that holds one whole step (``capture()``) makes every step wait for
+    its chain.  Here two chains are in flight next to the matching stream at any time, so the step rate is
+    max(matching, chain / 2).  In deployment the chain of batch i consumes the FCOS head's output of batch i, which
+    depends on matching i: the same three-stream shape with one event per batch.
+
+        steps = pipe.capture_streams(); steps.begin()
+        for ...: res, stream = steps.step()     # res: the FcosResult this step writes, ready in `stream` order
+        steps.join()                            # the current stream waits for everything issued so far
+
+    Output sets rotate (``len(pipe.posts)``, a multiple of 2): a set is rewritten only by the stream that wrote it."""
+
+    def __init__(self, pipe: "EpisodePipeline"):
+        if pipe.depth < 2 or len(pipe.posts) % 2 != 0:
+            raise ValueError("StreamedSteps needs an EpisodePipeline(pipeline_depth=2): two chains with their own workspaces")
+        self.pipe = pipe
+        dev = pipe.device
+        lo, hi = torch.cuda.Stream.priority_range()
+        self.s_match = torch.cuda.Stream(dev, priority=lo)
+        self.s_post = [torch.cuda.Stream(dev, priority=hi) for _ in range(2)]
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):       # warm-up outside capture (kernel attributes, lazy allocations)
+            pipe.match()
+            for post in pipe.posts:
+                post()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.g_match = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_match, stream=side):
+            pipe.match()
+        self.g_post, self.results = [], []
+        for post in pipe.posts:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                res = post()
+            self.g_post.append(g)
+            self.results.append(res)
+        self.i = 0
+
+    def begin(self):
+        cur = torch.cuda.current_stream(self.pipe.device)
+        for s in [self.s_match] + self.s_post:
+            s.wait_stream(cur)
+
+    def next_stream(self):
+        """The stream the NEXT step's chain runs on (where an exchange of its result has to be ordered)."""
+        return self.s_post[self.i & 1]
+
+    def step(self):
+        k = self.i % len(self.g_post)
+        s = self.s_post[self.i & 1]
+        with torch.cuda.stream(self.s_match):
+            self.g_match.replay()
+        with torch.cuda.stream(s):
+            self.g_post[k].replay()
+        self.i += 1
+        return self.results[k], s
+
+    def join(self):
+        cur = torch.cuda.current_stream(self.pipe.device)
+        for s in [self.s_match] + self.s_post:
+            cur.wait_stream(s)
 
 
 class HostStreamer:
