@@ -105,3 +105,38 @@ def test_double_buffered_graph_steps_and_result_block():
     g.finish()
     (bx, sc, ix, ct), = g.result(slot)
     assert torch.equal(bx, g1.boxes) and torch.equal(sc, g1.scores) and torch.equal(ct, g1.count)
+
+
+@pytest.mark.parametrize("double_buffer", [False, True])
+def test_streamed_steps_match_the_serial_step(double_buffer):
+    """capture_streams(): matching launches back to back on one stream, the post-processing chains of consecutive
+    batches alternating between two more, no join between steps -- every step's detections and the matching output
+    equal the serial step's, for several rotations of the output sets."""
+    from oneshotdet_b200.pipeline import EpisodePipeline, PostParams
+
+    sizes = [(250, 320), (256, 300), (256, 320)]
+    p = PostParams(0.0, 400, 0.7, 100, 0.0)
+    pipe = EpisodePipeline(3, 256, 320, sizes, channels=32, shots=2, params=p, device=DEV, double_buffer=double_buffer,
+                           pipeline_depth=2)
+    feats, supp = orc.synth_features(3, 2, 32, 256, 320, seed=5)
+    cls, reg, ctr = orc.synth_head_outputs(3, 256, 320, seed=6)
+    for dst, src in zip(pipe.input_tensors(), feats + supp + cls + reg + ctr):
+        dst.copy_(src.to(DEV))
+    ref = snapshot(pipe.run())
+    comb = [t.cpu().clone() for t in pipe.combined]
+    steps = pipe.capture_streams()
+    assert len(steps.results) == (4 if double_buffer else 2)
+    steps.begin()
+    seen = []
+    for i in range(9):
+        res, stream = steps.step()
+        seen.append((res, stream))
+        assert stream is steps.s_post[i & 1] and res is steps.results[i % len(steps.results)]
+    steps.join()
+    torch.cuda.synchronize()
+    for res in steps.results:
+        got = snapshot(res)
+        assert got[0] == ref[0] and all(torch.equal(x, y) for x, y in zip(got[1] + got[2], ref[1] + ref[2]))
+    assert all(torch.equal(t.cpu(), c) for t, c in zip(pipe.combined, comb))
+    with pytest.raises(ValueError):
+        EpisodePipeline(3, 256, 320, sizes, channels=32, shots=2, params=p, device=DEV).capture_streams()

@@ -1,16 +1,28 @@
 #!/bin/bash
-# One-GPU round check: the driver's own sequence (GPU tests, smoke, both bench arms) plus the ncu launch list and one
-# `--set full` capture of the path's kernels.  Outputs land in gpurun_out/ (copy what should be judged into profiles/).
+# One-GPU round check: the driver's own sequence (GPU tests, smoke, both bench arms) plus the ncu launch list of the
+# bench command and `--set full` captures of the path's kernels.  Outputs land in gpurun_out/ (copy what should be judged
+# into profiles/).  Usage: bash tools/gpu_round_check.sh [tag]
 set -x
-TAG=${1:-v10}
+TAG=${1:-r02_final}
+O=gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 python __graft_entry__.py --smoke 2>&1 | tail -2
-python bench.py 2>&1 | tail -1 > gpurun_out/bench_r01_$TAG.json
-python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 > gpurun_out/bench_r01_reference_arm_$TAG.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r01_launches_$TAG.csv python bench.py --steps 2 --warmup 3 --serial --no-graph --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'match_product_bulk|nms_mask|fcos_select|nms_sweep|nms_merge|nms_chunk' --launch-skip 40 -c 6 -o gpurun_out/r01_full_$TAG python bench.py --steps 2 --warmup 3 --serial --no-graph --no-cpu-baseline --no-fusion > gpurun_out/ncu_full.log 2>&1
-ncu -i gpurun_out/r01_full_$TAG.ncu-rep --page raw --csv > gpurun_out/r01_full_${TAG}_raw.csv 2>/dev/null
-ncu --set full --clock-control none --import-source on -k regex:'conv1x1_tc|fusion_gn_lrelu' --launch-skip 2 -c 3 -o gpurun_out/r01_fusion_$TAG python bench.py --steps 2 --warmup 3 --serial --no-graph --no-cpu-baseline > gpurun_out/ncu_fusion.log 2>&1
-ncu -i gpurun_out/r01_fusion_$TAG.ncu-rep --page raw --csv > gpurun_out/r01_fusion_${TAG}_raw.csv 2>/dev/null
-rm -f gpurun_out/*.ncu-rep
-cut -c1-200 gpurun_out/bench_r01_$TAG.json
+python bench.py 2>$O/bench_$TAG.err | tail -1 > $O/bench_$TAG.json
+python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > $O/bench_reference_arm_$TAG.json
+# launch list of the bench command (serialised, cold-cache per-launch times: shares, not absolutes)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv \
+    python bench.py --steps 2 --warmup 3 --pipeline graph --serial --no-graph --no-cpu-baseline --no-workloads --no-e2e > $O/ncu_launch.log 2>&1
+# full captures: the streaming / post-processing kernels of one step
+ncu --set full --clock-control none --import-source on -k regex:'match_product_bulk|nms_mask|fcos_select|nms_sweep|nms_merge|nms_chunk' \
+    --launch-skip 40 -c 6 -o $O/full_$TAG python bench.py --steps 2 --warmup 3 --pipeline graph --serial --no-graph --no-cpu-baseline --no-fusion --no-workloads --no-e2e > $O/ncu_full.log 2>&1
+ncu -i $O/full_$TAG.ncu-rep --page raw --csv > $O/full_${TAG}_raw.csv 2>/dev/null
+# the NMS kernels on the full problem (early_exit=False: all 67.3 M pairs per episode)
+ncu --set full --clock-control none --import-source on -k regex:'nms_mask|nms_sweep' --launch-skip 8 -c 2 \
+    -o $O/nmsfull_$TAG python bench.py --workload nms_noexit --steps 2 --warmup 3 --pipeline graph --serial --no-graph --no-cpu-baseline --no-fusion --no-workloads --no-e2e > $O/ncu_nmsfull.log 2>&1
+ncu -i $O/nmsfull_$TAG.ncu-rep --page raw --csv > $O/nmsfull_${TAG}_raw.csv 2>/dev/null
+# the fused fusion-conv kernels
+ncu --set full --clock-control none --import-source on -k regex:'fusion_stats1|fusion_b2b|fusion_gn_lrelu' --launch-skip 3 -c 3 \
+    -o $O/fusion_$TAG python tools/fusion_time.py --steps 2 > $O/ncu_fusion.log 2>&1
+ncu -i $O/fusion_$TAG.ncu-rep --page raw --csv > $O/fusion_${TAG}_raw.csv 2>/dev/null
+rm -f $O/*.ncu-rep
+cut -c1-300 $O/bench_$TAG.json
