@@ -25,6 +25,7 @@ import argparse
 import json
 import math
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -75,7 +76,7 @@ def config_dict(n_gpus, name="config2", gather=None):
             "global_episodes": wl["batch"] * n_gpus, "levels": LEVELS_TEXT[(wl["height"], wl["width"])],
             "match_mode": "product", "match_dtype": "f32", "shots": wl["shots"], "post_params": wl["params"],
             "parallelism": f"episode-dp{n_gpus}", "gather": gather,
-            "streams": "2 (matching || post-processing), see stages.overlap",
+            "streams": "3 (matching | two alternating post-processing chains), see stages.overlap",
             "cache": "inputs larger than L2 (features in + out per step >= 734 MB vs 126 MB L2)"}
 
 
@@ -288,8 +289,24 @@ def cpu_multi_process_throughput(processes=None, timed_steps=2):
             ok += 1
         except Exception:  # noqa: BLE001  (a worker that died only lowers the reported rate)
             pr.kill()
-    return {"value": rate, "unit": UNIT, "processes": ok, "threads_per_process": 1,
+    return {"value": rate, "unit": UNIT, "processes": ok, "threads_per_process": 1, "steps_per_worker": timed_steps,
             "what": "independent single-threaded workers, one episode per step each; sum of the workers' rates"}
+
+
+def cpu_baseline_dict(single, kind, multi):
+    """`value` = what ALL the host cores deliver on this path: the reference's nms_cpu cannot use a second thread, so
+    the way to use every core is one single-threaded worker process per core, each running the unmodified reference on
+    its own episodes (`multi`).  The reference run as it ships -- ONE process, torch.mul on all threads, NMS on one -- is
+    reported beside it as `single_process`.  Without the multi-process measurement the single process is the value."""
+    if multi is None or not multi.get("processes"):
+        return {"value": single["value"], "unit": UNIT, "cores": single["cores"], "kind": kind, "sample": single["sample"],
+                "single_process": single, "multi_process": None}
+    return {"value": multi["value"], "unit": UNIT, "cores": multi["processes"] * multi["threads_per_process"], "kind": kind,
+            "sample": f"{multi['processes']} worker processes x {multi['threads_per_process']} thread, each timing "
+                      f"{multi.get('steps_per_worker', 2)} steps of 1 episode of the workload after one warm-up step: "
+                      + re.sub(r" on \d+ threads", "", single["sample"].split(";")[0].split(": ", 1)[-1])
+                      + "; sum of the workers' rates",
+            "single_process": single, "multi_process": multi}
 
 
 def run_ref_worker(seed, steps):
@@ -303,9 +320,10 @@ def run_ref_worker(seed, steps):
 
 
 def run_reference_arm(args):
-    """The reference's CPU path with all the host threads it can use.  Under torchrun (N > 1) rank 0 alone runs and
-    prints the line, the other ranks exit without work (the contract of this tier); the line says so in
-    `cpu_processes`, so a per-N ratio against it compares N GPUs with ONE CPU process."""
+    """The reference's CPU path with all the host threads it can use: one single-threaded worker process per core, each
+    running the unmodified reference on its own episodes (its NMS cannot use a second thread); the one-process figure is
+    in `cpu_baseline.single_process`.  Under torchrun (N > 1) rank 0 alone runs and prints the line, the other ranks
+    exit without work (the contract of this tier): a per-N ratio against it compares N GPUs with this ONE host."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -321,15 +339,20 @@ def run_reference_arm(args):
             break
     nsteps = len(times)
     total = sum(times)
-    value = ref.episodes * nsteps / total
+    single = {"value": ref.episodes * nsteps / total, "unit": UNIT, "cores": ref.cores, "processes": 1,
+              "sample": ref.sample_text() + f"; {nsteps} steps, {total / nsteps:.3f} s/episode"}
+    multi = None if args.no_multi_process else cpu_multi_process_throughput(timed_steps=max(2, min(args.steps, 8)))
+    cpu = cpu_baseline_dict(single, ref.kind, multi)
+    value = cpu["value"]
+    procs = multi["processes"] if (multi and multi.get("processes")) else 1
+    # a step of this arm = every worker process finishing one episode: `procs` episodes per step
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
-            "steps": nsteps, "warmup": args.warmup, "ms_per_step": 1e3 * total / nsteps,
+            "steps": (multi["steps_per_worker"] if procs > 1 else nsteps), "warmup": args.warmup,
+            "ms_per_step": 1e3 * procs / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args.gpus, args.workload),
-            "cpu_processes": 1,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
-                             "sample": ref.sample_text(),
-                             "multi_process": None if args.no_multi_process else cpu_multi_process_throughput()},
+            "cpu_processes": procs,
+            "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -807,9 +830,9 @@ def run_b200_arm(args):
         ref = CpuReference(name, episodes=1)
         ref.step()
         ts = [sum(ref.step()) for _ in range(4)]
-        cpu = {"value": ref.episodes / statistics.median(ts), "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
-               "sample": ref.sample_text() + f"; median of 4 steps, {statistics.median(ts):.3f} s/episode",
-               "multi_process": None if args.no_multi_process else cpu_multi_process_throughput()}
+        single = {"value": ref.episodes / statistics.median(ts), "unit": UNIT, "cores": ref.cores, "processes": 1,
+                  "sample": ref.sample_text() + f"; median of 4 steps, {statistics.median(ts):.3f} s/episode"}
+        cpu = cpu_baseline_dict(single, ref.kind, None if args.no_multi_process else cpu_multi_process_throughput())
 
     # ---- the other BASELINE configs and the NMS worst cases (N = 1: parity-test cases, reported beside the headline)
     extra = None

@@ -255,7 +255,10 @@ __global__ void __launch_bounds__(kThreads, 5) match_nhwc_kernel(Args A, FastDiv
 // ---------------------------------------------------------------------------------------------
 // Ring depth, measured on one box as (two-stream step / kernel alone): 5 slots 0.183 / 0.161 ms, 6: 0.181 / 0.145,
 // 7: 0.192 / 0.135, 8: 0.204 / 0.136 -- deeper queues make the kernel itself faster and its neighbours slower.
-constexpr int kBulkSlots = 6;                                  // x 16 KB ring
+#ifndef OSD_BULK_SLOTS
+#define OSD_BULK_SLOTS 7   // measured best for the three-stream step; -DOSD_BULK_SLOTS=n builds an A/B variant
+#endif
+constexpr int kBulkSlots = OSD_BULK_SLOTS;                     // x 16 KB ring
 constexpr int kBulkGroups = 2;
 constexpr int kBulkMinBlocks = 5;   // launch bound that caps the kernel at 40 registers/thread: the other stream's CTAs
                                     // need the register file

@@ -26,7 +26,10 @@ def test_reference_arm_prints_the_contract_line():
     assert "workload" in line["config"] and "model" not in line["config"]
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("reference", "port", "port+reference-nms") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
-    assert line["cpu_processes"] == 1
+    # value = all the host cores: one single-threaded worker process per core; the one-process figure sits beside it
+    assert line["cpu_processes"] == cb["cores"] == cb["multi_process"]["processes"] >= 1
+    assert cb["single_process"]["processes"] == 1 and cb["single_process"]["value"] > 0
+    assert abs(line["ms_per_step"] - 1e3 * line["cpu_processes"] / line["value"]) < 1e-6 * line["ms_per_step"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -179,3 +179,9 @@ def test_pooler_bf16_rows_feed_the_dense_head(golden_dir):
     l0, r0 = head(full, supp)
     l1, r1 = head(rows, supp)
     assert torch.equal(l0, l1) and torch.equal(r0, r1)
+    # padded ROI lists (roi_count): rows past an image's count are zeros in both layouts
+    cnt = torch.tensor([rois.size(1) - 5, rois.size(1)], dtype=torch.int32, device=DEV)[:b]
+    rows_c = pooler.forward_fixed(fx, rois, cnt, rows_bf16=True)
+    full_c = pooler.forward_fixed(fx, rois, cnt)
+    assert torch.equal(rows_c, full_c.reshape(b, rois.size(1), c, 49).permute(0, 1, 3, 2).bfloat16())
+    assert float(rows_c[0, rois.size(1) - 5:].float().abs().max()) == 0.0 and torch.equal(rows_c[1], rows[1])

@@ -5,7 +5,8 @@ Tolerances (north_star: 'bf16 1x1-conv mode within stated tolerance'):
   * against the oracle evaluated on bf16-ROUNDED operands (same products, fp32 accumulation, different summation
     order): conv1 |err| <= 2e-4 + 1e-3*|ref|  -- this is the check that catches layout / descriptor mistakes;
   * against the pure fp32 oracle: conv1 max|err| <= 2 % of max|ref| (bf16 has 8 mantissa bits, K = C terms);
-    full module (after two GroupNorms, outputs are O(1)): max|err| <= 0.08, mean|err| <= 0.01."""
+    full module (after two GroupNorms, outputs are O(1)): max|err| <= 0.04, mean|err| <= 0.0035 (2x the observed
+    0.019 / 0.0017); the executed-reference fixtures keep the looser 0.08 (tiny levels normalise over few values)."""
 import os
 
 import numpy as np
@@ -76,7 +77,9 @@ def test_full_module(b, s, c, h, w):
         assert g.shape == r.shape
         assert float((g - e).abs().max()) <= 5e-3, f"vs bf16-emulated oracle: {float((g - e).abs().max()):.3e}"
         d = (g - r).abs()
-        assert float(d.max()) <= 0.08 and float(d.mean()) <= 0.01, (float(d.max()), float(d.mean()))
+        # observed on B200 (tools/fusion_err.py): max 0.016-0.019, mean 0.0015-0.0017 on outputs of magnitude <= 4.6;
+        # the bounds are twice that
+        assert float(d.max()) <= 0.04 and float(d.mean()) <= 0.0035, (float(d.max()), float(d.mean()))
 
 
 def test_full_module_baseline_geometry():
