@@ -437,9 +437,17 @@ __global__ void __launch_bounds__(256) pack_roi_kernel(const float* __restrict__
   extern __shared__ __nv_bfloat16 pk_tile[];   // [49][C + 2]
   const int pitch = C + 2;
   const float* src = in + (size_t)blockIdx.x * C * kPix;
-  for (int i = threadIdx.x; i < C * kPix; i += blockDim.x) {
-    const int c = i / kPix, p = i - c * kPix;
-    pk_tile[p * pitch + c] = __float2bfloat16_rn(__ldg(src + i));
+  // C * 49 floats per ROI with C a multiple of 4: the ROI's block is 16-byte aligned whenever `in` is
+  const float4* src4 = reinterpret_cast<const float4*>(src);
+  for (int i4 = threadIdx.x; i4 < C * kPix / 4; i4 += blockDim.x) {
+    const float4 v = __ldg(src4 + i4);
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = 4 * i4 + k;
+      const int c = i / kPix, p = i - c * kPix;
+      pk_tile[p * pitch + c] = __float2bfloat16_rn(e[k]);
+    }
   }
   __syncthreads();
   __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(out + (size_t)blockIdx.x * C * kPix);
@@ -596,6 +604,8 @@ extern "C" int osd_box_head_forward(const osd_box_head_desc* d, void* workspace,
   OSD_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "osd_box_head_forward: workspace must be 256-byte aligned");
   OSD_REQUIRE((d->pooled || d->pooled_nhwc_bf16) && d->supp && d->class_logits && d->box_regression,
               "osd_box_head_forward: null input / output");
+  OSD_REQUIRE(d->pooled == nullptr || (reinterpret_cast<uintptr_t>(d->pooled) & 15) == 0, "osd_box_head_forward: pooled must be 16-byte aligned");
+  OSD_REQUIRE((reinterpret_cast<uintptr_t>(d->supp) & 15) == 0, "osd_box_head_forward: supp must be 16-byte aligned");
   OSD_REQUIRE(d->pooled_nhwc_bf16 == nullptr || (reinterpret_cast<uintptr_t>(d->pooled_nhwc_bf16) & 15) == 0,
               "osd_box_head_forward: pooled_nhwc_bf16 must be 16-byte aligned");
   OSD_REQUIRE(d->w1 && d->b1 && d->gn1_w && d->gn1_b && d->w2 && d->b2 && d->gn2_w && d->gn2_b && d->w3 && d->b3 && d->gn3_w &&

@@ -185,3 +185,24 @@ def test_pooler_bf16_rows_feed_the_dense_head(golden_dir):
     full_c = pooler.forward_fixed(fx, rois, cnt)
     assert torch.equal(rows_c, full_c.reshape(b, rois.size(1), c, 49).permute(0, 1, 3, 2).bfloat16())
     assert float(rows_c[0, rois.size(1) - 5:].float().abs().max()) == 0.0 and torch.equal(rows_c[1], rows[1])
+
+
+def test_dense_head_is_independent_of_chunking_and_roi_order():
+    """Size-independent properties at a size the CPU oracle does not reach (4 x 700 ROIs, C = 256, MLP 1024): every ROI's
+    result depends on that ROI and its episode's support only -- so the outputs are bit-identical whatever the chunk
+    size (which ROIs share a launch / a 128-row tile) and a permutation of the ROIs inside an episode permutes the
+    outputs."""
+    torch.manual_seed(11)
+    c, mlp, b, r = 256, 1024, 4, 700
+    mods = orc.make_box_head_modules(c, mlp)
+    pooled = torch.randn(b, r, c, 7, 7, device=DEV)
+    supp = torch.randn(b, 1, c, 7, 7, device=DEV)
+    ref_l, ref_r = gpu_head(mods, c, mlp)(pooled, supp)
+    for chunk in (2, 64, 1001):
+        l, rg = gpu_head(mods, c, mlp, roi_chunk=chunk)(pooled, supp)
+        assert torch.equal(l, ref_l) and torch.equal(rg, ref_r), chunk
+    perm = torch.randperm(r, device=DEV)
+    lp, rp = gpu_head(mods, c, mlp)(pooled[:, perm].contiguous(), supp)
+    assert torch.equal(lp.view(b, r, -1), ref_l.view(b, r, -1)[:, perm])
+    assert torch.equal(rp.view(b, r, -1), ref_r.view(b, r, -1)[:, perm])
+    assert bool(torch.isfinite(ref_l).all()) and float(ref_l.abs().max()) > 0
