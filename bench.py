@@ -501,19 +501,19 @@ def time_steps(step_fn, steps, torch):
     return ev[0].elapsed_time(ev[-1]) / steps, statistics.median(per)
 
 
-def run_extra_workload(name, dev, steps, rank, use_graph=True, depth=1):
+def run_extra_workload(name, dev, steps, rank, use_graph=True, depth=1, streamed=False):
     """One of the non-headline workloads on this GPU: overlapped/graph step time, isolated stage times, parity spot
     check against the CPU reference path on episode 0, and that path's time on the same inputs."""
     import torch
 
     wl = WORKLOADS[name]
-    pipe = make_pipe(name, dev, depth=depth)
+    pipe = make_pipe(name, dev, depth=2 if streamed else depth)
     fill_inputs(pipe, seed=3000 + 17 * rank + sum(map(ord, name)), heads=wl["heads"])
-    runner = StepRunner(pipe, depth, overlap=True, use_graph=use_graph)
+    runner = StreamRunner(pipe) if streamed else StepRunner(pipe, depth, overlap=True, use_graph=use_graph)
     launch = runner.launch
-    runner.run(2 * depth)
+    runner.run(4 if streamed else 2 * depth)
     torch.cuda.synchronize()
-    n = max(4, min(steps, 10)) // depth * depth
+    n = max(8, min(steps, 20)) if streamed else max(4, min(steps, 10)) // depth * depth
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
     runner.run(n)
@@ -844,7 +844,8 @@ def run_b200_arm(args):
             if wname == name:
                 continue
             try:
-                extra[wname] = run_extra_workload(wname, dev, steps, rank, use_graph=not args.no_graph, depth=depth)
+                extra[wname] = run_extra_workload(wname, dev, steps, rank, use_graph=not args.no_graph, depth=depth,
+                                                  streamed=streamed)
             except Exception as exc:  # noqa: BLE001  (report, do not lose the headline line)
                 extra[wname] = {"error": repr(exc)}
 
