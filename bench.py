@@ -559,6 +559,80 @@ def h2d_ceiling(pipe, host_in, steps, torch, dist, world, dev):
 
 
 # ------------------------------------------------------------------------------------------------------
+def run_second_stage(dev, steps):
+    """The second stage at the first stage's output size -- 16 episodes x 2000 proposals, C = 256, MLP 1024 (SURVEY section
+    8(f) row 2): multi-level ROI pooler (bf16 [roi, pixel, channel] rows) -> dense head on tcgen05 -> PostProcessor
+    kernel.  Per-stage times from CUDA events on the launching stream; the head's outputs of a few ROIs are checked
+    against the fp32 oracle (stated bf16 tolerance: 3 % of the output range)."""
+    import torch
+
+    import oneshotdet_b200 as osd
+    from oneshotdet_b200 import ops
+    from oracle import oracle as orc
+
+    b, r, c, mlp, h, w = 16, 2000, CHANNELS, 1024, 800, 1344
+    g = torch.Generator(device=dev).manual_seed(4242)
+    feats = [torch.empty((b, c, -(-h // s), -(-w // s)), device=dev).normal_(generator=g) for s in (8, 16, 32, 64, 128)]
+    ctr = torch.rand((b, r, 2), device=dev, generator=g) * torch.tensor([1333.0, 800.0], device=dev)
+    wh = torch.rand((b, r, 2), device=dev, generator=g) * 400.0 + 16.0
+    rois = torch.cat((ctr - wh / 2, ctr + wh / 2), 2).clamp_(min=0.0)
+    rois[..., 2].clamp_(max=1332.0)
+    rois[..., 3].clamp_(max=799.0)
+    rois = rois.contiguous()
+    supp = torch.empty((b, 1, c, 7, 7), device=dev).normal_(generator=g)
+    torch.manual_seed(77)
+    mods = orc.make_box_head_modules(c, mlp)
+    head = osd.BoxHeadDense(c, mlp)
+    head.load_state_dict({("predictor." + k if k.startswith(("cls_score", "bbox_pred")) else k): v
+                          for k, v in mods.state_dict().items()})
+    head = head.to(dev).eval()
+    pooler = osd.Pooler((7, 7), [1 / s for s in (8, 16, 32, 64, 128)], 2)
+    sizes = [(800, 1333)] * b
+
+    def step():
+        rows = pooler.forward_fixed(feats, rois, rows_bf16=True)
+        logits, reg = head(rows, supp)
+        return rows, logits, reg, ops.box_postprocess(logits, reg, rois, sizes, score_thresh=0.05, nms_thresh=0.5,
+                                                      detections_per_img=100)
+
+    for _ in range(2):
+        out = step()
+    torch.cuda.synchronize()
+    n = max(2, min(steps, 5))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    t_pool = t_head = t_post = 0.0
+    for _ in range(n):
+        ev[0].record()
+        rows = pooler.forward_fixed(feats, rois, rows_bf16=True)
+        ev[1].record()
+        logits, reg = head(rows, supp)
+        ev[2].record()
+        post = ops.box_postprocess(logits, reg, rois, sizes, score_thresh=0.05, nms_thresh=0.5, detections_per_img=100)
+        ev[3].record()
+        torch.cuda.synchronize()
+        t_pool += ev[0].elapsed_time(ev[1]) / n
+        t_head += ev[1].elapsed_time(ev[2]) / n
+        t_post += ev[2].elapsed_time(ev[3]) / n
+    # parity spot check of the dense head: 6 ROIs of episode 0 through the fp32 oracle on the fp32 pooled features
+    k = 6
+    pooled32 = pooler.forward_fixed(feats, rois)[0:1, :k].cpu()
+    ol, orr = orc.box_head_dense(pooled32, supp[0:1].cpu(), mods)
+    gl, gr = logits[:k].cpu(), reg[:k].cpu()
+    err_l = float((gl - ol).abs().max()) / max(float(ol.abs().max()), 1e-12)
+    err_r = float((gr - orr).abs().max()) / max(float(orr.abs().max()), 1e-12)
+    total = t_pool + t_head + t_post
+    flops = 2.0 * b * r * (49 * 4 * c * c + 49 * 2 * c * c + 49 * 9 * c * (c // 2) + 49 * (c // 2) * mlp + mlp * mlp + mlp * 10)
+    return {"workload": "second stage at the first stage's output size: 16 episodes x 2000 proposals, 800x1333, C=256, MLP 1024: "
+                        "ROI pooler (7x7, sampling 2, 5 levels) -> dense head (concat + compress_dim_conv + feature_aggreg + fc6/fc7 "
+                        "+ predictor, tcgen05) -> PostProcessor (softmax, decode, 0.05 / NMS 0.5 / 100)",
+            "episodes_per_gpu": b, "rois": b * r, "ms_per_step": total, "episodes_per_s": b / (total * 1e-3), "steps": n,
+            "stages": {"pooler_ms": t_pool, "dense_head_ms": t_head, "post_ms": t_post},
+            "dense_head_tflops_useful": flops / (t_head * 1e-3) / 1e12,
+            "detections_per_episode": post.count.cpu().tolist()[:4],
+            "parity": {"checker": "oracle (fp32) on the first 6 ROIs of episode 0", "logits_rel_err": err_l,
+                       "regression_rel_err": err_r, "tolerance": 0.03, "ok": bool(err_l <= 0.03 and err_r <= 0.03)}}
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -848,6 +922,11 @@ def run_b200_arm(args):
                                                   streamed=streamed)
             except Exception as exc:  # noqa: BLE001  (report, do not lose the headline line)
                 extra[wname] = {"error": repr(exc)}
+        try:
+            torch.cuda.empty_cache()
+            extra["second_stage"] = run_second_stage(dev, steps)
+        except Exception as exc:  # noqa: BLE001
+            extra["second_stage"] = {"error": repr(exc)}
 
     if rank == 0:
         gather_text = None

@@ -133,17 +133,22 @@ def test_matching_module_fusion_mode_loads_reference_state_dict():
         assert float((o.cpu() - r).abs().max()) <= 0.08
 
 
-@pytest.mark.parametrize("mode", ["single", "mc", "pair"])
+@pytest.mark.parametrize("mode", ["single", "mc", "pair", "gram"])
 def test_cluster_modes_in_subprocess(mode):
-    """The fused kernels' other launch forms (OSD_FUSION_MODE is read once per process): clusters of two CTAs with
-    multicast weight stages ('mc'), CTA pairs on cta_group::2 ('pair') and the plain one-CTA form must all pass the
-    full-module parity tests of this file."""
+    """The fused kernels' other launch forms (the switches are read once per process): clusters of eight CTAs with
+    multicast weight stages ('mc'), CTA pairs on cta_group::2 ('pair'), the plain one-CTA form, and pass A taking the
+    GroupNorm-1 statistics from a Gram GEMM ('gram', OSD_FUSION_GRAM=1) must all pass the full-module parity tests of
+    this file."""
     import subprocess
     import sys
 
     if os.environ.get("OSD_FUSION_SUBTEST"):
         pytest.skip("already inside the subprocess")
-    env = dict(os.environ, OSD_FUSION_MODE=mode, OSD_FUSION_SUBTEST="1")
+    env = dict(os.environ, OSD_FUSION_SUBTEST="1")
+    if mode == "gram":
+        env.update(OSD_FUSION_MODE="single", OSD_FUSION_GRAM="1")
+    else:
+        env.update(OSD_FUSION_MODE=mode)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
                         "full_module or reference_fixtures", "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=900,
