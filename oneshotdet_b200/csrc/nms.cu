@@ -17,6 +17,8 @@
 #include <climits>
 #include <cmath>
 
+#include <cstdlib>
+
 #include "osd_common.cuh"
 #include "osd_device_utils.cuh"
 
@@ -857,7 +859,10 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
       if (b1 < NPu) {
         bounds[npass++] = b1;
         // 2112 -> 4096 -> 8064 -> all for post_top_n = 2000; short lists grow by 4x; no pass within 25 % of the full list
-        for (int b = (b1 < 2048 ? 4 : 2) * (b1 - 64); npass < 5 && (int64_t)4 * b <= (int64_t)3 * NPu; b = (b < 2048 ? 4 : 2) * (b - 64))
+        // OSD_NMS_MAX_PASSES (diagnosis): cap on the number of passes, the last one always covers everything
+        static const int max_passes = [] { const char* e = getenv("OSD_NMS_MAX_PASSES"); return e ? atoi(e) : 6; }();
+        for (int b = (b1 < 2048 ? 4 : 2) * (b1 - 64); npass < 5 && npass + 1 < max_passes && (int64_t)4 * b <= (int64_t)3 * NPu;
+             b = (b < 2048 ? 4 : 2) * (b - 64))
           bounds[npass++] = b;
       }
     }
