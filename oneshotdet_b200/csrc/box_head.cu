@@ -48,9 +48,9 @@ constexpr uint32_t kRingBytes = 4 * (kABytes + 256 * kBK * 2);   // 192 KB of op
 constexpr int kMaxRing = 10;
 // ring depth for an N tile of BN columns: a stage is the A tile (16 KB) + BN rows of W (128 B each).  Narrow layers get a
 // deeper ring -- their stages are consumed faster (4 MMAs of BN/2 clocks each) while the TMA latency stays the same
-__host__ __device__ constexpr uint32_t stage_bytes(int bn) { return kABytes + (uint32_t)bn * 128u; }
-__host__ __device__ constexpr int ring_depth(int bn) {
-  return (int)(kRingBytes / stage_bytes(bn)) < kMaxRing ? (int)(kRingBytes / stage_bytes(bn)) : kMaxRing;
+__host__ __device__ constexpr uint32_t stage_bytes(int bn, int mt) { return (uint32_t)mt * kABytes + (uint32_t)bn * 128u; }
+__host__ __device__ constexpr int ring_depth(int bn, int mt) {
+  return (int)(kRingBytes / stage_bytes(bn, mt)) < kMaxRing ? (int)(kRingBytes / stage_bytes(bn, mt)) : kMaxRing;
 }
 constexpr int kMaxEpiWarps = 16;
 constexpr int kMaxParamCols = 2048;            // bias / gamma / beta of up to this many output columns are staged in smem
@@ -129,7 +129,9 @@ __device__ __forceinline__ void store_bf16_row(__nv_bfloat16* dst, const uint32_
 // CL = 2: launched as clusters of two CTAs that work on two M tiles of the SAME N tile in lock step; every W stage is
 // fetched from L2 once per cluster (each CTA loads half of its rows and the TMA unit multicasts them into both CTAs'
 // rings).  The ROI layers stream the whole weight matrix per M tile and are bound by that L2 -> SM stream.
-template <int EPI, int CPW, int GS, int NH, int CL>
+// MT = 2 (N tile <= 128): a CTA tile is TWO 128-row M tiles against one weight stage (two accumulators of 128 columns per
+// TMEM buffer) -- a 256 x 128 tile moves 28 % fewer operand bytes per FLOP than 128 x 128.
+template <int EPI, int CPW, int GS, int NH, int CL, int MT>
 __global__ void __launch_bounds__(32 * (4 * NH + 2), 1)
 roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                 const __grid_constant__ CUtensorMap mapW, const GemmArgs G) {
@@ -141,8 +143,10 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const int ncta = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int LD = CPW >= 32 ? 32 : 16;
   static_assert(BN <= 256 && BN % 16 == 0, "N tile");
-  constexpr int kRing = ring_depth(BN);
-  constexpr uint32_t kStage = stage_bytes(BN);
+  static_assert(MT == 1 || (MT == 2 && BN <= 128), "two M tiles per CTA tile need two accumulators per TMEM buffer");
+  constexpr int kRing = ring_depth(BN, MT);
+  constexpr uint32_t kStage = stage_bytes(BN, MT);
+  constexpr uint32_t kAStage = (uint32_t)MT * kABytes;
   static_assert(kStage % 1024 == 0 && kRing >= 2 && 8 * (2 * kRing + 4) + 4 <= 256, "ring layout");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -157,7 +161,7 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   float* sBeta = sGamma + 512;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int m_tiles = G.a_mode == A_PLAIN ? (G.M + kBM - 1) / kBM : (G.M + 1) / 2;
+  const int m_tiles = G.a_mode == A_PLAIN ? (G.M + kBM * MT - 1) / (kBM * MT) : (G.M + 2 * MT - 1) / (2 * MT);
   const int n_tiles = (G.N + BN - 1) / BN;
   // pairs: tile t of the loop = (pair of M tiles t / n_tiles, N tile t % n_tiles); rank r takes M tile 2 * pair + r (past
   // the last M tile: a dummy whose loads are out of range = zero-filled and whose rows are all invalid)
@@ -190,28 +194,33 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t c = 0;
-      const uint32_t a_bytes = G.a_mode == A_PLAIN ? kABytes : 2u * kPix * 128u;
+      const uint32_t a_bytes = (uint32_t)MT * (G.a_mode == A_PLAIN ? kABytes : 2u * kPix * 128u);
       for (int tile = cta; tile < total; tile += ncta) {
         const int mt = (tile / n_tiles) * CL + (int)crank, nt = tile % n_tiles;
         for (int k = 0; k < num_k; ++k, ++c) {
           const uint32_t s = c % kRing, ph = (c / kRing) & 1u;
           mbar_wait(b_empty + 8u * s, ph ^ 1u);
-          const uint32_t sA = base + s * kStage, sB = sA + kABytes, fb = b_full + 8u * s;
+          const uint32_t sA0 = base + s * kStage, sB = sA0 + kAStage, fb = b_full + 8u * s;
           mbar_expect_tx(fb, a_bytes + (uint32_t)BN * 128u);
           const int k0 = k * kBK;
-          if (G.a_mode == A_PLAIN) {
-            tma_load_2d(sA, &mapA, k0, mt * kBM, fb);
-          } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int roi = mt * 2 + j;              // past the last ROI: out of range -> zero-filled, bytes still counted
-              const uint32_t dst = sA + (uint32_t)j * (64u * 128u);
-              if (G.a_mode == A_ROI) {
-                if (k0 < G.k_split) tma_load_2d(dst, &mapA, k0, roi * kPix, fb);
-                else tma_load_2d(dst, &mapA2, k0 - G.k_split, ((G.roi0 + roi) / G.rois_per_image) * kPix, fb);
-              } else {
-                const int tap = k0 / G.tap_c, kc = k0 - tap * G.tap_c;
-                tma_load_4d(dst, &mapA, kc, tap % 3 - 1, tap / 3 - 1, roi, fb);
+          for (int mi = 0; mi < MT; ++mi) {
+            const uint32_t sA = sA0 + (uint32_t)mi * kABytes;
+            const int ms = mt * MT + mi;               // 128-row M tile
+            if (G.a_mode == A_PLAIN) {
+              tma_load_2d(sA, &mapA, k0, ms * kBM, fb);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int roi = ms * 2 + j;            // past the last ROI: out of range -> zero-filled, bytes still counted
+                const uint32_t dst = sA + (uint32_t)j * (64u * 128u);
+                if (G.a_mode == A_ROI) {
+                  if (k0 < G.k_split) tma_load_2d(dst, &mapA, k0, roi * kPix, fb);
+                  else tma_load_2d(dst, &mapA2, k0 - G.k_split, ((G.roi0 + roi) / G.rois_per_image) * kPix, fb);
+                } else {
+                  const int tap = k0 / G.tap_c, kc = k0 - tap * G.tap_c;
+                  tma_load_4d(dst, &mapA, kc, tap % 3 - 1, tap / 3 - 1, roi, fb);
+                }
               }
             }
           }
@@ -243,11 +252,14 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         mbar_wait(b_full + 8u * s, ph);
         tc_fence_after();
         if (elect_one_lane()) {
-          const uint64_t ad = make_smem_desc(base + s * kStage, 16u, 1024u);
-          const uint64_t bd = make_smem_desc(base + s * kStage + kABytes, 16u, 1024u);
+          const uint64_t bd = make_smem_desc(base + s * kStage + kAStage, 16u, 1024u);
 #pragma unroll
-          for (int k16 = 0; k16 < kBK / 16; ++k16)
-            umma_bf16(d, ad + (uint64_t)(k16 * 2), bd + (uint64_t)(k16 * 2), idesc, (k | k16) != 0 ? 1u : 0u);
+          for (int mi = 0; mi < MT; ++mi) {
+            const uint64_t ad = make_smem_desc(base + s * kStage + (uint32_t)mi * kABytes, 16u, 1024u);
+#pragma unroll
+            for (int k16 = 0; k16 < kBK / 16; ++k16)
+              umma_bf16(d + (uint32_t)mi * 128u, ad + (uint64_t)(k16 * 2), bd + (uint64_t)(k16 * 2), idesc, (k | k16) != 0 ? 1u : 0u);
+          }
           if (CL == 2) umma_commit_mc(b_empty + 8u * s, (uint16_t)3);
           else umma_commit(b_empty + 8u * s);
         }
@@ -279,15 +291,20 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const int mt = (tile / n_tiles) * CL + (int)crank, nt = tile % n_tiles;
       const uint32_t acc = it & 1u;
       const int col0 = nt * BN + hh * CPW;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(hh * CPW);
       mbar_wait(b_accf + 8u * acc, (it >> 1) & 1u);
       tc_fence_after();
+#pragma unroll 1
+      for (int mi = 0; mi < MT; ++mi) {
+      const int ms = mt * MT + mi;                       // this accumulator's 128-row M tile
+      const uint32_t par = (it * MT + (uint32_t)mi) & 1u; // parity of the exchange / coefficient buffers
+      const bool last_sub = mi == MT - 1;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)mi * 128u + (uint32_t)(hh * CPW);
       if constexpr (EPI == 1) {
         constexpr int NG = CPW / GS;
         static_assert(NG <= 16, "a warp keeps (sum, sum of squares) of at most 16 groups");
         const int row = q * 32 + lane, rl = row & 63;
         const int rloc = row >> 6;                       // which of the tile's two ROIs
-        const int roi = mt * 2 + rloc;
+        const int roi = ms * 2 + rloc;
         const bool valid = rl < kPix && roi < G.M;
         // ---- pass 1: (sum, sum of squares) of y = d + bias per group over this thread's row
         float acc_s[32];
@@ -319,8 +336,8 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
         transpose_reduce32(acc_s, lane);
         // rows of one ROI sit in two warps (q even: rows 0-31, q odd: rows 32-48): exchange through shared memory
-        float* mine = xch + ((it & 1u) * kEpiWarps + warp) * 32;
-        const float* theirs = xch + ((it & 1u) * kEpiWarps + (warp ^ 1)) * 32;
+        float* mine = xch + (par * kEpiWarps + warp) * 32;
+        const float* theirs = xch + (par * kEpiWarps + (warp ^ 1)) * 32;
         mine[lane] = acc_s[0];
         named_bar_sync(1 + (warp >> 1), 64);
         const float tot = acc_s[0] + theirs[lane];
@@ -332,7 +349,7 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const float rstd = 1.0f / sqrtf(var + G.eps);          // lanes 2g, 2g+1: statistics of group g
         // ---- coefficient table of this (ROI, column half): y_out = d * scale + shift, computed once per column by the
         //      64 threads of the warp pair instead of once per element by every row
-        float2* ctab = coef + (((it & 1u) * 2 + rloc) * NH + hh) * CPW;    // [parity][roi][part][CPW columns]
+        float2* ctab = coef + ((par * 2 + rloc) * NH + hh) * CPW;          // [parity][roi][part][CPW columns]
 #pragma unroll
         for (int u = 0; u < (CPW + 63) / 64; ++u) {
           const int cl = (q & 1) * 32 + lane + 64 * u;          // column inside this warp pair's half
@@ -354,7 +371,7 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           uint32_t r[32];
           tmem_ld_cols<LD>(taddr + (uint32_t)cb, r);
           tmem_ld_wait();
-          if (cb + LD >= CPW) {   // last read of this accumulator
+          if (cb + LD >= CPW && last_sub) {   // last read of this TMEM buffer
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(b_acce + 8u * acc);
@@ -373,14 +390,14 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           if (valid) store_bf16_row<LD / 2>(orow + cb, p);
         }
       } else {
-        const int row = mt * kBM + q * 32 + lane;
+        const int row = ms * kBM + q * 32 + lane;
         const bool valid = row < G.M;
 #pragma unroll
         for (int cb = 0; cb < CPW; cb += LD) {
           uint32_t r[32];
           tmem_ld_cols<LD>(taddr + (uint32_t)cb, r);
           tmem_ld_wait();
-          if (cb + LD >= CPW) {
+          if (cb + LD >= CPW && last_sub) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(b_acce + 8u * acc);
@@ -420,6 +437,7 @@ roi_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           }
         }
       }
+      }   // sub-tiles
     }
   }
 
@@ -484,12 +502,17 @@ bool head_pairs() {
   return on;
 }
 
-template <int EPI, int CPW, int GS, int NH>
+bool head_two_m_tiles() {
+  static const bool on = [] { const char* e = getenv("OSD_BOX_HEAD_MT"); return !(e && e[0] == '1'); }();
+  return on;
+}
+
+template <int EPI, int CPW, int GS, int NH, int MT = 1>
 int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mW, const GemmArgs& G, cudaStream_t stream,
                 const char* name, bool pairs) {
   constexpr int BN = NH * CPW;
   constexpr int kGemmThreads = 32 * (4 * NH + 2);
-  const int m_tiles = G.a_mode == A_PLAIN ? (G.M + kBM - 1) / kBM : (G.M + 1) / 2;
+  const int m_tiles = G.a_mode == A_PLAIN ? (G.M + kBM * MT - 1) / (kBM * MT) : (G.M + 2 * MT - 1) / (2 * MT);
   const int n_tiles = (G.N + BN - 1) / BN;
   if (m_tiles * n_tiles <= 0) return OSD_OK;
   cudaLaunchConfig_t cfg{};
@@ -503,7 +526,7 @@ int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (pairs) {
-    auto k = roi_gemm_kernel<EPI, CPW, GS, NH, 2>;
+    auto k = roi_gemm_kernel<EPI, CPW, GS, NH, 2, MT>;
     int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(k), kGemmSmem);
     if (rc != OSD_OK) return rc;
     const int total = ((m_tiles + 1) / 2) * n_tiles;
@@ -511,7 +534,7 @@ int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap
     cfg.gridDim = dim3((unsigned)(2 * std::min(total, kNumSMs / 2)));
     OSD_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mA2, mW, G));
   } else {
-    auto k = roi_gemm_kernel<EPI, CPW, GS, NH, 1>;
+    auto k = roi_gemm_kernel<EPI, CPW, GS, NH, 1, MT>;
     int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(k), kGemmSmem);
     if (rc != OSD_OK) return rc;
     attr[0].val.clusterDim.x = 1;
@@ -531,7 +554,10 @@ int launch_gn_gemm(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensor
     // operand stream, not by the epilogue's issue rate; section 8.1 of DESIGN.md)
     case 512: return launch_gemm<1, 128, 16, 2>(mA, mA2, mW, G, stream, name, pairs);
     case 256: return launch_gemm<1, 128, 8, 2>(mA, mA2, mW, G, stream, name, pairs);
-    case 128: return launch_gemm<1, 64, 4, 2>(mA, mA2, mW, G, stream, name, pairs);
+    case 128:
+      // 256 x 128 CTA tiles (two accumulators per TMEM buffer); OSD_BOX_HEAD_MT=1: 128 x 128
+      if (head_two_m_tiles()) return launch_gemm<1, 64, 4, 2, 2>(mA, mA2, mW, G, stream, name, pairs);
+      return launch_gemm<1, 64, 4, 2>(mA, mA2, mW, G, stream, name, pairs);
     case 64: return launch_gemm<1, 32, 2, 2>(mA, mA2, mW, G, stream, name, pairs);
     case 32: return launch_gemm<1, 16, 1, 2>(mA, mA2, mW, G, stream, name, pairs);
   }
