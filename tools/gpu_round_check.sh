@@ -26,3 +26,7 @@ ncu --set full --clock-control none --import-source on -k regex:'fusion_stats1|f
 ncu -i $O/fusion_$TAG.ncu-rep --page raw --csv > $O/fusion_${TAG}_raw.csv 2>/dev/null
 rm -f $O/*.ncu-rep
 cut -c1-300 $O/bench_$TAG.json
+# the dense head's GEMM launches of one chunk
+ncu --set full --clock-control none --import-source on -k regex:'roi_gemm' --launch-skip 12 -c 6 -o $O/head_$TAG python tools/box_head_time.py --batch 2 --rois 1184 --steps 1 > $O/ncu_head.log 2>&1
+ncu -i $O/head_$TAG.ncu-rep --page raw --csv > $O/head_${TAG}_raw.csv 2>/dev/null
+rm -f $O/*.ncu-rep
