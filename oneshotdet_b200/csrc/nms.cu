@@ -358,6 +358,8 @@ struct MaskArgs {
   int col_begin, col_end;  // columns this launch covers, multiples of 64
   int tiles_r, tiles_c;    // tile grid per episode
   int pass;                // which tile counter to use
+  int compact_rows;        // rows [0, compact_rows) (a multiple of the tile height) have FINAL kept bits from earlier passes:
+                           // only kept boxes can suppress, so their row tiles walk W.klist instead of every row
   IouTest test;
 };
 
@@ -387,6 +389,16 @@ __global__ void __launch_bounds__(kMaskRows) nms_mask_kernel(NmsWorkspace W, Mas
     const int col_end = min(n, A.col_end);
     if (row0 >= row_end || col0 >= col_end) continue;
     if (col0 + kMaskCols <= row0) continue;  // every column precedes every row of this tile
+    // compacted row tile: its 128 threads take the rbi-th group of 128 KEPT rows (the list is ascending, so the entries
+    // below compact_rows are a prefix of it); a group past them has nothing to do
+    const bool compact = row0 < A.compact_rows;
+    const int32_t* kl = W.klist + (size_t)e * W.NP;
+    int kc = 0;
+    if (compact) {
+      kc = W.kcount[e];
+      const int k0 = rbi * kMaskRows;
+      if (k0 >= kc || kl[k0] >= A.compact_rows) continue;
+    }
     const float4* sbox = W.sbox + (size_t)e * W.NP;
     const float* sarea = W.sarea + (size_t)e * W.NP;
     const int ncols = min(kMaskCols, col_end - col0);
@@ -397,7 +409,12 @@ __global__ void __launch_bounds__(kMaskRows) nms_mask_kernel(NmsWorkspace W, Mas
       carea[c] = sarea[cc];
     }
     __syncthreads();
-    const int i = row0 + threadIdx.x;
+    int i = row0 + threadIdx.x;
+    if (compact) {
+      const int k = rbi * kMaskRows + (int)threadIdx.x;
+      i = k < kc ? kl[k] : INT_MAX;
+      if (i >= A.compact_rows) continue;
+    }
     if (i >= row_end) continue;
     const float4 rb = sbox[i];
     const float ra = sarea[i];
@@ -743,6 +760,22 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(CandLayout L, 
     __syncthreads();  // kw[] complete; the ring is free to be reused as emit scratch
     emit_episode(L, W, O, A.post_top_n, e, count, kw, kw + W.NW, reinterpret_cast<int*>(kw + 2 * W.NW), warp_tot);
   }
+  if (!finished && !A.passthrough) {
+    // the kept rows so far as a compact ascending list for the next pass's mask tiles (kw[] holds blocks [0, blk_next))
+    __syncthreads();
+    int* prefix = reinterpret_cast<int*>(kw + W.NW);   // the ring is idle now
+    prefix_popc(kw, prefix, blk_next, warp_tot);
+    int32_t* kl = W.klist + (size_t)e * W.NP;
+    for (int w = tid; w < blk_next; w += kSweepThreads) {
+      u64 m = kw[w];
+      int p = prefix[w];
+      while (m) {
+        const int b = __ffsll((long long)m) - 1;
+        m &= m - 1ull;
+        kl[p++] = 64 * w + b;
+      }
+    }
+  }
   if (tid == 0) {
     W.kcount[e] = count;
     if (finished) {
@@ -780,6 +813,7 @@ size_t nms_workspace_carve(Carver& c, int64_t E, int64_t max_len, NmsWorkspace* 
   w.ecount = c.take<int32_t>(E);
   w.ecap = kEdgeCap;
   w.mask = c.take<unsigned long long>(E * NP * NW);
+  w.klist = c.take<int32_t>(E * NP);
   if (ws) *ws = w;
   return c.total();
 }
@@ -878,6 +912,9 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
       M.tiles_r = (int)ceil_div(hi, kMaskRows);
       M.tiles_c = (int)ceil_div(hi - prev, kMaskCols);
       M.pass = p;
+      // OSD_NMS_COMPACT=0 (diagnosis): every row of the earlier passes again, kept or not
+      static const bool compact_on = [] { const char* e = getenv("OSD_NMS_COMPACT"); return !(e && e[0] == '0'); }();
+      M.compact_rows = (p > 0 && compact_on) ? (prev / kMaskRows) * kMaskRows : 0;
       const int64_t tiles = (int64_t)E * M.tiles_r * M.tiles_c;
       OSD_REQUIRE(tiles < (1ll << 31), "nms: too many mask tiles");
       const int grid = (int)std::min<int64_t>(tiles, (int64_t)kNumSMs * 12);

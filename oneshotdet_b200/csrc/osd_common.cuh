@@ -117,6 +117,8 @@ struct NmsWorkspace {
   unsigned long long* edges;    // [E, kEdgeCap] suppression edges (i << 32 | j): box j (earlier) overlaps box i enough to suppress it
   int32_t* ecount;              // [E] edges found so far (may exceed the capacity: then the bitmask sweep is used)
   int32_t ecap;
+  int32_t* klist;               // [E, NP] visiting positions of the boxes kept so far (ascending), written by a sweep pass that
+                                //          leaves its episode unfinished: the next pass's mask tiles walk these rows only
 };
 
 size_t nms_workspace_carve(Carver& c, int64_t E, int64_t max_len, NmsWorkspace* ws);

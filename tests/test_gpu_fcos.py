@@ -148,6 +148,33 @@ def test_early_exit_miss_falls_through_to_second_pass():
     check_against_oracle(cls, reg, ctr, sizes, p, early_exit=True)
 
 
+@pytest.mark.parametrize("width", [12.0, 7.0])
+def test_early_exit_passes_at_full_geometry_with_clustered_boxes(width):
+    """BASELINE geometry with one box shape per level (2 x width strides wide): neighbouring locations suppress each other
+    at IoU 0.8, the first pass (2112 rows) cannot reach post_top_n + 1 survivors and the later passes run -- with the
+    kept-row compaction of their mask tiles.  The result must equal the single full pass (early_exit=False) bit for
+    bit, and the oracle's keep list on the same candidates.  Stale workspace contents must not matter: the passes are
+    run twice on different inputs through one FCOSPostProcessor (one workspace)."""
+    sizes = [(800, 1333)] * 2
+    post_e = make_post(orc.TWO_STAGE, early_exit=True)
+    post_f = make_post(orc.TWO_STAGE, early_exit=False)
+    for seed in (2100, 2101):
+        cls, reg, ctr = orc.synth_head_outputs(2, 800, 1344, seed=seed)
+        reg = [r * 0 + float(width * s) for r, s in zip(reg, orc.FPN_STRIDES)]
+        a = post_e.forward_fixed(to_dev(cls), to_dev(reg), to_dev(ctr), sizes)
+        b = post_f.forward_fixed(to_dev(cls), to_dev(reg), to_dev(ctr), sizes)
+        torch.cuda.synchronize()
+        assert torch.equal(a.count, b.count)
+        for e, n in enumerate(a.count.tolist()):
+            assert torch.equal(a.index[e, :n], b.index[e, :n]) and torch.equal(a.boxes[e, :n], b.boxes[e, :n])
+            assert torch.equal(a.scores[e, :n], b.scores[e, :n])
+        # the exit must really have been missed in pass 1 for this test to mean anything
+        kept = a.kept_before_cut().cpu().numpy()
+        full = b.kept_before_cut().cpu().numpy()
+        assert np.all(full < 0.9 * 11600), full
+    check_against_oracle(cls, reg, ctr, sizes, orc.TWO_STAGE, early_exit=True)
+
+
 def test_stress_params_config5():
     """BASELINE config 5: thresh 0.01, 1000 per level, NMS 0.6, 20 episodes sharing one image size."""
     cls, reg, ctr = orc.synth_head_outputs(4, 800, 1344, seed=5000)
