@@ -885,18 +885,26 @@ int nms_run(const CandLayout& L, const NmsWorkspace& W, const NmsParams& P, cons
     int npass = 0;
     if (early) {
       // enough boxes to keep post_top_n + 1 when at most ~5 % of the best-scored boxes are suppressed, then prefixes
-      // that double (the first of them still inside the sweep's "small pass" limit of 4096 boxes): when the best-scored
-      // boxes suppress each other heavily (a trained detector's clusters around objects) the exit is reached after a
-      // fraction of the 67 M pairs of the full problem instead of after all of them.  A pass whose episodes have all
+      // that grow by 1.5x (2112 -> 3200 -> 4800 -> 7200 -> all for post_top_n = 2000): when the best-scored boxes
+      // suppress each other heavily (a trained detector's clusters around objects) the exit is reached after a fraction
+      // of the 67 M pairs of the full problem instead of after all of them, and the rows of the earlier passes enter the
+      // later ones through the compact list of their kept boxes only.  Measured on the clustered bench workload
+      // (post-processing chain alone): growth 2.0 0.63 ms, 1.5 0.45 ms, 1.3 0.55 ms.  A pass whose episodes have all
       // finished returns at once (W.sched[0]).
       const int b1 = (int)align_up((size_t)P.post_top_n + 1, 64) + 64;
       if (b1 < NPu) {
         bounds[npass++] = b1;
-        // 2112 -> 4096 -> 8064 -> all for post_top_n = 2000; short lists grow by 4x; no pass within 25 % of the full list
+        // short lists grow by 4x; no pass within 25 % of the full list
         // OSD_NMS_MAX_PASSES (diagnosis): cap on the number of passes, the last one always covers everything
-        static const int max_passes = [] { const char* e = getenv("OSD_NMS_MAX_PASSES"); return e ? atoi(e) : 6; }();
-        for (int b = (b1 < 2048 ? 4 : 2) * (b1 - 64); npass < 5 && npass + 1 < max_passes && (int64_t)4 * b <= (int64_t)3 * NPu;
-             b = (b < 2048 ? 4 : 2) * (b - 64))
+        static const int max_passes = [] { const char* e = getenv("OSD_NMS_MAX_PASSES"); return e ? atoi(e) : 7; }();
+        // OSD_NMS_GROWTH (percent, diagnosis): growth of the prefix from pass to pass for lists of 2048+ rows
+        static const int growth = [] { const char* e = getenv("OSD_NMS_GROWTH"); const int g = e ? atoi(e) : 150; return g < 110 ? 110 : g; }();
+        auto next = [&](int b) {
+          if (b < 2048) return 4 * (b - 64);
+          if (growth == 200) return 2 * (b - 64);
+          return (int)align_up((size_t)((int64_t)b * growth / 100), 128);
+        };
+        for (int b = next(b1); npass < 6 && npass + 1 < max_passes && (int64_t)4 * b <= (int64_t)3 * NPu; b = next(b))
           bounds[npass++] = b;
       }
     }
