@@ -14,7 +14,7 @@
 //
 // One persistent, warp-specialised GEMM kernel serves all six layers:
 //   D[rows, N] = A[rows, K] . W[N, K]^T     bf16 x bf16 -> fp32 in tensor memory
-//   * A and W tiles come through TMA (128-byte swizzle, K-major) into a 4-stage ring; the A tile of the ROI layers is
+//   * A and W tiles come through TMA (128-byte swizzle, K-major) into a 4-9-stage ring; the A tile of the ROI layers is
 //     two boxes of 49 rows.  conv1's concat is never materialised: the K range [0, C) is read from the ROI's rows and
 //     [C, 2C) from the support rows of the ROI's episode (a second tensor map).  The 3x3 convolution is an implicit
 //     GEMM: its A tile for tap (dy, dx) is a box of the 4-D map [roi, y, x, c] at offset (dy-1, dx-1) -- the TMA unit
@@ -23,8 +23,12 @@
 //     8 epilogue warps (TMEM lane quadrant x column half) drain the other one: bias, GroupNorm statistics over the
 //     ROI's 49 rows (registers -> warp transpose-reduce -> one shared-memory exchange between the two warps that share
 //     an ROI), normalise + LeakyReLU on a second read of tensor memory, bf16 rows straight to global memory.
-//   * activations between layers are bf16 [roi, pixel, channel]; the host walks the ROIs in chunks sized so that a
-//     chunk's intermediates stay in the 126 MB L2 between consecutive layers.
+//   * the ROI layers are bound by the L2 -> SM operand stream (every tile streams the layer's whole weight matrix): the
+//     layers with N <= 128 therefore run 256 x 128 CTA tiles (two M tiles against one weight stage, two accumulators per
+//     TMEM buffer); fc6 (K = 6272) runs at the tensor pipe's peak.
+//   * activations between layers are bf16 [roi, pixel, channel]; the host walks the ROIs in chunks (1184 = 4 full waves of
+//     two-ROI tiles) so that a chunk's intermediates stay in the 126 MB L2 between consecutive layers; the fully
+//     connected layers run once over all ROIs.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
