@@ -85,9 +85,9 @@ class StreamRunner:
     the post-processing chains of consecutive batches alternating between two more; no join between steps.
     ``before(1)`` / ``after([res])`` are called in the stream context of the step's chain."""
 
-    def __init__(self, pipe):
+    def __init__(self, pipe, after_post=None):
         self.pipe, self.depth, self.launch = pipe, 1, "cuda-graphs (1 matching + 1 chain per step) on 3 streams"
-        self.steps = pipe.capture_streams()
+        self.steps = pipe.capture_streams(after_post)
 
     def run(self, k, before=None, after=None, mark=None):
         import torch
@@ -660,7 +660,7 @@ def run_b200_arm(args):
     wl = WORKLOADS[name]
     batch = wl["batch"]
 
-    block_mode = args.gather in ("peer", "peer-kernel", "block")
+    block_mode = args.gather in ("peer", "peer-kernel", "peer-graph", "block")
     overlap = not args.serial
     # steps in flight: the post-processing chains of `depth` consecutive steps run side by side under `depth` matching
     # launches (one chain alone takes longer than one matching launch).  The NCCL block gather has two slots: depth 1.
@@ -672,8 +672,7 @@ def run_b200_arm(args):
     pipe = make_pipe(name, dev, double_buffer=(world > 1 and block_mode), depth=2 if streamed else depth)
     fill_inputs(pipe, seed=2000 + rank, heads=wl["heads"])
     ep_off = rank * batch
-    runner = StreamRunner(pipe) if streamed else StepRunner(pipe, depth, overlap=overlap, use_graph=not args.no_graph)
-    launch = runner.launch
+    runner = None if streamed else StepRunner(pipe, depth, overlap=overlap, use_graph=not args.no_graph)
 
     # N > 1: the step's detections go to every rank.  "peer" (default): the result block of a step (one contiguous
     # buffer of a double-buffered pipeline) is pushed into every rank's receive buffer through CUDA-IPC-mapped peer
@@ -683,14 +682,34 @@ def run_b200_arm(args):
     gatherer = None
     K = pipe.post.plan.out_capacity
     if world > 1 and args.gather != "none":
-        if args.gather in ("peer", "peer-kernel"):
-            gatherer = PeerBlockGatherer(batch, K, dev, slots=len(pipe.posts), mode="copy" if args.gather == "peer" else "kernel")
+        if args.gather in ("peer", "peer-kernel", "peer-graph"):
+            gatherer = PeerBlockGatherer(batch, K, dev, slots=len(pipe.posts), mode="kernel" if args.gather == "peer-kernel" else "copy")
         elif args.gather == "block":
             gatherer = BlockGatherer(batch, K, dev)
         else:
             gatherer = DetectionGatherer(batch, K, dev, ep_off, steps_per_gather=args.gather_every)
 
+    # --gather peer-graph: the push of a step's block is recorded at the end of that step's chain graph (no per-step host
+    # work for the exchange at any N).  Measured at N = 2: 213.6 k episodes/s against 218.4 k for the default, which issues
+    # the copies from the host on a side stream -- inside the graph they sit on the chain's own stream and delay the next
+    # chain of that stream.
+    in_graph = streamed and gatherer is not None and args.gather == "peer-graph"
+    if streamed:
+        hook = (lambda k, r: gatherer.push_on_current_stream(k, r.block)) if in_graph else None
+        try:
+            runner = StreamRunner(pipe, hook)
+        except Exception as exc:  # noqa: BLE001  (capture of the peer copies refused: fall back to per-step submits)
+            if not in_graph:
+                raise
+            print(f"[bench] capturing the peer pushes failed ({exc}); submitting them per step", file=sys.stderr)
+            torch.cuda.synchronize()
+            in_graph = False
+            runner = StreamRunner(pipe)
+    launch = runner.launch
+
     def before(n):
+        if in_graph:
+            return
         # the exchanges that still read the blocks these steps overwrite have finished.  Full-depth replays cycle through
         # the 2 x depth output sets in submission order (the previous replay's pushes may stay in flight); a remainder
         # step uses the one-step graphs' own rotation, so it waits for everything.
@@ -701,6 +720,9 @@ def run_b200_arm(args):
                 gatherer.acquire(n, in_flight=(depth if n == depth else 0))
 
     def after(results):
+        if in_graph:
+            gatherer.i += len(results)     # bookkeeping only: the pushes are part of the chains' graphs
+            return
         if gatherer is not None:       # asynchronous: step i crosses NVLink while step i+1 computes
             for r in results:
                 if block_mode:
@@ -796,7 +818,9 @@ def run_b200_arm(args):
         ok_local = bool(torch.equal(got[rank], res.block))
         flag = torch.tensor([int(ok_nccl and ok_local)], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        exchange = {"mode": args.gather, "block_bytes": gatherer.block_bytes, "ranks": world,
+        exchange = {"mode": args.gather, "issued": ("inside the CUDA graph of each step's post-processing chain" if in_graph
+                                                    else "per step from the host"),
+                    "block_bytes": gatherer.block_bytes, "ranks": world,
                     "equals_nccl_all_gather": ok_nccl, "own_block_round_trip": ok_local, "all_ranks_ok": bool(flag.item())}
 
     # ---- roofline of the dominant streaming kernel (match_product_bulk_kernel: one launch per step)
@@ -935,7 +959,11 @@ def run_b200_arm(args):
         if world > 1:
             gather_text = {"none": "none (DIAGNOSIS RUN: not a multi-GPU measurement)",
                            "peer": "result block pushed to every rank's receive buffer over peer memory (copy engines), "
-                                   "every step, asynchronous; one final NCCL all-gather",
+                                   "every step, asynchronous (issued from the host on a side stream behind events); one "
+                                   "final NCCL all-gather",
+                           "peer-graph": "result block pushed to every rank's receive buffer over peer memory (copy "
+                                         "engines), every step, the copies recorded in the CUDA graph of the step's "
+                                         "post-processing chain; one final NCCL all-gather",
                            "peer-kernel": "result block pushed to every rank by one store kernel over peer memory, every "
                                           "step, asynchronous; one final NCCL all-gather",
                            "block": "result block, NCCL all-gather every step, asynchronous",
@@ -978,7 +1006,7 @@ def main():
                          "(two chains in flight); graph: one CUDA graph per step (match || chain), steps serialised")
     ap.add_argument("--depth", type=int, default=1,
                     help="consecutive steps issued per graph replay, their post-processing chains side by side (1: one step)")
-    ap.add_argument("--gather", choices=["peer", "peer-kernel", "block", "packed", "none"], default="peer",
+    ap.add_argument("--gather", choices=["peer", "peer-kernel", "peer-graph", "block", "packed", "none"], default="peer",
                     help="N>1: how a step's detections reach every rank (see run_b200_arm); 'none' is a diagnosis run")
     ap.add_argument("--gather-every", type=int, default=10,
                     help="N>1, --gather packed: steps per NCCL all-gather of the detections (1 = every step)")

@@ -5,6 +5,8 @@ ByteTensor -> two all_gathers -> unpickle (maskrcnn_benchmark/utils/comm.py:48-8
 engine/inference.py:133-152)."""
 from __future__ import annotations
 
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -254,6 +256,26 @@ class PeerBlockGatherer:
         self._events.append(ev)
         if len(self._events) > 4 * self.slots:      # acquire() is not being called: do not grow without bound
             self._events.pop(0)
+        return slot
+
+    def push_on_current_stream(self, slot: int, block):
+        """The same push as ``submit`` -- the block into row ``rank`` of receive slot ``slot`` of every rank -- issued on
+        the CURRENT stream with no events and no bookkeeping.  Made for stream capture: recorded at the end of the CUDA
+        graph of a post-processing chain (``EpisodePipeline.capture_streams(after_post=...)``) the exchange costs the host
+        nothing per step, whatever the number of ranks (submit() issues world copies + two events from Python every step).
+        The caller's stream order is the only ordering: a slot is rewritten by the stream that wrote it last."""
+        from . import _lib
+
+        if block.numel() != self.block_bytes:
+            raise ValueError(f"result block of {block.numel()} bytes, expected {self.block_bytes}")
+        if not 0 <= slot < self.slots:
+            raise ValueError(f"slot {slot} out of range (0..{self.slots - 1})")
+        ptrs = (ctypes.c_void_p * self.world)(*[self._peer[r] + (slot * self.world + self.rank) * self.block_bytes
+                                               for r in range(self.world)])
+        fn = self.lib.osd_comm_push if self.mode == "copy" else self.lib.osd_comm_push_kernel
+        with torch.cuda.device(self.device):
+            _lib.check(fn(ptrs, self.world, block.data_ptr(), self.block_bytes,
+                          torch.cuda.current_stream(self.device).cuda_stream), "osd_comm_push")
         return slot
 
     def drain(self):

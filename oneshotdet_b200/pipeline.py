@@ -160,10 +160,12 @@ class EpisodePipeline:
 
         return replay
 
-    def capture_streams(self):
+    def capture_streams(self, after_post=None):
         """Continuous software pipelining instead of one graph per step: returns a ``StreamedSteps`` (needs
-        ``pipeline_depth >= 2``)."""
-        return StreamedSteps(self)
+        ``pipeline_depth >= 2``).  ``after_post(k, result)`` is called INSIDE the capture of output set k's chain, right
+        after its post-processing launches: what it enqueues on the current stream (e.g. the multi-GPU push of the
+        result block, ``PeerBlockGatherer.push_on_current_stream``) becomes part of that chain's CUDA graph."""
+        return StreamedSteps(self, after_post)
 
     def input_tensors(self):
         return self.features + self.supp + self.cls + self.reg + self.ctr
@@ -219,7 +221,7 @@ class StreamedSteps:
 
     Output sets rotate (``len(pipe.posts)``, a multiple of 2): a set is rewritten only by the stream that wrote it."""
 
-    def __init__(self, pipe: "EpisodePipeline"):
+    def __init__(self, pipe: "EpisodePipeline", after_post=None):
         if pipe.depth < 2 or len(pipe.posts) % 2 != 0:
             raise ValueError("StreamedSteps needs an EpisodePipeline(pipeline_depth=2): two chains with their own workspaces")
         self.pipe = pipe
@@ -239,10 +241,12 @@ class StreamedSteps:
         with torch.cuda.graph(self.g_match, stream=side):
             pipe.match()
         self.g_post, self.results = [], []
-        for post in pipe.posts:
+        for k, post in enumerate(pipe.posts):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side):
                 res = post()
+                if after_post is not None:
+                    after_post(k, res)
             self.g_post.append(g)
             self.results.append(res)
         self.i = 0
