@@ -259,7 +259,10 @@ __global__ void __launch_bounds__(kThreads, 5) match_nhwc_kernel(Args A, FastDiv
 #define OSD_BULK_SLOTS 7   // measured best for the three-stream step; -DOSD_BULK_SLOTS=n builds an A/B variant
 #endif
 constexpr int kBulkSlots = OSD_BULK_SLOTS;                     // x 16 KB ring
-constexpr int kBulkGroups = 2;
+#ifndef OSD_BULK_GROUPS
+#define OSD_BULK_GROUPS 2
+#endif
+constexpr int kBulkGroups = OSD_BULK_GROUPS;
 constexpr int kBulkMinBlocks = 5;   // launch bound that caps the kernel at 40 registers/thread: the other stream's CTAs
                                     // need the register file
 constexpr unsigned kBulkBackoffNs = 200;
