@@ -669,7 +669,7 @@ def run_b200_arm(args):
     streamed = args.pipeline == "streams" and not args.serial and not args.no_graph and not (world > 1 and args.gather == "packed")
     if streamed:
         depth = 1
-    pipe = make_pipe(name, dev, double_buffer=(world > 1 and block_mode), depth=2 if streamed else depth)
+    pipe = make_pipe(name, dev, double_buffer=(world > 1 and block_mode), depth=max(2, args.chains) if streamed else depth)
     fill_inputs(pipe, seed=2000 + rank, heads=wl["heads"])
     ep_off = rank * batch
     runner = None if streamed else StepRunner(pipe, depth, overlap=overlap, use_graph=not args.no_graph)
@@ -1004,6 +1004,8 @@ def main():
     ap.add_argument("--pipeline", choices=["streams", "graph"], default="streams",
                     help="streams: matching and the post-processing chains of consecutive steps on three self-ordered streams "
                          "(two chains in flight); graph: one CUDA graph per step (match || chain), steps serialised")
+    ap.add_argument("--chains", type=int, default=2,
+                    help="--pipeline streams: post-processing chains in flight (streams they alternate between)")
     ap.add_argument("--depth", type=int, default=1,
                     help="consecutive steps issued per graph replay, their post-processing chains side by side (1: one step)")
     ap.add_argument("--gather", choices=["peer", "peer-kernel", "peer-graph", "block", "packed", "none"], default="peer",

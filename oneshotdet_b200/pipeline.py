@@ -222,13 +222,14 @@ class StreamedSteps:
     Output sets rotate (``len(pipe.posts)``, a multiple of 2): a set is rewritten only by the stream that wrote it."""
 
     def __init__(self, pipe: "EpisodePipeline", after_post=None):
-        if pipe.depth < 2 or len(pipe.posts) % 2 != 0:
-            raise ValueError("StreamedSteps needs an EpisodePipeline(pipeline_depth=2): two chains with their own workspaces")
+        if pipe.depth < 2 or len(pipe.posts) % pipe.depth != 0:
+            raise ValueError("StreamedSteps needs an EpisodePipeline(pipeline_depth>=2): chains with their own workspaces")
         self.pipe = pipe
+        self.chains = pipe.depth                      # chains in flight = streams they alternate between
         dev = pipe.device
         lo, hi = torch.cuda.Stream.priority_range()
         self.s_match = torch.cuda.Stream(dev, priority=lo)
-        self.s_post = [torch.cuda.Stream(dev, priority=hi) for _ in range(2)]
+        self.s_post = [torch.cuda.Stream(dev, priority=hi) for _ in range(self.chains)]
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):       # warm-up outside capture (kernel attributes, lazy allocations)
@@ -258,11 +259,11 @@ class StreamedSteps:
 
     def next_stream(self):
         """The stream the NEXT step's chain runs on (where an exchange of its result has to be ordered)."""
-        return self.s_post[self.i & 1]
+        return self.s_post[self.i % self.chains]
 
     def step(self):
         k = self.i % len(self.g_post)
-        s = self.s_post[self.i & 1]
+        s = self.s_post[self.i % self.chains]
         with torch.cuda.stream(self.s_match):
             self.g_match.replay()
         with torch.cuda.stream(s):
